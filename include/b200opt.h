@@ -1,0 +1,194 @@
+/*
+ * b200opt.h - C ABI of the B200-native Optimistix hot path.
+ *
+ * The reference (patrick-kidger/optimistix 0.1.0) is pure Python traced into one XLA program and has
+ * NO plugin/FFI interface of its own.  The seam this library sits behind is
+ * the body of the jit'd entry points, i.e. what `jax.vmap(optx.least_squares)(...)` lowers to:
+ *
+ *   b200opt_least_squares  replaces  optimistix/_least_squares.py:44-135  -> _iterate.py:194-268 driving
+ *                                    _solver/levenberg_marquardt.py:256-294 / _solver/gauss_newton.py:361-395
+ *   b200opt_root_find      replaces  optimistix/_root_find.py:119-241 (and _fixed_point.py:50-129 through
+ *                                    `fn(y) - y`)  -> _solver/newton_chord.py:59-251
+ *   b200opt_minimise       replaces  optimistix/_minimise.py:37-119  -> _solver/quasi_newton.py:418-458 (BFGS)
+ *   b200opt_lsq_step       replaces  one AbstractGaussNewton.step (gauss_newton.py:243-334) for an arbitrary
+ *                                    user `fn`: the caller (XLA / torch) evaluates r and J, the kernel does
+ *                                    search + accept/reject + termination + damped solve
+ *   b200opt_gn_gram        replaces  the `lx.linear_solve(J, r)` of NewtonDescent (gauss_newton.py:64-78) for
+ *                                    the single large row-sharded problem: per-shard J^T J, J^T r, r^T r
+ *
+ * Conventions
+ *   - every pointer in the non-`_host` entry points is a DEVICE pointer; the call only enqueues work on
+ *     `stream` (a cudaStream_t) and never synchronises, so it can be called from an XLA FFI handler.
+ *   - the `_host` entry points take HOST pointers, copy in/out themselves (chunked, double-buffered over
+ *     two streams) and return when the results are in the output buffers.
+ *   - the caller owns every buffer; the library keeps no global mutable state and allocates nothing
+ *     persistent (the `_host` variants allocate and free their staging buffers per call).
+ *   - return value: 0 on success, a negative B200OPT_E* code otherwise; b200opt_last_error() gives the
+ *     message for the calling thread.  Per-problem outcomes go to `result[]` using the member names of
+ *     optimistix.RESULTS (optimistix/_solution.py:11-20; compare by NAME, b200opt_result_name()).
+ *   - batched arrays are row-major with the problem index leading: y0[batch][n], per-problem args
+ *     [batch][problem_args_stride].
+ */
+#ifndef B200OPT_H_
+#define B200OPT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200OPT_VERSION 100 /* 0.1.0, tracks the reference version restated */
+
+/* error codes (return values) */
+#define B200OPT_OK 0
+#define B200OPT_EINVAL (-1)   /* bad argument (unknown model/dtype/solver, n or m not supported by the model) */
+#define B200OPT_ECUDA (-2)    /* CUDA runtime error (launch failure, out of memory in a _host call) */
+#define B200OPT_ENOTIMPL (-3) /* combination not compiled into this build */
+
+/* dtype of y / args / outputs: the arithmetic type of the whole solve (jax_enable_x64 analogue) */
+#define B200OPT_F32 0
+#define B200OPT_F64 1
+
+/* norms: optimistix.max_norm / two_norm / rms_norm  (optimistix/_misc.py:41-45) */
+#define B200OPT_NORM_MAX 0
+#define B200OPT_NORM_TWO 1
+#define B200OPT_NORM_RMS 2
+
+/* per-problem result codes; names via b200opt_result_name(). lineax members first (lx.RESULTS), then
+ * optimistix/_solution.py:11-20 */
+#define B200OPT_RESULT_SUCCESSFUL 0
+#define B200OPT_RESULT_MAX_STEPS_REACHED 1          /* lineax (iterative linear solvers; unused here) */
+#define B200OPT_RESULT_SINGULAR 2                   /* lineax: non-finite linear solution */
+#define B200OPT_RESULT_BREAKDOWN 3                  /* lineax (unused here) */
+#define B200OPT_RESULT_STAGNATION 4                 /* lineax (unused here) */
+#define B200OPT_RESULT_NONLINEAR_MAX_STEPS_REACHED 5
+#define B200OPT_RESULT_NONLINEAR_DIVERGENCE 6
+#define B200OPT_RESULT_NONFINITE 7
+
+/* solver ids */
+#define B200OPT_SOLVER_LEVENBERG_MARQUARDT 0 /* ClassicalTrustRegion + DampedNewtonDescent */
+#define B200OPT_SOLVER_GAUSS_NEWTON 1        /* LearningRate(1.0) + NewtonDescent */
+#define B200OPT_SOLVER_NEWTON 2
+#define B200OPT_SOLVER_CHORD 3
+#define B200OPT_SOLVER_BFGS 4                /* use_inverse=True, BacktrackingArmijo */
+
+/* model kinds */
+#define B200OPT_KIND_LEAST_SQUARES 0 /* residual model: y[n] -> r[m] */
+#define B200OPT_KIND_ROOT 1          /* y[n] -> F[n] */
+#define B200OPT_KIND_MINIMISE 2      /* y[n] -> scalar */
+
+/* Solver options: the constructor fields of the reference solver classes
+ * (levenberg_marquardt.py:281-294, gauss_newton.py:382-395, newton_chord.py:59-65, quasi_newton.py:443-458)
+ * plus the `max_steps` keyword of the entry points (default 256, _least_squares.py:53). */
+typedef struct b200opt_options {
+  double rtol;
+  double atol;
+  int32_t norm;               /* B200OPT_NORM_* */
+  int32_t max_steps;          /* >= 0 */
+  int32_t cauchy_termination; /* Newton/Chord only: 1 (default) or 0 = Hairer-Wanner test, newton_chord.py:179-192 */
+  int32_t root_near_zero;     /* 1 = also require norm(f) < atol (root_find through LM/BFGS, _root_find.py:45-80) */
+  double kappa;               /* Newton/Chord non-Cauchy mode, default 1e-2 */
+} b200opt_options_t;
+
+/* Residual-model plugin registry: the compiled-in model families (device residual/Jacobian functions). */
+typedef struct b200opt_model_info {
+  int32_t id;
+  int32_t kind;            /* B200OPT_KIND_* */
+  int32_t n;               /* number of parameters; 0 = any n accepted up to n_max */
+  int32_t n_max;
+  int32_t m_max;           /* least squares: maximum residual count; 0 = not applicable */
+  int32_t shared_args;     /* number of shared-argument elements as a function of (n,m): see shared_layout */
+  const char* name;        /* e.g. "exp_decay" */
+  const char* params;      /* human-readable parameter layout */
+  const char* shared_layout;  /* what `shared_args` points to */
+  const char* problem_layout; /* what each row of `problem_args` holds */
+} b200opt_model_info_t;
+
+int32_t b200opt_version(void);
+const char* b200opt_last_error(void);
+const char* b200opt_result_name(int32_t result_code);
+int32_t b200opt_model_count(void);
+int32_t b200opt_model_info_get(int32_t model_id, b200opt_model_info_t* out);
+int32_t b200opt_model_id(const char* name); /* -1 if unknown */
+void b200opt_default_options(b200opt_options_t* out);
+
+/* ---- batched nonlinear least squares (LM / GN), one warp per problem, persistent kernel ---------------
+ * y0           [batch][n]
+ * shared_args  model-specific, shared by all problems (e.g. the abscissa grid t[m])
+ * problem_args [batch][problem_args_stride] (e.g. the data d[m])
+ * outputs: y_out [batch][n]; num_steps[batch]; result[batch];
+ *          optional (may be NULL): step_size_out[batch] (final trust-region radius, dtype),
+ *                                  num_accepted_out[batch] (gauss_newton.py:153-155 counter) */
+int32_t b200opt_least_squares(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, int32_t m,
+                              const void* y0, const void* shared_args, const void* problem_args,
+                              int64_t problem_args_stride, const b200opt_options_t* opts, void* y_out,
+                              int32_t* num_steps, int32_t* result, void* step_size_out, int32_t* num_accepted_out,
+                              void* stream);
+
+/* ---- batched root finding (Newton / Chord), one warp per problem --------------------------------------
+ * lower/upper: optional [n] clip bounds shared by all problems (options["lower"/"upper"], newton_chord.py:112-135) */
+int32_t b200opt_root_find(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, const void* y0,
+                          const void* shared_args, const void* problem_args, int64_t problem_args_stride,
+                          const void* lower, const void* upper, const b200opt_options_t* opts, void* y_out,
+                          int32_t* num_steps, int32_t* result, void* stream);
+
+/* ---- batched minimisation (BFGS, dense inverse Hessian on chip), one CTA per problem -------------------
+ * optional outputs (may be NULL): f_out[batch] (dtype), hessian_inv_out[batch][n][n] (dtype), num_accepted_out */
+int32_t b200opt_minimise(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, const void* y0,
+                         const void* shared_args, const void* problem_args, int64_t problem_args_stride,
+                         const b200opt_options_t* opts, void* y_out, int32_t* num_steps, int32_t* result,
+                         void* f_out, void* hessian_inv_out, int32_t* num_accepted_out, void* stream);
+
+/* ---- HOST-buffer variants: same meaning, pointers are host memory; chunked H2D / solve / D2H pipeline.
+ * `device` is the CUDA device ordinal; chunk = problems per pipeline stage (0 = library default). */
+int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch,
+                                   int32_t n, int32_t m, const void* y0, const void* shared_args,
+                                   int64_t shared_args_count, const void* problem_args, int64_t problem_args_stride,
+                                   const b200opt_options_t* opts, void* y_out, int32_t* num_steps, int32_t* result,
+                                   int64_t chunk);
+int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch,
+                               int32_t n, const void* y0, const void* shared_args, int64_t shared_args_count,
+                               const void* problem_args, int64_t problem_args_stride, const b200opt_options_t* opts,
+                               void* y_out, int32_t* num_steps, int32_t* result, int64_t chunk);
+int32_t b200opt_minimise_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
+                              const void* y0, const void* shared_args, int64_t shared_args_count,
+                              const void* problem_args, int64_t problem_args_stride, const b200opt_options_t* opts,
+                              void* y_out, int32_t* num_steps, int32_t* result, int64_t chunk);
+
+/* ---- generic per-iteration step for an arbitrary user `fn` (J and r computed by the caller) ------------
+ * One call = one AbstractGaussNewton.step + the driver bookkeeping of _iterate.py:234-241 for every
+ * still-running problem.  `state` is an opaque per-problem carry of b200opt_lsq_step_state_size(dtype,n,m)
+ * bytes per problem, zero-initialised by b200opt_lsq_step_init.
+ *   r_eval [batch][m], J_eval [batch][m][n]: residual and Jacobian at y_eval (as written by the last call)
+ *   y_eval [batch][n] in/out: the next trial point;  y [batch][n] in/out: last accepted point
+ *   active_count (device int32, optional): number of problems still running after this step */
+int64_t b200opt_lsq_step_state_size(int32_t dtype, int32_t n, int32_t m);
+int32_t b200opt_lsq_step_init(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* y0, void* y, void* y_eval,
+                              void* state, int32_t* num_steps, int32_t* result, void* stream);
+int32_t b200opt_lsq_step(int32_t solver, int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* r_eval,
+                         const void* J_eval, void* y, void* y_eval, void* state, const b200opt_options_t* opts,
+                         int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream);
+/* after the loop: result successful & not terminated -> nonlinear_max_steps_reached (_iterate.py:253-257) */
+int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* state, int32_t* result,
+                                void* stream);
+
+/* ---- large row-sharded Gauss-Newton Gram on tcgen05 tensor cores (TF32 in, FP32 accumulate in TMEM) ----
+ * J [m_local][n] row-major fp32 (n == 256 in this build), r [m_local] fp32.
+ * out [n*n + n + 1] fp32: G = J^T J (row-major, full symmetric), then g = J^T r, then r^T r.
+ * The caller all-reduces `out` across ranks (NCCL sum) and calls b200opt_gn_solve. `workspace` must hold
+ * b200opt_gn_gram_workspace_size(n) bytes. */
+int64_t b200opt_gn_gram_workspace_size(int32_t n);
+int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace,
+                        void* stream);
+/* Solve (G + lambda I) p = g in fp64 on one CTA; p_out [n] fp32; status_out: device int32 result code. */
+int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float* p_out, int32_t* status_out,
+                         void* stream);
+/* r = J y - d for the "linear_rows" family, fused single pass (used by the GaussNewton driver for configs[4]) */
+int32_t b200opt_linear_residual(const float* J, const float* y, const float* d, int64_t m_local, int32_t n, float* r,
+                                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OPT_H_ */

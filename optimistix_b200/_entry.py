@@ -1,0 +1,372 @@
+"""Entry points: least_squares / minimise / root_find / fixed_point.
+
+Signatures follow the reference (optimistix/_least_squares.py:44-58, _minimise.py:37-51,
+_root_find.py:119-133, _fixed_point.py:50-66):
+    f(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps=256,
+      adjoint=ImplicitAdjoint(), throw=True, tags=frozenset()) -> Solution
+
+What differs, by construction: the reference is batched from outside with `jax.vmap`; here the batch
+axis is explicit.  `y0` of shape [n] is one problem, `[B, n]` is B independent problems whose
+per-problem args carry the same leading axis.  CUDA tensors in -> CUDA tensors out, asynchronously on
+torch's current stream (unless `throw=True`, which has to look at the result codes).  NumPy / CPU
+tensors in -> NumPy out through the `_host` C entry points (chunked H2D / solve / D2H pipeline).
+
+There is no CPU implementation behind these functions: without the CUDA library they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+from ._models import KIND_LSQ, KIND_MIN, KIND_ROOT, RegisteredModel
+from ._solution import RESULTS, Solution
+from ._solvers import (
+    BFGS,
+    AbstractLeastSquaresSolver,
+    AbstractMinimiser,
+    AbstractRootFinder,
+    BacktrackingArmijo,
+    Chord,
+    ClassicalTrustRegion,
+    GaussNewton,
+    ImplicitAdjoint,
+    LearningRate,
+    LevenbergMarquardt,
+    Newton,
+)
+
+_NP_DTYPES = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class _Buf:
+    """Uniform view of a torch-CUDA tensor or a NumPy array as (pointer, keepalive)."""
+
+    def __init__(self, device: bool, dtype_code: int):
+        self.device = device
+        self.dtype_code = dtype_code
+        if device:
+            t = _torch()
+            self.tdtype = t.float32 if dtype_code == _lib.F32 else t.float64
+        self.ndtype = np.float32 if dtype_code == _lib.F32 else np.float64
+
+    def arr(self, x, dev=None):
+        if self.device:
+            t = _torch()
+            x = t.as_tensor(x, dtype=self.tdtype, device=dev)
+            return x.contiguous()
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        return np.ascontiguousarray(x, dtype=self.ndtype)
+
+    def empty(self, shape, like, dtype=None):
+        if self.device:
+            t = _torch()
+            return t.empty(shape, dtype=dtype or self.tdtype, device=like.device)
+        return np.empty(shape, dtype=dtype or self.ndtype)
+
+    def empty_i32(self, shape, like):
+        if self.device:
+            return _torch().empty(shape, dtype=_torch().int32, device=like.device)
+        return np.empty(shape, dtype=np.int32)
+
+    @staticmethod
+    def ptr(x):
+        if x is None:
+            return None
+        if _is_torch(x):
+            return x.data_ptr()
+        return x.ctypes.data
+
+
+def _prepare_y0(y0):
+    if _is_torch(y0):
+        t = _torch()
+        if not y0.dtype.is_floating_point:
+            y0 = y0.to(t.get_default_dtype())  # inexact_asarray, _misc.py:281-285
+        if y0.dtype not in (t.float32, t.float64):
+            raise TypeError(f"unsupported dtype {y0.dtype}: the CUDA path computes in float32 or float64")
+        code = _lib.F32 if y0.dtype == t.float32 else _lib.F64
+        device = y0.is_cuda
+    else:
+        y0 = np.asarray(y0)
+        if not np.issubdtype(y0.dtype, np.floating):
+            y0 = y0.astype(np.float64)
+        if y0.dtype not in _NP_DTYPES:
+            raise TypeError(f"unsupported dtype {y0.dtype}")
+        code = _NP_DTYPES[y0.dtype]
+        device = False
+    single = y0.ndim == 1
+    if y0.ndim not in (1, 2):
+        raise ValueError("y0 must have shape [n] (one problem) or [batch, n]")
+    buf = _Buf(device, code)
+    y0 = buf.arr(y0, dev=y0.device if device else None)
+    if single:
+        y0 = y0[None]
+    return y0, buf, single
+
+
+def _finish(buf, single, throw, value, num_steps, result, max_steps, extra_stats=None, state=None):
+    if throw:
+        # reference: result.error_if(sol, result != successful) (_iterate.py:357-358) - a runtime error if
+        # ANY lane failed.  Needs the codes on the host, so this synchronises.
+        res_host = result.cpu().numpy() if _is_torch(result) else result
+        bad = np.flatnonzero(res_host != RESULTS.successful)
+        if bad.size:
+            code = int(res_host[bad[0]])
+            raise RuntimeError(
+                f"{bad.size} of {res_host.size} solves failed; first failure (problem {int(bad[0])}): "
+                f"{RESULTS.name(code)}: {RESULTS[code]}"
+            )
+    stats = {"num_steps": num_steps, "max_steps": max_steps}
+    if extra_stats:
+        stats.update(extra_stats)
+    if single:
+        value, result = value[0], result[0]
+        stats = {k: (v[0] if hasattr(v, "__len__") else v) for k, v in stats.items()}
+    return Solution(value=value, result=result, aux=None, stats=stats, state=state)
+
+
+def _stream_ptr(buf, like):
+    if not buf.device:
+        return None
+    return _torch().cuda.current_stream(like.device).cuda_stream
+
+
+def _check_common(fn, options, has_aux, adjoint):
+    if has_aux:
+        raise NotImplementedError("has_aux=True: registered model families return no auxiliary output")
+    if options:
+        unknown = set(options) - {"jac", "autodiff_mode", "lower", "upper"}
+        if unknown:
+            raise ValueError(f"unknown options {sorted(unknown)}")
+        if options.get("jac", "fwd") not in ("fwd", "bwd"):
+            raise ValueError("Only `jac='fwd'` or `jac='bwd'` are valid.")  # gauss_newton.py:180
+        if options.get("autodiff_mode", "bwd") not in ("fwd", "bwd"):
+            raise ValueError("Only `autodiff_mode='fwd'` or `autodiff_mode='bwd'` are valid.")  # _misc.py:255-258
+
+
+def _check_defaults(solver):
+    search = getattr(solver, "search", None)
+    if isinstance(solver, LevenbergMarquardt) and search != ClassicalTrustRegion():
+        raise NotImplementedError("the CUDA LM kernel implements ClassicalTrustRegion with the reference defaults")
+    if isinstance(solver, GaussNewton) and search != LearningRate(1.0):
+        raise NotImplementedError("the CUDA GN kernel implements LearningRate(1.0)")
+    if isinstance(solver, BFGS) and search != BacktrackingArmijo():
+        raise NotImplementedError("the CUDA BFGS kernel implements BacktrackingArmijo with the reference defaults")
+
+
+# ------------------------------------------------------------------------------------------ least squares
+def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
+                  adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), _root_near_zero=False, chunk: int = 0):
+    """Solve (a batch of) nonlinear least-squares problems. Reference: optimistix/_least_squares.py:44-135."""
+    if isinstance(solver, AbstractMinimiser):
+        raise NotImplementedError("least_squares through a minimiser (_least_squares.py:102-114) needs the generic path")
+    if not isinstance(solver, (LevenbergMarquardt, GaussNewton)):
+        raise TypeError(f"least_squares: unsupported solver {type(solver).__name__}")
+    _check_common(fn, options, has_aux, adjoint)
+    _check_defaults(solver)
+    if max_steps is None:
+        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+    if not isinstance(fn, RegisteredModel):
+        from ._generic import least_squares_generic
+
+        return least_squares_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, root_near_zero=_root_near_zero)
+    if fn.kind != KIND_LSQ:
+        raise TypeError(f"model {fn.name} is not a least-squares family")
+    lib = _lib.load()
+    y0, buf, single = _prepare_y0(y0)
+    B, n = y0.shape
+    a = fn.split_args(args)
+    dev = y0.device if buf.device else None
+    shared = buf.arr(a[fn.arg_names[0]], dev).reshape(-1)
+    prob = buf.arr(a[fn.arg_names[1]], dev)
+    if single and prob.ndim == 1:
+        prob = prob[None]
+    m = int(shared.shape[0])
+    if prob.ndim != 2 or prob.shape[0] != B or prob.shape[1] != m:
+        raise ValueError(f"{fn.name}: per-problem data must have shape [{B}, {m}], got {tuple(prob.shape)}")
+    solver_id = _lib.SOLVER_LM if isinstance(solver, LevenbergMarquardt) else _lib.SOLVER_GN
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=_root_near_zero)
+    y_out = buf.empty((B, n), y0)
+    steps = buf.empty_i32((B,), y0)
+    res = buf.empty_i32((B,), y0)
+    extra = {}
+    if buf.device:
+        step_size = buf.empty((B,), y0)
+        nacc = buf.empty_i32((B,), y0)
+        code = lib.b200opt_least_squares(solver_id, fn.model_id, buf.dtype_code, B, n, m, buf.ptr(y0), buf.ptr(shared),
+                                         buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res),
+                                         buf.ptr(step_size), buf.ptr(nacc), _stream_ptr(buf, y0))
+        extra = {"step_size": step_size, "num_accepted_steps": nacc}
+    else:
+        t = _torch()
+        device = t.cuda.current_device() if t.cuda.is_available() else 0
+        code = lib.b200opt_least_squares_host(device, solver_id, fn.model_id, buf.dtype_code, B, n, m, buf.ptr(y0),
+                                              buf.ptr(shared), m, buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out),
+                                              buf.ptr(steps), buf.ptr(res), int(chunk))
+    _lib.check(code, "b200opt_least_squares")
+    return _finish(buf, single, throw, y_out, steps, res, max_steps, extra)
+
+
+# ------------------------------------------------------------------------------------------ root find
+def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
+              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0):
+    """Solve (a batch of) root-finding problems. Reference: optimistix/_root_find.py:119-241."""
+    _check_common(fn, options, has_aux, adjoint)
+    if max_steps is None:
+        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+    if isinstance(solver, AbstractLeastSquaresSolver):
+        # _root_find.py:200-225: least-squares solver wrapped in _LstsqToRoot (extra `norm(f) < atol` test)
+        return least_squares(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, _root_near_zero=True, chunk=chunk)
+    if isinstance(solver, AbstractMinimiser):
+        raise NotImplementedError("root_find through a minimiser (_root_find.py:176-199) needs the generic path")
+    if not isinstance(solver, (Newton, Chord)):
+        raise TypeError(f"root_find: unsupported solver {type(solver).__name__}")
+    if not isinstance(fn, RegisteredModel):
+        from ._generic import root_find_generic
+
+        return root_find_generic(fn, solver, y0, args, options, max_steps=max_steps, throw=throw)
+    if fn.kind != KIND_ROOT:
+        raise TypeError(f"model {fn.name} is not a root-finding family")
+    lib = _lib.load()
+    y0, buf, single = _prepare_y0(y0)
+    B, n = y0.shape
+    a = fn.split_args(args)
+    dev = y0.device if buf.device else None
+    shared, prob, stride = _pack_root_args(fn, a, buf, dev, B, n, single)
+    lower = upper = None
+    if options:
+        if options.get("lower") is not None:
+            lower = _bound(buf, options["lower"], n, dev)
+        if options.get("upper") is not None:
+            upper = _bound(buf, options["upper"], n, dev)
+    solver_id = _lib.SOLVER_NEWTON if isinstance(solver, Newton) else _lib.SOLVER_CHORD
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps,
+                             cauchy_termination=solver.cauchy_termination, kappa=solver.kappa)
+    y_out = buf.empty((B, n), y0)
+    steps = buf.empty_i32((B,), y0)
+    res = buf.empty_i32((B,), y0)
+    if buf.device:
+        code = lib.b200opt_root_find(solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared), buf.ptr(prob),
+                                     stride, buf.ptr(lower), buf.ptr(upper), C.byref(opts), buf.ptr(y_out), buf.ptr(steps),
+                                     buf.ptr(res), _stream_ptr(buf, y0))
+    else:
+        if lower is not None or upper is not None:
+            raise NotImplementedError("lower/upper bounds are only wired on the device-pointer entry point")
+        t = _torch()
+        device = t.cuda.current_device() if t.cuda.is_available() else 0
+        code = lib.b200opt_root_find_host(device, solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared),
+                                          int(shared.shape[0]), buf.ptr(prob), stride, C.byref(opts), buf.ptr(y_out),
+                                          buf.ptr(steps), buf.ptr(res), int(chunk))
+    _lib.check(code, "b200opt_root_find")
+    return _finish(buf, single, throw, y_out, steps, res, max_steps)
+
+
+def _bound(buf, b, n, dev):
+    if buf.device:
+        t = _torch()
+        return t.broadcast_to(t.as_tensor(b, dtype=buf.tdtype, device=dev), (n,)).contiguous()
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=buf.ndtype), (n,)))
+
+
+def _pack_root_args(fn, a, buf, dev, B, n, single):
+    """implicit_euler: shared = [A | B] (2 n^2), per problem = [y_prev (n) | dt | pad] with an even stride."""
+    if fn.name != "implicit_euler":
+        raise NotImplementedError(fn.name)
+    A, Bm = buf.arr(a["A"], dev), buf.arr(a["B"], dev)
+    if tuple(A.shape) != (n, n) or tuple(Bm.shape) != (n, n):
+        raise ValueError(f"implicit_euler: A and B must be [{n}, {n}]")
+    y_prev, dt = buf.arr(a["y_prev"], dev), buf.arr(a["dt"], dev)
+    if single:
+        y_prev, dt = y_prev.reshape(1, n), dt.reshape(1)
+    if tuple(y_prev.shape) != (B, n) or tuple(dt.shape) != (B,):
+        raise ValueError(f"implicit_euler: y_prev must be [{B}, {n}] and dt [{B}]")
+    stride = n + 2
+    if buf.device:
+        t = _torch()
+        shared = t.cat([A.reshape(-1), Bm.reshape(-1)])
+        prob = t.empty((B, stride), dtype=buf.tdtype, device=dev)
+        prob[:, :n] = y_prev
+        prob[:, n] = dt
+        prob[:, n + 1] = 0
+    else:
+        shared = np.concatenate([A.reshape(-1), Bm.reshape(-1)])
+        prob = np.zeros((B, stride), dtype=buf.ndtype)
+        prob[:, :n] = y_prev
+        prob[:, n] = dt
+    return shared, prob, stride
+
+
+# ------------------------------------------------------------------------------------------ fixed point
+def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
+                adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset()):
+    """Find a fixed point. Reference: optimistix/_fixed_point.py:50-154: with a root finder / least-squares
+    solver / minimiser this is `root_find` on `fn(y, args) - y` (:35-47, :115-129)."""
+    if isinstance(fn, RegisteredModel):
+        raise TypeError("registered model families are residual/root/objective functions, not fixed-point maps; "
+                        "use root_find, or pass a Python callable")
+    if not isinstance(solver, (AbstractRootFinder, AbstractLeastSquaresSolver, AbstractMinimiser)):
+        raise NotImplementedError("FixedPointIteration is out of scope (SURVEY section 2); use Newton/Chord/LM")
+
+    def _to_root_fn(y, a):  # _fixed_point.py:35-47
+        out = fn(y, a)
+        if out.shape != y.shape:
+            raise ValueError("The input and output of `fixed_point_fn` must have the same structure")
+        return out - y
+
+    return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, throw=throw)
+
+
+# ------------------------------------------------------------------------------------------ minimise
+def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
+             adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False):
+    """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
+    _check_common(fn, options, has_aux, adjoint)
+    if not isinstance(solver, BFGS):
+        raise TypeError(f"minimise: unsupported solver {type(solver).__name__}")
+    _check_defaults(solver)
+    if max_steps is None:
+        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+    if not isinstance(fn, RegisteredModel):
+        from ._generic import minimise_generic
+
+        return minimise_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw)
+    if fn.kind != KIND_MIN:
+        raise TypeError(f"model {fn.name} is not a minimisation family")
+    lib = _lib.load()
+    y0, buf, single = _prepare_y0(y0)
+    B, n = y0.shape
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps)
+    y_out = buf.empty((B, n), y0)
+    steps = buf.empty_i32((B,), y0)
+    res = buf.empty_i32((B,), y0)
+    extra, state = {}, None
+    if buf.device:
+        f_out = buf.empty((B,), y0)
+        nacc = buf.empty_i32((B,), y0)
+        hinv = buf.empty((B, n, n), y0) if return_hessian_inv else None
+        code = lib.b200opt_minimise(_lib.SOLVER_BFGS, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), None, None, 0,
+                                    C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res), buf.ptr(f_out),
+                                    buf.ptr(hinv), buf.ptr(nacc), _stream_ptr(buf, y0))
+        extra = {"num_accepted_steps": nacc}
+        state = {"f": f_out, "hessian_inv": hinv}
+    else:
+        t = _torch()
+        device = t.cuda.current_device() if t.cuda.is_available() else 0
+        code = lib.b200opt_minimise_host(device, _lib.SOLVER_BFGS, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), None, 0,
+                                         None, 0, C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res), int(chunk))
+    _lib.check(code, "b200opt_minimise")
+    return _finish(buf, single, throw, y_out, steps, res, max_steps, extra, state)

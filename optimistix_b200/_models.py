@@ -1,0 +1,109 @@
+"""Residual-model plugin registry, host side.
+
+A `RegisteredModel` stands where the reference takes the user callable `fn(y, args)`
+(optimistix/_least_squares.py:44-58 etc.).  Passing one to `least_squares` / `root_find` /
+`minimise` / `fixed_point` selects the persistent CUDA kernel whose device functions implement
+that family (optimistix_b200/csrc/models.cuh); an arbitrary Python callable goes to the generic
+per-iteration step kernel instead.  Each model also carries `torch_fn`, the same function
+written with torch ops, so that `fn(y, args)` can still be *evaluated* like the reference's fn
+(used by tests and by users who want residuals at the solution); it is never used to solve.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Any, Callable
+
+KIND_LSQ, KIND_ROOT, KIND_MIN = 0, 1, 2
+
+
+@dataclasses.dataclass(frozen=True)
+class RegisteredModel:
+    name: str
+    model_id: int
+    kind: int
+    n: int  # 0 = any
+    arg_names: tuple  # names in `args`, shared ones first
+    n_shared: int  # how many of arg_names are shared by all problems
+    torch_fn: Callable | None = None
+    doc: str = ""
+
+    def __call__(self, y, args):
+        if self.torch_fn is None:
+            raise NotImplementedError(f"model {self.name} has no host-side evaluator")
+        return self.torch_fn(y, self.split_args(args))
+
+    def split_args(self, args) -> dict:
+        if args is None:
+            args = ()
+        if isinstance(args, dict):
+            missing = [k for k in self.arg_names if k not in args]
+            if missing:
+                raise TypeError(f"model {self.name}: args is missing {missing}; expected {self.arg_names}")
+            return {k: args[k] for k in self.arg_names}
+        if len(args) != len(self.arg_names):
+            raise TypeError(f"model {self.name}: expected args {self.arg_names}, got {len(args)} items")
+        return dict(zip(self.arg_names, args))
+
+
+def _exp_decay(y, a):
+    import torch
+
+    t, d = a["t"], a["d"]
+    return y[..., 0:1] * torch.exp(-y[..., 1:2] * t) + y[..., 2:3] - d
+
+
+def _gauss2(y, a):
+    import torch
+
+    x, d = a["x"], a["d"]
+    z1 = (x - y[..., 1:2]) / y[..., 2:3]
+    z2 = (x - y[..., 4:5]) / y[..., 5:6]
+    return (y[..., 0:1] * torch.exp(-0.5 * z1 * z1) + y[..., 3:4] * torch.exp(-0.5 * z2 * z2)
+            + y[..., 6:7] + y[..., 7:8] * x - d)
+
+
+def _implicit_euler(y, a):
+    A, B, y_prev, dt = a["A"], a["B"], a["y_prev"], a["dt"]
+    f = y @ A.T + y * (y @ B.T)
+    return y - y_prev - dt[..., None] * f
+
+
+def _rosenbrock(y, a):
+    p = y[..., 1:] - y[..., :-1] ** 2
+    q = 1.0 - y[..., :-1]
+    return (100.0 * p * p + q * q).sum(-1)
+
+
+exp_decay = RegisteredModel("exp_decay", 0, KIND_LSQ, 3, ("t", "d"), 1, _exp_decay,
+                            "r_i = a*exp(-b*t_i) + c - d_i, y = [a, b, c]")
+gauss2 = RegisteredModel("gauss2", 1, KIND_LSQ, 8, ("x", "d"), 1, _gauss2,
+                         "two Gaussians + linear baseline, y = [A1, mu1, s1, A2, mu2, s2, b0, b1]")
+implicit_euler = RegisteredModel("implicit_euler", 2, KIND_ROOT, 32, ("A", "B", "y_prev", "dt"), 2, _implicit_euler,
+                                 "F(y) = y - y_prev - dt*(A y + y*(B y))")
+rosenbrock = RegisteredModel("rosenbrock", 3, KIND_MIN, 0, (), 0, _rosenbrock, "standard chained Rosenbrock")
+linear_rows = RegisteredModel("linear_rows", 4, KIND_LSQ, 256, ("J", "d"), 0, None,
+                              "r = J y - d, J materialised row-major in HBM (single large problem)")
+
+_REGISTRY = {m.name: m for m in (exp_decay, gauss2, implicit_euler, rosenbrock, linear_rows)}
+
+
+def get(name: str) -> RegisteredModel:
+    return _REGISTRY[name]
+
+
+def names():
+    return tuple(_REGISTRY)
+
+
+def check_against_library(lib) -> None:
+    """The Python table must describe exactly what is compiled into libb200opt.so."""
+    import ctypes as C
+
+    from ._lib import ModelInfo
+
+    assert lib.b200opt_model_count() == len(_REGISTRY)
+    for m in _REGISTRY.values():
+        info = ModelInfo()
+        assert lib.b200opt_model_info_get(m.model_id, C.byref(info)) == 0
+        assert info.name.decode() == m.name and info.kind == m.kind and info.n == m.n, (m.name, info.name, info.kind, info.n)
+        assert lib.b200opt_model_id(m.name.encode()) == m.model_id

@@ -1,0 +1,74 @@
+"""In-tree build of libb200opt.so (nvcc, sm_100a only) and of the C oracle.
+
+`python -m optimistix_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
+Objects go to optimistix_b200/csrc/build/, the library to optimistix_b200/libb200opt.so (git-ignored,
+but it travels to the GPU box with the gpurun snapshot).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libb200opt.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps_hash(src: str) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(FLAGS).encode())
+    for f in sorted(os.listdir(CSRC)) + ["../../include/b200opt.h"]:
+        if f.endswith((".cuh", ".h")) or f == src:
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
+def _compile(src: str, force: bool) -> str:
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    stamp = obj + ".hash"
+    want = _deps_hash(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+        return obj
+    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    with open(obj + ".log", "w") as fh:  # ptxas -v output: registers / spills / smem per kernel
+        fh.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{res.stderr[-6000:]}")
+    with open(stamp, "w") as fh:
+        fh.write(want)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = _sources()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force), srcs))
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stderr[-4000:])
+    if verbose:
+        print(f"[b200opt] built {LIB} from {len(srcs)} sources", file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,94 @@
+// Host-side launcher for the batched LM/GN kernel: picks rows-per-lane, grid size and shared memory.
+#pragma once
+#include "lsq_kernel.cuh"
+
+namespace b200opt {
+
+struct LsqArgs {
+  int solver, dtype;
+  int64_t batch;
+  int n, m;
+  const void *y0, *shared, *prob;
+  int64_t prob_stride;
+  const b200opt_options_t* opts;
+  void* y_out;
+  int32_t *num_steps, *result;
+  void* step_size_out;
+  int32_t* num_accepted;
+  cudaStream_t stream;
+};
+
+int device_sm_count();
+
+template <class Model, typename T, int RPL, bool TRUST> int lsq_launch_one(const LsqParams<T>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel<Model, T, RPL, TRUST>;
+  const size_t smem = sizeof(T) * lsq_smem_elems_per_warp<Model, T, RPL>() * kLsqWarpsPerBlock;
+  static thread_local int blocks_per_sm = 0;  // per instantiation
+  if (blocks_per_sm == 0) {
+    if (smem > 48 * 1024)
+      if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
+        return B200OPT_ECUDA;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy"))
+      return B200OPT_ECUDA;
+    blocks_per_sm = occ > 0 ? occ : 1;
+  }
+  const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
+  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;  // persistent: one resident wave, grid-stride
+  const int grid = (int)(need < cap ? need : cap);
+  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "lsq_solve_kernel launch");
+}
+
+template <class Model, typename T, bool TRUST> int lsq_launch_rpl(const LsqParams<T>& p, cudaStream_t stream) {
+  const int m = p.m;
+  if (m <= 32) return lsq_launch_one<Model, T, 1, TRUST>(p, stream);
+  if (m <= 64) return lsq_launch_one<Model, T, 2, TRUST>(p, stream);
+  if (m <= 128) return lsq_launch_one<Model, T, 4, TRUST>(p, stream);
+  if (m <= 256) return lsq_launch_one<Model, T, 8, TRUST>(p, stream);
+  if (m <= 512) return lsq_launch_one<Model, T, 16, TRUST>(p, stream);
+  set_error("least_squares: m=%d exceeds the register-resident limit of 512 residuals per problem", m);
+  return B200OPT_EINVAL;
+}
+
+template <template <typename> class ModelT, typename T> int lsq_launch_typed(const LsqArgs& a) {
+  using Model = ModelT<T>;
+  if (a.n != Model::N) {
+    set_error("least_squares: model expects n=%d parameters, got n=%d", Model::N, a.n);
+    return B200OPT_EINVAL;
+  }
+  LsqParams<T> p;
+  p.y0 = static_cast<const T*>(a.y0);
+  p.shared = static_cast<const T*>(a.shared);
+  p.prob = static_cast<const T*>(a.prob);
+  p.prob_stride = a.prob_stride;
+  p.y_out = static_cast<T*>(a.y_out);
+  p.num_steps = a.num_steps;
+  p.result = a.result;
+  p.step_size_out = static_cast<T*>(a.step_size_out);
+  p.num_accepted = a.num_accepted;
+  p.batch = a.batch;
+  p.m = a.m;
+  p.rtol = (T)a.opts->rtol;
+  p.atol = (T)a.opts->atol;
+  p.norm = a.opts->norm;
+  p.max_steps = a.opts->max_steps;
+  p.root_near_zero = a.opts->root_near_zero;
+  constexpr int V = Num<T>::kVec;
+  p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
+  if (a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT) return lsq_launch_rpl<Model, T, true>(p, a.stream);
+  return lsq_launch_rpl<Model, T, false>(p, a.stream);
+}
+
+template <template <typename> class ModelT> int lsq_launch_model(const LsqArgs& a) {
+  if (a.dtype == B200OPT_F32) return lsq_launch_typed<ModelT, float>(a);
+  if (a.dtype == B200OPT_F64) return lsq_launch_typed<ModelT, double>(a);
+  set_error("least_squares: unknown dtype %d", a.dtype);
+  return B200OPT_EINVAL;
+}
+
+// one translation unit per model family (parallel nvcc)
+int lsq_launch_exp_decay(const LsqArgs& a);
+int lsq_launch_gauss2(const LsqArgs& a);
+
+}  // namespace b200opt

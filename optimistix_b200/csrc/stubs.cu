@@ -1,0 +1,40 @@
+// Entry points declared in include/b200opt.h whose kernels are not built yet return B200OPT_ENOTIMPL
+// (loudly - the Python layer raises).  Each stub disappears when its kernel lands.
+#include "common.cuh"
+using namespace b200opt;
+#define NOTIMPL(name) \
+  set_error(name ": not implemented in this build"); \
+  return B200OPT_ENOTIMPL;
+extern "C" {
+int32_t b200opt_root_find(int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, const void*, int64_t,
+                          const void*, const void*, const b200opt_options_t*, void*, int32_t*, int32_t*, void*) {
+  NOTIMPL("root_find")
+}
+int32_t b200opt_minimise(int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, const void*, int64_t,
+                         const b200opt_options_t*, void*, int32_t*, int32_t*, void*, void*, int32_t*, void*) {
+  NOTIMPL("minimise")
+}
+int32_t b200opt_root_find_host(int32_t, int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, int64_t,
+                               const void*, int64_t, const b200opt_options_t*, void*, int32_t*, int32_t*, int64_t) {
+  NOTIMPL("root_find_host")
+}
+int32_t b200opt_minimise_host(int32_t, int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, int64_t,
+                              const void*, int64_t, const b200opt_options_t*, void*, int32_t*, int32_t*, int64_t) {
+  NOTIMPL("minimise_host")
+}
+int64_t b200opt_lsq_step_state_size(int32_t, int32_t, int32_t) { return -1; }
+int32_t b200opt_lsq_step_init(int32_t, int64_t, int32_t, int32_t, const void*, void*, void*, void*, int32_t*, int32_t*, void*) {
+  NOTIMPL("lsq_step_init")
+}
+int32_t b200opt_lsq_step(int32_t, int32_t, int64_t, int32_t, int32_t, const void*, const void*, void*, void*, void*,
+                         const b200opt_options_t*, int32_t*, int32_t*, int32_t*, void*) {
+  NOTIMPL("lsq_step")
+}
+int32_t b200opt_lsq_step_finish(int32_t, int64_t, int32_t, int32_t, const void*, int32_t*, void*) { NOTIMPL("lsq_step_finish") }
+int64_t b200opt_gn_gram_workspace_size(int32_t) { return -1; }
+int32_t b200opt_gn_gram(const float*, const float*, int64_t, int32_t, float*, void*, void*) { NOTIMPL("gn_gram") }
+int32_t b200opt_gn_solve(const float*, int32_t, double, float*, int32_t*, void*) { NOTIMPL("gn_solve") }
+int32_t b200opt_linear_residual(const float*, const float*, const float*, int64_t, int32_t, float*, void*) {
+  NOTIMPL("linear_residual")
+}
+}
