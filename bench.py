@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 Optimistix hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Headline workload (BASELINE.json configs[1]): LevenbergMarquardt over 1,048,576 independent two-Gaussian +
+baseline fits (n=8 parameters, m=256 residuals, fp32, rtol=atol=1e-4, max_steps=256) PER GPU (weak scaling:
+problems are independent, ranks share nothing, there is no data-path collective).  A "step" is one pass of
+the hot path over that batch.  Prints ONE JSON line (rank 0).
+
+  value     problems/s, whole job, inputs resident in HBM, timed with CUDA events on the launching stream
+  e2e       problems/s through the C ABI host entry point (b200opt_least_squares_host) with pinned HOST
+            buffers: H2D of y0+data and D2H of y/num_steps/result are inside the timed region
+  roofline  the LM kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes
+            = 1096 B/problem; the binding roof is the fp32 FMA pipe, reported in "fp"
+  cpu_baseline / --impl reference: the reference's algorithm (augmented QR solve) restated in C + OpenMP
+            (oracle/c), timed on this box's host cores on a bounded sample of the same inputs.  The real
+            reference (JAX) cannot run in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, per-GPU batch, algorithmic HBM bytes / problem, dtype)
+    "gauss2": ("LM 2-Gaussian+baseline fits n=8 m=256 fp32 rtol=atol=1e-4 max_steps=256 (BASELINE configs[1])", 1 << 20, 1096, "f32"),
+    "exp_decay": ("LM exponential-decay fits n=3 m=64 fp64 rtol=atol=1e-8 max_steps=256 (BASELINE configs[0])", 4096, 568, "f64"),
+    "newton": ("Newton implicit-Euler root finds n=32 fp64 rtol=atol=1e-8 (BASELINE configs[2])", 1 << 18, 528, "f64"),
+    "bfgs": ("BFGS chained-Rosenbrock minimisations n=64 fp64 rtol=atol=1e-8 max_steps=4096 (BASELINE configs[3])", 1 << 16, 1032, "f64"),
+}
+CPU_SAMPLE = {"gauss2": 32768, "exp_decay": 4096, "newton": 8192, "bfgs": 256}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_inputs(name: str, batch: int, seed_offset: int):
+    from optimistix_b200 import synthetic
+
+    if name == "gauss2":
+        w = synthetic.gauss2_batch(batch, seed=1 + 1000 * seed_offset)
+        return dict(y0=w["y0"], shared=w["x"], prob=w["d"], truth=w["truth"])
+    if name == "exp_decay":
+        w = synthetic.exp_decay_batch(batch, seed=0 + 1000 * seed_offset)
+        return dict(y0=w["y0"], shared=w["t"], prob=w["d"], truth=w["truth"])
+    if name == "newton":
+        w = synthetic.implicit_euler_batch(batch, seed=2 + 1000 * seed_offset)
+        return dict(y0=w["y0"], A=w["A"], B=w["B"], y_prev=w["y_prev"], dt=w["dt"])
+    if name == "bfgs":
+        w = synthetic.rosenbrock_batch(batch, seed=3 + 1000 * seed_offset)
+        return dict(y0=w["y0"])
+    raise ValueError(name)
+
+
+def solver_for(name: str):
+    import optimistix_b200 as optx
+
+    if name == "gauss2":
+        return optx.models.gauss2, optx.LevenbergMarquardt(1e-4, 1e-4), 256
+    if name == "exp_decay":
+        return optx.models.exp_decay, optx.LevenbergMarquardt(1e-8, 1e-8), 256
+    if name == "newton":
+        return optx.models.implicit_euler, optx.Newton(1e-8, 1e-8), 256
+    if name == "bfgs":
+        return optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), 4096
+    raise ValueError(name)
+
+
+def run_device(name, inp_dev):
+    """One step with inputs resident in HBM: exactly one persistent-kernel launch."""
+    import optimistix_b200 as optx
+
+    fn, solver, max_steps = solver_for(name)
+    if name in ("gauss2", "exp_decay"):
+        return optx.least_squares(fn, solver, inp_dev["y0"], (inp_dev["shared"], inp_dev["prob"]), max_steps=max_steps, throw=False)
+    if name == "newton":
+        return optx.root_find(fn, solver, inp_dev["y0"], (inp_dev["A"], inp_dev["B"], inp_dev["y_prev"], inp_dev["dt"]),
+                              max_steps=max_steps, throw=False)
+    return optx.minimise(fn, solver, inp_dev["y0"], None, max_steps=max_steps, throw=False)
+
+
+def run_host(name, inp_host, chunk):
+    """One end-to-end step through the host C entry point: pinned host buffers in, host buffers out."""
+    import optimistix_b200 as optx
+
+    fn, solver, max_steps = solver_for(name)
+    if name in ("gauss2", "exp_decay"):
+        return optx.least_squares(fn, solver, inp_host["y0"], (inp_host["shared"], inp_host["prob"]), max_steps=max_steps,
+                                  throw=False, chunk=chunk)
+    if name == "newton":
+        return optx.root_find(fn, solver, inp_host["y0"], (inp_host["A"], inp_host["B"], inp_host["y_prev"], inp_host["dt"]),
+                              max_steps=max_steps, throw=False, chunk=chunk)
+    return optx.minimise(fn, solver, inp_host["y0"], None, max_steps=max_steps, throw=False, chunk=chunk)
+
+
+def cpu_reference(name, inp, sample, linsolve="qr"):
+    """The reference algorithm restated on the CPU (oracle), all host threads, on the first `sample` problems."""
+    from oracle import c_oracle
+
+    if name in ("gauss2", "exp_decay"):
+        tol = 1e-4 if name == "gauss2" else 1e-8
+        t0 = time.perf_counter()
+        out = c_oracle.levenberg_marquardt(name, inp["y0"][:sample], inp["shared"], inp["prob"][:sample], rtol=tol, atol=tol,
+                                           max_steps=256, linsolve=linsolve)
+        dt = time.perf_counter() - t0
+        return out, dt, c_oracle.max_threads(), "C+OpenMP restatement (oracle/c), augmented-QR solve as in the reference"
+    from oracle import models as M
+    from oracle import solvers as S
+
+    t0 = time.perf_counter()
+    if name == "newton":
+        a = dict(A=inp["A"], B=inp["B"], y_prev=inp["y_prev"][:sample], dt=inp["dt"][:sample])
+        out = S.newton_chord(M.implicit_euler, inp["y0"][:sample], a, rtol=1e-8, atol=1e-8)
+    else:
+        out = S.bfgs(M.rosenbrock, inp["y0"][:sample], None, rtol=1e-8, atol=1e-8, max_steps=4096)
+    dt = time.perf_counter() - t0
+    return out, dt, 1, "NumPy restatement (oracle/solvers.py), batched, single thread + BLAS"
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gauss2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the BASELINE config)")
+    ap.add_argument("--chunk", type=int, default=1 << 16, help="problems per pipeline stage in the host entry point")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload
+    desc, batch, bytes_per_problem, dtype = WORKLOADS[name]
+    if args.batch:
+        batch = args.batch
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = max(args.steps, 1)
+    config = {"workload": desc, "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"batch-sharded x{world}, no collective",
+              "l2": "inputs (>= 1 GB at the headline size) exceed the 126 MB L2; every step re-reads them from HBM"}
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = min(CPU_SAMPLE[name], batch)
+        inp = make_inputs(name, sample, 0)
+        for _ in range(args.warmup):
+            cpu_reference(name, inp, sample)
+        t = []
+        for _ in range(K):
+            _, dt, cores, kind_note = cpu_reference(name, inp, sample)
+            t.append(dt)
+        ms = 1e3 * float(np.mean(t))
+        val = sample / (ms / 1e3)
+        line = {"impl": "reference", "metric": "LM problems solved/sec" if name in ("gauss2", "exp_decay") else f"{name} problems solved/sec",
+                "value": val, "unit": "problems/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": "problems/s", "cores": cores, "kind": "port",
+                                 "sample": f"first {sample} problems of the workload per step; {kind_note}; the JAX reference itself cannot run in this image"},
+                "e2e": {"value": val, "unit": "problems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    inp = make_inputs(name, batch, rank)
+    keys = [k for k in inp if k != "truth"]
+    inp_dev = {k: torch.as_tensor(inp[k], device=dev) for k in keys}
+    torch.cuda.synchronize()
+
+    # ---- value: device-resident, one kernel launch per step, CUDA events on the launching (current) stream
+    for _ in range(W):
+        sol = run_device(name, inp_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        a.record()
+        sol = run_device(name, inp_dev)
+        b.record()
+    torch.cuda.synchronize()
+    t_total_local = sum(a.elapsed_time(b) for a, b in evs)  # ms, device time of the K steps
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    clocks = sampler.stop()
+    t_total = max_over_ranks(t_total_local)
+    ms_per_step = t_total / K
+    value = batch * world / (ms_per_step / 1e3)
+    launches = K
+
+    # size-independent checks at the full size (cheap, outside the timed region)
+    res = sol.result
+    steps_t = sol.stats["num_steps"]
+    n_ok = int((res == 0).sum().item())
+    mean_steps = float(steps_t.float().mean().item())
+    checks = {"successful_frac": n_ok / batch, "mean_num_steps": mean_steps}
+    if "truth" in inp:
+        err = (sol.value - torch.as_tensor(inp["truth"], device=dev)).abs().median(0).values
+        checks["median_abs_err_vs_truth_max"] = float(err.max().item())
+
+    # ---- e2e: host C entry point, pinned host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        inp_host = {k: torch.as_tensor(inp[k]).pin_memory().numpy() for k in keys}
+        h2d = sum(inp_host[k].nbytes for k in keys)
+        for _ in range(2):
+            hs = run_host(name, inp_host, args.chunk)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            hs = run_host(name, inp_host, args.chunk)
+        torch.cuda.synchronize()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / K
+        d2h = hs.value.nbytes + hs.stats["num_steps"].nbytes + hs.result.nbytes
+        same = bool(np.array_equal(hs.value, sol.value.cpu().numpy()))
+        checks["e2e_bitwise_equal_device_path"] = same
+        e2e = {"value": batch * world / (e2e_ms / 1e3), "unit": "problems/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_ms, "api": "b200opt_least_squares_host via optimistix_b200.least_squares(numpy inputs)" if name in ("gauss2", "exp_decay") else "host entry point",
+               "chunk": args.chunk}
+        launches += K * ((batch + args.chunk - 1) // args.chunk)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel
+    peak, peak_src = _peaks()
+    achieved = bytes_per_problem * batch / (ms_per_step / 1e3) / 1e9  # GB/s per GPU (per launch)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "lsq_solve_kernel" if name in ("gauss2", "exp_decay") else name,
+                "algorithmic_bytes_per_problem": bytes_per_problem, "peak_source": peak_src,
+                "note": "HBM is NOT the binding roof for this path (SURVEY F8): state is on-chip, ~0.5 Mflop per 1.1 KB; see 'fp'"}
+    flops_per_iter = {"gauss2": 50e3, "exp_decay": 6.5e3, "newton": 28e3, "bfgs": 41e3}[name]
+    fp_achieved = value / world * mean_steps * flops_per_iter / 1e12
+    fp_peak = 148 * 128 * 2 * 1.965e9 / 1e12 * (1.0 if dtype == "f32" else 0.5)
+    fp = {"achieved_tflops_algorithmic": fp_achieved, "peak_tflops_nominal": fp_peak, "frac": fp_achieved / fp_peak,
+          "note": "algorithmic flops/iteration from SURVEY 8d x measured mean iterations; nominal FMA-pipe peak at max clock"}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        sample = min(CPU_SAMPLE[name], batch)
+        out, dt, cores, kind_note = cpu_reference(name, inp, sample)
+        cpu = {"value": sample / dt, "unit": "problems/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} problems of the same inputs, one pass; {kind_note}"}
+        gv = sol.value[:sample].cpu().numpy()
+        tol = 1e-4 if dtype == "f32" else 1e-8
+        scaled = np.max(np.abs(gv - out["value"]) / (tol + tol * np.abs(out["value"])), axis=1)
+        checks["gpu_vs_cpu_port_within_tol_frac"] = float(np.mean(scaled <= 1.0))
+        checks["cpu_port_mean_num_steps"] = float(out["num_steps"].mean())
+
+    line = {"metric": "LM problems solved/sec" if name in ("gauss2", "exp_decay") else f"{name} problems solved/sec",
+            "value": value, "unit": "problems/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": config, "roofline": roofline, "fp": fp, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "checks": checks, "wall_ms_timed_region": wall_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

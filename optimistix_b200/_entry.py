@@ -72,15 +72,18 @@ class _Buf:
         return np.ascontiguousarray(x, dtype=self.ndtype)
 
     def empty(self, shape, like, dtype=None):
+        t = _torch()
         if self.device:
-            t = _torch()
             return t.empty(shape, dtype=dtype or self.tdtype, device=like.device)
-        return np.empty(shape, dtype=dtype or self.ndtype)
+        # host outputs are page-locked so the D2H copies of the chunk pipeline stay asynchronous
+        td = t.float32 if (dtype or self.ndtype) == np.float32 else t.float64
+        return t.empty(shape, dtype=td, pin_memory=t.cuda.is_available()).numpy()
 
     def empty_i32(self, shape, like):
+        t = _torch()
         if self.device:
-            return _torch().empty(shape, dtype=_torch().int32, device=like.device)
-        return np.empty(shape, dtype=np.int32)
+            return t.empty(shape, dtype=t.int32, device=like.device)
+        return t.empty(shape, dtype=t.int32, pin_memory=t.cuda.is_available()).numpy()
 
     @staticmethod
     def ptr(x):

@@ -1,5 +1,7 @@
 // C ABI of the B200 Optimistix hot path (declarations + reference citations: include/b200opt.h).
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -165,6 +167,9 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
   if (int e = validate_common("least_squares_host", dtype, batch, opts)) return e;
   if (batch == 0) return 0;
   if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return B200OPT_ECUDA;
+  const bool timing = getenv("B200OPT_HOST_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   const size_t es = dtype == B200OPT_F32 ? 4 : 8;
   if (chunk <= 0) chunk = 1 << 16;
   if (chunk > batch) chunk = batch;
@@ -188,6 +193,7 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
   }
   if (check_cuda(cudaMemcpy(d_shared, shared_args, es * shared_args_count, cudaMemcpyHostToDevice), "H2D shared"))
     return B200OPT_ECUDA;
+  const double t_alloc = now();
   const char* h_y0 = static_cast<const char*>(y0);
   const char* h_prob = static_cast<const char*>(problem_args);
   char* h_y = static_cast<char*>(y_out);
@@ -205,8 +211,15 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
     cudaMemcpyAsync(num_steps + off, d_steps[s], 4 * nb, cudaMemcpyDeviceToHost, hp.st[s]);
     cudaMemcpyAsync(result + off, d_res[s], 4 * nb, cudaMemcpyDeviceToHost, hp.st[s]);
   }
+  const double t_enq = now();
   for (int s = 0; s < 2; ++s)
     if (check_cuda(cudaStreamSynchronize(hp.st[s]), "least_squares_host sync")) return B200OPT_ECUDA;
+  if (timing) {
+    cudaPointerAttributes pa{};
+    cudaPointerGetAttributes(&pa, problem_args);
+    fprintf(stderr, "[b200opt host] alloc+shared %.2f ms, enqueue %.2f ms, drain %.2f ms, chunks %d, prob memtype %d (1=host-pinned, 0=unregistered)\n",
+            t_alloc - t_begin, t_enq - t_alloc, now() - t_enq, c, (int)pa.type);
+  }
   return 0;
 }
 

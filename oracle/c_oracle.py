@@ -1,0 +1,55 @@
+"""ctypes wrapper of oracle/c/liboracle.so (C + OpenMP restatement of the LM step; TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+_SO = os.path.join(_DIR, "liboracle.so")
+_lib = None
+MODELS = {"exp_decay": 0, "gauss2": 1}
+
+
+def build():
+    subprocess.run(["make", "-C", _DIR], check=True, capture_output=True)
+    return _SO
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_lm_solve.restype = C.c_int
+        _lib.oracle_lm_solve.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int]
+        _lib.oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+def max_threads() -> int:
+    return load().oracle_max_threads()
+
+
+def levenberg_marquardt(model: str, y0, x, d, *, rtol, atol, max_steps=256, linsolve="qr", nthreads=0):
+    lib = load()
+    y0 = np.ascontiguousarray(y0)
+    dt = y0.dtype
+    x = np.ascontiguousarray(x, dtype=dt)
+    d = np.ascontiguousarray(d, dtype=dt)
+    B, n = y0.shape
+    m = x.shape[0]
+    y = np.empty_like(y0)
+    steps = np.empty(B, np.int32)
+    res = np.empty(B, np.int32)
+    rc = lib.oracle_lm_solve(MODELS[model], 1 if dt == np.float64 else 0, B, n, m, y0.ctypes.data, x.ctypes.data, d.ctypes.data,
+                             d.shape[1], rtol, atol, max_steps, 0 if linsolve == "qr" else 1, y.ctypes.data, steps.ctypes.data,
+                             res.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_lm_solve failed: {rc}")
+    return dict(value=y, num_steps=steps, result=res)

@@ -173,6 +173,11 @@ def gauss_newton_family(
     num_steps = np.zeros(B, np.int32)
     num_accepted = np.zeros(B, np.int32)
     lm = search == "trust_region"
+    # Not part of the reference: the smallest distance of any accept/good/terminate comparison from its
+    # threshold, in units of the rounding noise of the quantities compared.  A problem whose margin is
+    # large takes the same branches under ANY faithful floating-point evaluation order; one whose margin
+    # is O(1) has a coin-flip iteration count (see DESIGN.md "iteration-count parity").
+    margin = np.full(B, np.inf)
 
     with np.errstate(all="ignore"):
         for _ in range(max_steps):
@@ -197,12 +202,20 @@ def gauss_newton_family(
                 mul = np.where(good, dt.type(3.5), dt.type(1.0))
                 mul = np.where(accept, mul, dt.type(0.25))
                 new_delta = mul * delta
+                noise = fi.eps * np.maximum(f_min, f_min_eval) + fi.tiny
+                mg = np.minimum(np.abs(df - dt.type(0.01) * pred), np.abs(df - dt.type(0.99) * pred)) / noise
+                mg = np.where(first, np.inf, mg)
+                margin = np.where(active, np.minimum(margin, mg), margin)
             else:
                 accept = np.ones(B, bool)  # learning_rate.py:24-35
                 new_delta = np.ones(B, dt)
             # gauss_newton.py:276-296 accepted/rejected branches
             term_acc = cauchy_termination(rtol, atol, nrm, y_eval, d, r_e, r_e - r)
             new_terminate = np.where(accept, term_acc, False)
+            yn_ = nrm(np.abs(d) / (atol + rtol * np.abs(y_eval)))
+            fn_ = nrm(np.abs(r_e - r) / (atol + rtol * np.abs(r_e)))
+            mt = np.minimum(np.abs(yn_ - 1), np.abs(fn_ - 1)) / (64 * fi.eps)
+            margin = np.where(active & accept, np.minimum(margin, mt), margin)
             y_new = _freeze(accept, y_eval, y)
             r_new = _freeze(accept, r_e, r)
             J_new = _freeze(accept, J_e, J)
@@ -250,7 +263,7 @@ def gauss_newton_family(
             num_steps = num_steps + active
     # _iterate.py:253-257
     result = np.where((result == OK) & ~terminate, MAXSTEPS, result)
-    return dict(value=y, num_steps=num_steps, result=result, step_size=delta, num_accepted=num_accepted)
+    return dict(value=y, num_steps=num_steps, result=result, step_size=delta, num_accepted=num_accepted, margin=margin)
 
 
 def levenberg_marquardt(model, y0, args, **kw):
