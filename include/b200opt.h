@@ -21,8 +21,9 @@
  *     `stream` (a cudaStream_t) and never synchronises, so it can be called from an XLA FFI handler.
  *   - the `_host` entry points take HOST pointers, copy in/out themselves (chunked, double-buffered over
  *     two streams) and return when the results are in the output buffers.
- *   - the caller owns every buffer; the library keeps no global mutable state and allocates nothing
- *     persistent (the `_host` variants allocate and free their staging buffers per call).
+ *   - the caller owns every buffer.  The device-pointer entry points keep no state and allocate nothing.
+ *     The `_host` variants keep per-host-thread staging (two streams, device slabs, page-locked bounce
+ *     buffers; grow-only) between calls; b200opt_host_cache_release() frees it for the calling thread.
  *   - return value: 0 on success, a negative B200OPT_E* code otherwise; b200opt_last_error() gives the
  *     message for the calling thread.  Per-problem outcomes go to `result[]` using the member names of
  *     optimistix.RESULTS (optimistix/_solution.py:11-20; compare by NAME, b200opt_result_name()).
@@ -151,6 +152,7 @@ int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id,
                                int32_t n, const void* y0, const void* shared_args, int64_t shared_args_count,
                                const void* problem_args, int64_t problem_args_stride, const b200opt_options_t* opts,
                                void* y_out, int32_t* num_steps, int32_t* result, int64_t chunk);
+void b200opt_host_cache_release(void);
 int32_t b200opt_minimise_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
                               const void* y0, const void* shared_args, int64_t shared_args_count,
                               const void* problem_args, int64_t problem_args_stride, const b200opt_options_t* opts,

@@ -75,15 +75,14 @@ class _Buf:
         t = _torch()
         if self.device:
             return t.empty(shape, dtype=dtype or self.tdtype, device=like.device)
-        # host outputs are page-locked so the D2H copies of the chunk pipeline stay asynchronous
-        td = t.float32 if (dtype or self.ndtype) == np.float32 else t.float64
-        return t.empty(shape, dtype=td, pin_memory=t.cuda.is_available()).numpy()
+        # plain pageable outputs: the C host pipeline bounces D2H through its own cached page-locked buffers
+        return np.empty(shape, dtype=dtype or self.ndtype)
 
     def empty_i32(self, shape, like):
         t = _torch()
         if self.device:
             return t.empty(shape, dtype=t.int32, device=like.device)
-        return t.empty(shape, dtype=t.int32, pin_memory=t.cuda.is_available()).numpy()
+        return np.empty(shape, dtype=np.int32)
 
     @staticmethod
     def ptr(x):

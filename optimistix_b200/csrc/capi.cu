@@ -1,5 +1,4 @@
 // C ABI of the B200 Optimistix hot path (declarations + reference citations: include/b200opt.h).
-#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -78,21 +77,156 @@ static int validate_common(const char* who, int dtype, int64_t batch, const b200
 }
 
 // ---- chunked host pipeline shared by the *_host entry points --------------------------------------------------
-struct HostPipe {
+// Two streams, each with its own device staging buffers: chunk c+1's H2D overlaps chunk c's kernel and chunk
+// c-1's D2H.  Page-locked caller memory is copied directly; pageable OUTPUT arrays go through page-locked bounce
+// buffers so that no D2H ever blocks the enqueueing thread (a blocking copy would serialise the pipeline).
+// The staging buffers are cached per host thread (grow-only) and released by b200opt_host_cache_release().
+struct HostCache {
+  int device = -1;
   cudaStream_t st[2] = {nullptr, nullptr};
-  std::vector<void*> allocs;
-  ~HostPipe() {
-    for (auto s : st)
-      if (s) cudaStreamDestroy(s);
-    for (auto a : allocs) cudaFree(a);
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  void* dev[2] = {nullptr, nullptr};
+  size_t dev_bytes = 0;
+  void* pin[2] = {nullptr, nullptr};
+  size_t pin_bytes = 0;
+  void* shared = nullptr;
+  size_t shared_bytes = 0;
+  void release() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    for (int s = 0; s < 2; ++s) {
+      if (st[s]) cudaStreamDestroy(st[s]);
+      if (done[s]) cudaEventDestroy(done[s]);
+      if (dev[s]) cudaFree(dev[s]);
+      if (pin[s]) cudaFreeHost(pin[s]);
+      st[s] = nullptr, done[s] = nullptr, dev[s] = nullptr, pin[s] = nullptr;
+    }
+    if (shared) cudaFree(shared);
+    shared = nullptr;
+    dev_bytes = pin_bytes = shared_bytes = 0;
+    device = -1;
   }
-  void* alloc(size_t bytes) {
-    void* ptr = nullptr;
-    if (cudaMalloc(&ptr, bytes ? bytes : 1) != cudaSuccess) return nullptr;
-    allocs.push_back(ptr);
-    return ptr;
-  }
+  ~HostCache() { /* process teardown: the CUDA context may already be gone; leak rather than crash */ }
 };
+static thread_local HostCache g_host;
+
+struct HostIn {
+  const void* h;
+  size_t bytes_per_problem;
+};
+struct HostOut {
+  void* h;
+  size_t bytes_per_problem;
+};
+
+static bool is_pinned(const void* ptr) {
+  cudaPointerAttributes pa{};
+  if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// launch(nb, d_shared, d_in[], d_out[], stream) enqueues the solve of one chunk.
+template <class Launch>
+static int host_pipeline(const char* who, int device, int64_t batch, int64_t chunk, const void* shared_h, size_t shared_bytes,
+                         const std::vector<HostIn>& ins, const std::vector<HostOut>& outs, Launch launch) {
+  if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return B200OPT_ECUDA;
+  HostCache& hc = g_host;
+  if (hc.device != device) {
+    hc.release();
+    hc.device = device;
+    for (int s = 0; s < 2; ++s) {
+      if (check_cuda(cudaStreamCreateWithFlags(&hc.st[s], cudaStreamNonBlocking), "stream create")) return B200OPT_ECUDA;
+      if (check_cuda(cudaEventCreateWithFlags(&hc.done[s], cudaEventDisableTiming), "event create")) return B200OPT_ECUDA;
+    }
+  }
+  if (chunk <= 0) chunk = 1 << 16;
+  if (chunk > batch) chunk = batch;
+  // carve one device slab and one pinned slab per stream
+  std::vector<size_t> in_off(ins.size()), out_off(outs.size()), bounce_off(outs.size());
+  std::vector<bool> out_pinned(outs.size());
+  size_t dev_need = 0, pin_need = 0;
+  for (size_t i = 0; i < ins.size(); ++i) in_off[i] = dev_need, dev_need += align256(ins[i].bytes_per_problem * chunk);
+  for (size_t i = 0; i < outs.size(); ++i) {
+    out_off[i] = dev_need, dev_need += align256(outs[i].bytes_per_problem * chunk);
+    out_pinned[i] = is_pinned(outs[i].h);
+    if (!out_pinned[i]) bounce_off[i] = pin_need, pin_need += align256(outs[i].bytes_per_problem * chunk);
+  }
+  if (dev_need > hc.dev_bytes) {
+    for (int s = 0; s < 2; ++s) {
+      if (hc.dev[s]) cudaFree(hc.dev[s]);
+      hc.dev[s] = nullptr;
+      if (check_cuda(cudaMalloc(&hc.dev[s], dev_need), "staging cudaMalloc")) return hc.dev_bytes = 0, B200OPT_ECUDA;
+    }
+    hc.dev_bytes = dev_need;
+  }
+  if (pin_need > hc.pin_bytes) {
+    for (int s = 0; s < 2; ++s) {
+      if (hc.pin[s]) cudaFreeHost(hc.pin[s]);
+      hc.pin[s] = nullptr;
+      if (check_cuda(cudaMallocHost(&hc.pin[s], pin_need), "bounce cudaMallocHost")) return hc.pin_bytes = 0, B200OPT_ECUDA;
+    }
+    hc.pin_bytes = pin_need;
+  }
+  if (shared_bytes > hc.shared_bytes) {
+    if (hc.shared) cudaFree(hc.shared);
+    hc.shared = nullptr;
+    if (check_cuda(cudaMalloc(&hc.shared, shared_bytes), "shared cudaMalloc")) return hc.shared_bytes = 0, B200OPT_ECUDA;
+    hc.shared_bytes = shared_bytes;
+  }
+  if (shared_bytes) {
+    if (check_cuda(cudaMemcpyAsync(hc.shared, shared_h, shared_bytes, cudaMemcpyHostToDevice, hc.st[0]), "H2D shared"))
+      return B200OPT_ECUDA;
+    cudaEventRecord(hc.done[0], hc.st[0]);
+    cudaStreamWaitEvent(hc.st[1], hc.done[0], 0);
+  }
+  struct Pending {
+    int64_t off = -1, nb = 0;
+  } pending[2];
+  auto drain = [&](int s) -> int {  // copy stream s's finished bounce buffers into the caller's pageable arrays
+    if (pending[s].off < 0) return 0;
+    if (check_cuda(cudaEventSynchronize(hc.done[s]), who)) return B200OPT_ECUDA;
+    for (size_t i = 0; i < outs.size(); ++i)
+      if (!out_pinned[i])
+        memcpy(static_cast<char*>(outs[i].h) + outs[i].bytes_per_problem * pending[s].off,
+               static_cast<char*>(hc.pin[s]) + bounce_off[i], outs[i].bytes_per_problem * pending[s].nb);
+    pending[s].off = -1;
+    return 0;
+  };
+  std::vector<const void*> d_in(ins.size());
+  std::vector<void*> d_out(outs.size());
+  int c = 0;
+  for (int64_t off = 0; off < batch; off += chunk, ++c) {
+    const int s = c & 1;
+    const int64_t nb = (batch - off < chunk) ? batch - off : chunk;
+    if (int e = drain(s)) return e;  // the bounce buffers of this stream are about to be reused
+    char* base = static_cast<char*>(hc.dev[s]);
+    for (size_t i = 0; i < ins.size(); ++i) {
+      d_in[i] = base + in_off[i];
+      if (ins[i].bytes_per_problem)
+        cudaMemcpyAsync(base + in_off[i], static_cast<const char*>(ins[i].h) + ins[i].bytes_per_problem * off,
+                        ins[i].bytes_per_problem * nb, cudaMemcpyHostToDevice, hc.st[s]);
+    }
+    for (size_t i = 0; i < outs.size(); ++i) d_out[i] = base + out_off[i];
+    if (int e = launch(nb, hc.shared, d_in.data(), d_out.data(), hc.st[s])) return e;
+    for (size_t i = 0; i < outs.size(); ++i) {
+      void* dst = out_pinned[i] ? static_cast<void*>(static_cast<char*>(outs[i].h) + outs[i].bytes_per_problem * off)
+                                : static_cast<void*>(static_cast<char*>(hc.pin[s]) + bounce_off[i]);
+      cudaMemcpyAsync(dst, d_out[i], outs[i].bytes_per_problem * nb, cudaMemcpyDeviceToHost, hc.st[s]);
+    }
+    cudaEventRecord(hc.done[s], hc.st[s]);
+    pending[s].off = off, pending[s].nb = nb;
+  }
+  for (int s = 0; s < 2; ++s) {
+    if (int e = drain(s)) return e;
+    if (check_cuda(cudaStreamSynchronize(hc.st[s]), who)) return B200OPT_ECUDA;
+  }
+  return check_cuda(cudaGetLastError(), who);
+}
 
 }  // namespace b200opt
 
@@ -166,61 +300,41 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
                                    int64_t chunk) {
   if (int e = validate_common("least_squares_host", dtype, batch, opts)) return e;
   if (batch == 0) return 0;
-  if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return B200OPT_ECUDA;
-  const bool timing = getenv("B200OPT_HOST_TIMING") != nullptr;
-  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t_begin = now();
+  if (!y0 || !shared_args || !problem_args || !y_out || !num_steps || !result) {
+    set_error("least_squares_host: NULL buffer");
+    return B200OPT_EINVAL;
+  }
   const size_t es = dtype == B200OPT_F32 ? 4 : 8;
-  if (chunk <= 0) chunk = 1 << 16;
-  if (chunk > batch) chunk = batch;
-  HostPipe hp;
-  void* d_shared = hp.alloc(es * shared_args_count);
-  void *d_y0[2], *d_prob[2], *d_y[2];
-  int32_t *d_steps[2], *d_res[2];
-  bool ok = d_shared != nullptr;
-  for (int s = 0; s < 2 && ok; ++s) {
-    ok = ok && cudaStreamCreateWithFlags(&hp.st[s], cudaStreamNonBlocking) == cudaSuccess;
-    d_y0[s] = hp.alloc(es * chunk * n);
-    d_prob[s] = hp.alloc(es * chunk * problem_args_stride);
-    d_y[s] = hp.alloc(es * chunk * n);
-    d_steps[s] = static_cast<int32_t*>(hp.alloc(4 * chunk));
-    d_res[s] = static_cast<int32_t*>(hp.alloc(4 * chunk));
-    ok = ok && d_y0[s] && d_prob[s] && d_y[s] && d_steps[s] && d_res[s];
+  return host_pipeline(
+      "least_squares_host", device, batch, chunk, shared_args, es * shared_args_count,
+      {{y0, es * n}, {problem_args, es * (size_t)problem_args_stride}}, {{y_out, es * n}, {num_steps, 4}, {result, 4}},
+      [&](int64_t nb, const void* d_shared, const void** d_in, void** d_out, cudaStream_t st) {
+        return b200opt_least_squares(solver, model_id, dtype, nb, n, m, d_in[0], d_shared, d_in[1], problem_args_stride, opts,
+                                     d_out[0], static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), nullptr,
+                                     nullptr, st);
+      });
+}
+
+void b200opt_host_cache_release(void) { g_host.release(); }
+
+int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
+                               const void* y0, const void* shared_args, int64_t shared_args_count, const void* problem_args,
+                               int64_t problem_args_stride, const b200opt_options_t* opts, void* y_out, int32_t* num_steps,
+                               int32_t* result, int64_t chunk) {
+  if (int e = validate_common("root_find_host", dtype, batch, opts)) return e;
+  if (batch == 0) return 0;
+  if (!y0 || !shared_args || !problem_args || !y_out || !num_steps || !result) {
+    set_error("root_find_host: NULL buffer");
+    return B200OPT_EINVAL;
   }
-  if (!ok) {
-    set_error("least_squares_host: device allocation failed");
-    return B200OPT_ECUDA;
-  }
-  if (check_cuda(cudaMemcpy(d_shared, shared_args, es * shared_args_count, cudaMemcpyHostToDevice), "H2D shared"))
-    return B200OPT_ECUDA;
-  const double t_alloc = now();
-  const char* h_y0 = static_cast<const char*>(y0);
-  const char* h_prob = static_cast<const char*>(problem_args);
-  char* h_y = static_cast<char*>(y_out);
-  int c = 0;
-  for (int64_t off = 0; off < batch; off += chunk, ++c) {
-    const int s = c & 1;
-    const int64_t nb = (batch - off < chunk) ? batch - off : chunk;
-    cudaMemcpyAsync(d_y0[s], h_y0 + es * off * n, es * nb * n, cudaMemcpyHostToDevice, hp.st[s]);
-    cudaMemcpyAsync(d_prob[s], h_prob + es * off * problem_args_stride, es * nb * problem_args_stride,
-                    cudaMemcpyHostToDevice, hp.st[s]);
-    int e = b200opt_least_squares(solver, model_id, dtype, nb, n, m, d_y0[s], d_shared, d_prob[s], problem_args_stride,
-                                  opts, d_y[s], d_steps[s], d_res[s], nullptr, nullptr, hp.st[s]);
-    if (e) return e;
-    cudaMemcpyAsync(h_y + es * off * n, d_y[s], es * nb * n, cudaMemcpyDeviceToHost, hp.st[s]);
-    cudaMemcpyAsync(num_steps + off, d_steps[s], 4 * nb, cudaMemcpyDeviceToHost, hp.st[s]);
-    cudaMemcpyAsync(result + off, d_res[s], 4 * nb, cudaMemcpyDeviceToHost, hp.st[s]);
-  }
-  const double t_enq = now();
-  for (int s = 0; s < 2; ++s)
-    if (check_cuda(cudaStreamSynchronize(hp.st[s]), "least_squares_host sync")) return B200OPT_ECUDA;
-  if (timing) {
-    cudaPointerAttributes pa{};
-    cudaPointerGetAttributes(&pa, problem_args);
-    fprintf(stderr, "[b200opt host] alloc+shared %.2f ms, enqueue %.2f ms, drain %.2f ms, chunks %d, prob memtype %d (1=host-pinned, 0=unregistered)\n",
-            t_alloc - t_begin, t_enq - t_alloc, now() - t_enq, c, (int)pa.type);
-  }
-  return 0;
+  const size_t es = dtype == B200OPT_F32 ? 4 : 8;
+  return host_pipeline(
+      "root_find_host", device, batch, chunk, shared_args, es * shared_args_count,
+      {{y0, es * n}, {problem_args, es * (size_t)problem_args_stride}}, {{y_out, es * n}, {num_steps, 4}, {result, 4}},
+      [&](int64_t nb, const void* d_shared, const void** d_in, void** d_out, cudaStream_t st) {
+        return b200opt_root_find(solver, model_id, dtype, nb, n, d_in[0], d_shared, d_in[1], problem_args_stride, nullptr,
+                                 nullptr, opts, d_out[0], static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), st);
+      });
 }
 
 }  // extern "C"

@@ -40,6 +40,8 @@ template <> struct Num<double> {
 
 __device__ __forceinline__ float t_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double t_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ float t_exp(float x) { return expf(x); }
 __device__ __forceinline__ double t_exp(double x) { return exp(x); }
 __device__ __forceinline__ float t_abs(float x) { return fabsf(x); }
@@ -64,29 +66,6 @@ template <typename T> __device__ __forceinline__ T warp_nanmax(T v) {
   for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(kFull, v, o));
   return v;
 }
-
-// Sum K per-lane partials across the warp and leave all K totals in every lane.
-// Staged through shared memory: K stores, ceil(K/32) column sums of 32 loads, K broadcast loads
-// (vs 5 shuffles + 5 adds per value for a butterfly).  Summation order is fixed (lane 0..31).
-// `sm` must hold 32*(K|1) + K elements for this warp.
-template <typename T, int K> __device__ __forceinline__ void warp_allreduce_array(T (&v)[K], T* sm, int lane) {
-  constexpr int KP = K | 1;  // odd row pitch: conflict-free stores and column reads
-#pragma unroll
-  for (int k = 0; k < K; ++k) sm[lane * KP + k] = v[k];
-  __syncwarp();
-  T* tot = sm + 32 * KP;
-  for (int c = lane; c < K; c += 32) {
-    T a = T(0);
-#pragma unroll
-    for (int l = 0; l < 32; ++l) a += sm[l * KP + c];
-    tot[c] = a;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = tot[k];
-  __syncwarp();
-}
-template <typename T, int K> constexpr int warp_allreduce_scratch() { return 32 * (K | 1) + K; }
 
 // ---- norms over a small per-lane-replicated vector and over warp-distributed rows -----------------------------
 // acc_* implement max_norm / two_norm / rms_norm (lineax.internal, re-exported at optimistix/_misc.py:41-45)
@@ -124,7 +103,7 @@ __device__ __forceinline__ void spd_solve(const T (&G)[Tri<N>::size], T lam, con
     T s = G[Tri<N>::at(j, j)] + lam;
 #pragma unroll
     for (int k = 0; k < j; ++k) s -= L[Tri<N>::at(j, k)] * L[Tri<N>::at(j, k)];
-    const T inv = T(1) / t_sqrt(s);  // s <= 0 or NaN -> NaN -> reported as `singular` by the caller
+    const T inv = t_rsqrt(s);  // s < 0 or NaN -> NaN, s == 0 -> inf: reported as `singular` by the caller
     L[Tri<N>::at(j, j)] = inv;
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {

@@ -8,9 +8,11 @@
 //   termination   optimistix/_misc.py:291-310
 //
 // B200 design (not a translation):
-//   * the whole solve of a problem stays in one warp's registers: y, y_eval, the accepted residuals of
-//     this lane's rows, the packed Gram matrix G = J^T J and g = J^T r.  HBM is touched twice per problem:
-//     one coalesced (128-bit where aligned) read of y0/data, one write of y/num_steps/result.
+//   * the whole solve of a problem stays on chip.  Registers (replicated in every lane): y, y_eval, the packed
+//     Gram matrix G = J^T J, g = J^T r, the radius.  Shared memory (per warp, lane-interleaved so every access is
+//     conflict free): this problem's data row, the accepted and the trial residuals (ping-pong), the model's
+//     cached per-row intermediates.  HBM is touched twice per problem: one coalesced (128-bit where aligned)
+//     read of y0/data, one write of y/num_steps/result.
 //   * J is never materialised.  The accepted (r, J) of the reference is carried as (r, G, g, r^T r): the
 //     predicted reduction 0.5(|J d + r|^2 - |r|^2) of trust_region.py:182-186 is evaluated as the
 //     algebraically identical  d.g + 0.5 d.G d,  and the augmented QR solve of
@@ -19,7 +21,8 @@
 //   * the Jacobian/Gram pass only runs for ACCEPTED trial points (the reference linearises every step and
 //     discards rejected ones; values are identical, work is not).
 //   * warp-uniform control flow: one problem per warp means accept/reject and the iteration count never
-//     diverge inside a warp.
+//     diverge inside a warp.  Row loops are rolled (rows live in shared memory, not in registers), which keeps
+//     the kernel at ~100 registers (16 resident warps/SM) and inside the instruction cache for any m.
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
@@ -38,6 +41,7 @@ template <typename T> struct LsqParams {
   int32_t* num_accepted;   // optional
   int64_t batch;
   int m;
+  int m_pad;               // m rounded up to a multiple of 32 (row pitch of the per-warp shared arrays)
   T rtol, atol;
   int norm;
   int max_steps;
@@ -47,80 +51,133 @@ template <typename T> struct LsqParams {
 
 constexpr int kLsqWarpsPerBlock = 4;
 
-template <class Model, typename T, int RPL> constexpr int lsq_smem_elems_per_warp() {
-  return warp_allreduce_scratch<T, Tri<Model::N>::size + Model::N>();
+// ---- warp all-reduce of K per-lane partial sums through shared memory, 128-bit accesses ---------------------------
+// Layout: row `lane` of the scratch holds that lane's K partials (pitch KP chosen so 128-bit row accesses of the
+// 8 lanes of a quarter-warp fall in distinct bank groups).  Column sums: lane (q, h) sums quad-column q over the
+// rows of half h in {0,1} (rows h*16 .. h*16+15), halves are combined with one shuffle, totals are written once
+// and read back by every lane as broadcasts.  Order of additions is fixed (deterministic results).
+template <typename T, int K> struct WarpReduceLayout {
+  static constexpr int V = 16 / sizeof(T);                       // elements per 128-bit access
+  static constexpr int KQ = (K + V - 1) / V;                     // quads per row
+  static constexpr int KPAD = KQ * V;
+  static constexpr int KP = KPAD + V * ((KQ % 2 == 0) ? 1 : 0);  // odd number of quads per row -> conflict free
+  static constexpr int elems = 32 * KP + KPAD;
+};
+
+template <typename T, int K> __device__ __forceinline__ void warp_allreduce_array(T (&v)[K], T* sm, int lane) {
+  using L = WarpReduceLayout<T, K>;
+  using Vec = typename Num<T>::Vec;
+  constexpr int V = L::V;
+  T* row = sm + lane * L::KP;
+#pragma unroll
+  for (int q = 0; q < L::KQ; ++q) {
+    Vec w;
+    T* ww = reinterpret_cast<T*>(&w);
+#pragma unroll
+    for (int e = 0; e < V; ++e) ww[e] = (q * V + e < K) ? v[q * V + e] : T(0);
+    *reinterpret_cast<Vec*>(row + q * V) = w;
+  }
+  __syncwarp();
+  T* tot = sm + 32 * L::KP;
+  // lanes 0-15 sum rows 0-15 of quad-column q, lanes 16-31 rows 16-31 of the same quad (a quarter-warp reads 8
+  // consecutive quads of one row: conflict free); the halves meet through one xor-16 shuffle per element.
+  for (int qb = 0; qb < L::KQ; qb += 16) {
+    const int q = qb + (lane & 15), h = lane >> 4;
+    const bool on = q < L::KQ;
+    const unsigned mask = __ballot_sync(kFull, on);
+    if (on) {
+      T a[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) a[e] = T(0);
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const Vec w = *reinterpret_cast<const Vec*>(sm + (h * 16 + l) * L::KP + q * V);
+        const T* ww = reinterpret_cast<const T*>(&w);
+#pragma unroll
+        for (int e = 0; e < V; ++e) a[e] += ww[e];
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const T o = __shfl_xor_sync(mask, a[e], 16);
+        a[e] = (h == 0) ? a[e] + o : o + a[e];  // rows 0-15 first, then 16-31: same order in both halves
+      }
+      if (h == 0) {
+        Vec w;
+        T* ww = reinterpret_cast<T*>(&w);
+#pragma unroll
+        for (int e = 0; e < V; ++e) ww[e] = a[e];
+        *reinterpret_cast<Vec*>(tot + q * V) = w;
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < L::KQ; ++q) {
+    const Vec w = *reinterpret_cast<const Vec*>(tot + q * V);
+    const T* ww = reinterpret_cast<const T*>(&w);
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+      if (q * V + e < K) v[q * V + e] = ww[e];
+  }
+  __syncwarp();
 }
 
-// Row owned by (lane, k): vectorised layout when V > 1 so that a lane's V consecutive rows are one 128-bit load.
-template <int V> __device__ __forceinline__ int lsq_row_index(int k, int lane) {
-  return (k / V) * (32 * V) + lane * V + (k % V);
+// per-warp shared memory (in elements of T): reduction scratch | data d | residual A | residual B | aux[NAUX]
+template <class Model, typename T> __host__ __device__ constexpr int lsq_scratch_elems() {
+  return WarpReduceLayout<T, Tri<Model::N>::size + Model::N>::elems;
+}
+template <class Model, typename T> __host__ __device__ inline size_t lsq_smem_bytes(int m_pad) {
+  const size_t per_warp = lsq_scratch_elems<Model, T>() + (size_t)(3 + Model::NAUX) * m_pad;
+  return sizeof(T) * ((size_t)m_pad /* shared abscissa grid */ + kLsqWarpsPerBlock * per_warp);
 }
 
-template <class Model, typename T, int RPL, bool TRUST>
-__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32) lsq_solve_kernel(const LsqParams<T> p) {
+template <class Model, typename T, bool TRUST>
+__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 2)) lsq_solve_kernel(const LsqParams<T> p) {
   constexpr int N = Model::N;
   constexpr int NG = Tri<N>::size;
   constexpr int NAUX = Model::NAUX;
-  constexpr int V = (RPL >= Num<T>::kVec) ? Num<T>::kVec : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  T* scratch = reinterpret_cast<T*>(smem_raw) + warp_in_block * lsq_smem_elems_per_warp<Model, T, RPL>();
-  const int64_t warp0 = (int64_t)blockIdx.x * kLsqWarpsPerBlock + warp_in_block;
+  const int wib = threadIdx.x >> 5;
+  const int m = p.m, mp = p.m_pad;
+  T* xs = reinterpret_cast<T*>(smem_raw);
+  T* wbase = xs + mp + (size_t)wib * (lsq_scratch_elems<Model, T>() + (size_t)(3 + NAUX) * mp);
+  T* scratch = wbase;
+  T* ds = wbase + lsq_scratch_elems<Model, T>();
+  T* racc = ds + mp;       // residuals at the last accepted point
+  T* rtry = racc + mp;     // residuals at the trial point
+  T* auxs = rtry + mp;     // NAUX arrays of m_pad
+  const int64_t warp0 = (int64_t)blockIdx.x * kLsqWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kLsqWarpsPerBlock;
-  const int m = p.m;
   const T rtol = p.rtol, atol = p.atol;
+  const bool maxnorm = p.norm == B200OPT_NORM_MAX;
 
-  // abscissa grid for this lane's rows: identical for every problem, loaded once per warp
-  T xs[RPL];
-  T wgt[RPL];  // 1 for rows < m, 0 for the ragged tail (their clamped loads are multiplied away)
-#pragma unroll
-  for (int k = 0; k < RPL; ++k) {
-    const int i = lsq_row_index<V>(k, lane);
-    wgt[k] = (i < m) ? T(1) : T(0);
-    xs[k] = p.shared[i < m ? i : m - 1];
-  }
+  for (int i = threadIdx.x; i < mp; i += blockDim.x) xs[i] = p.shared[i < m ? i : m - 1];
+  __syncthreads();
 
   for (int64_t prob = warp0; prob < p.batch; prob += nwarps) {
-    // ---------------- load: y0 (broadcast) and this lane's data rows (coalesced; 128-bit when aligned)
+    // ---------------- load: y0 (broadcast) and the data row (coalesced; 128-bit when aligned) into shared memory
     T y[N], ye[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) y[j] = ye[j] = p.y0[prob * N + j];
-    CurveRow<T> rows[RPL];
+    for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);
     const T* drow = p.prob + prob * p.prob_stride;
-    if (V > 1 && p.vec_ok) {
+    if (p.vec_ok) {
       using Vec = typename Num<T>::Vec;
-#pragma unroll
-      for (int k = 0; k < RPL; k += V) {
-        const int i = lsq_row_index<V>(k, lane);
-        if (i < m) {
-          const Vec v = __ldg(reinterpret_cast<const Vec*>(drow + i));
-          const T* vv = reinterpret_cast<const T*>(&v);
-#pragma unroll
-          for (int q = 0; q < V; ++q) rows[k + q].d = vv[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < V; ++q) rows[k + q].d = T(0);
-        }
-      }
+      constexpr int V = Num<T>::kVec;
+      for (int i = lane; i < m / V; i += 32)
+        reinterpret_cast<Vec*>(ds)[i] = __ldg(reinterpret_cast<const Vec*>(drow) + i);
     } else {
-#pragma unroll
-      for (int k = 0; k < RPL; ++k) {
-        const int i = lsq_row_index<V>(k, lane);
-        rows[k].d = (i < m) ? __ldg(drow + i) : T(0);
-      }
+      for (int i = lane; i < m; i += 32) ds[i] = __ldg(drow + i);
     }
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) rows[k].x = xs[k];
+    for (int i = lane; i < mp; i += 32) racc[i] = T(0);
+    __syncwarp();
 
     // ---------------- init (gauss_newton.py:229-241, trust_region.py:75, _iterate.py:214-219)
-    T G[NG], g[N], r[RPL];
+    T G[NG], g[N];
 #pragma unroll
     for (int a = 0; a < NG; ++a) G[a] = T(0);
 #pragma unroll
     for (int j = 0; j < N; ++j) g[j] = T(0);
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) r[k] = T(0);
     T rr = T(0);
     T delta = T(1);
     bool first = true, terminate = false;
@@ -138,12 +195,15 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32) lsq_solve_kernel(const
 
       // ---- residual at the trial point (gauss_newton.py:253)
       const typename Model::Pre pre = Model::prepare(ye);
-      T re[RPL], aux[RPL][NAUX];
       T part = T(0);
+#pragma unroll 2
+      for (int i = lane; i < m; i += 32) {
+        T aux[NAUX];
+        const T r = Model::residual(ye, pre, CurveRow<T>{xs[i], ds[i]}, aux);
+        rtry[i] = r;
 #pragma unroll
-      for (int k = 0; k < RPL; ++k) {
-        re[k] = wgt[k] * Model::residual(ye, pre, rows[k], aux[k]);
-        part += re[k] * re[k];
+        for (int q = 0; q < NAUX; ++q) auxs[q * mp + i] = aux[q];
+        part += r * r;
       }
       const T rre = warp_sum(part);
 
@@ -174,52 +234,68 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32) lsq_solve_kernel(const
 
       // ---- accepted / rejected (gauss_newton.py:276-296)
       if (accept) {
-        NormAcc<T> yn(p.norm), fn(p.norm);
+        // y-space half of cauchy_termination (_misc.py:306-309). For max_norm, max_i(|d_i|/s_i) < 1 is evaluated
+        // as all_i(|d_i| < s_i): same truth value except when a quotient rounds to exactly 1; no divisions.
+        bool yconv;
+        if (maxnorm) {
+          yconv = true;
 #pragma unroll
-        for (int j = 0; j < N; ++j) yn.add(t_abs(d[j]) / (atol + rtol * t_abs(ye[j])));
+          for (int j = 0; j < N; ++j) yconv = yconv && (t_abs(d[j]) < atol + rtol * t_abs(ye[j]));
+        } else {
+          NormAcc<T> yn(p.norm);
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          const T q = t_abs(re[k] - r[k]) / (atol + rtol * t_abs(re[k]));
-          fn.add(wgt[k] != T(0) ? q : T(0));
-        }
-        fn.warp_combine();
-        terminate = (yn.finish(N) < T(1)) && (fn.finish(m) < T(1));  // _misc.py:306-310
-        if (p.root_near_zero) {
-          // _LstsqToRoot (_root_find.py:64-73): norm(residual at the PRE-step accepted y) < atol
-          NormAcc<T> zn(p.norm);
-#pragma unroll
-          for (int k = 0; k < RPL; ++k) zn.add(t_abs(first ? re[k] : r[k]));
-          zn.warp_combine();
-          terminate = terminate && (zn.finish(m) < atol);
+          for (int j = 0; j < N; ++j) yn.add(t_abs(d[j]) / (atol + rtol * t_abs(ye[j])));
+          yconv = yn.finish(N) < T(1);
         }
         ++naccept;
 #pragma unroll
         for (int j = 0; j < N; ++j) y[j] = ye[j];
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) r[k] = re[k];
         rr = rre;
-        // Gram pass at the newly accepted point: acc = [G (packed lower) | g]
+        // one fused pass over the rows at the newly accepted point: Jacobian row -> Gram/gradient partials,
+        // f-space half of the termination test, and (root_find through LM) the near-zero test.
         T acc[NG + N];
 #pragma unroll
         for (int a = 0; a < NG + N; ++a) acc[a] = T(0);
+        NormAcc<T> fn(p.norm), zn(p.norm);
+        bool fconv = true;
+#pragma unroll 2
+        for (int i = lane; i < m; i += 32) {
+          T aux[NAUX], j[N];
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          T j[N];
-          Model::jac_row(y, pre, rows[k], aux[k], j);
-#pragma unroll
-          for (int a = 0; a < N; ++a) j[a] *= wgt[k];
+          for (int q = 0; q < NAUX; ++q) aux[q] = auxs[q * mp + i];
+          const T re = rtry[i], ro = racc[i];
+          Model::jac_row(y, pre, CurveRow<T>{xs[i], T(0)}, aux, j);
 #pragma unroll
           for (int a = 0; a < N; ++a) {
 #pragma unroll
             for (int b = 0; b <= a; ++b) acc[Tri<N>::at(a, b)] += j[a] * j[b];
-            acc[NG + a] += j[a] * re[k];
+            acc[NG + a] += j[a] * re;
           }
+          const T fs = atol + rtol * t_abs(re);
+          if (maxnorm) fconv = fconv && (t_abs(re - ro) < fs);
+          else fn.add(t_abs(re - ro) / fs);
+          if (p.root_near_zero) zn.add(t_abs(first ? re : ro));
         }
         warp_allreduce_array<T, NG + N>(acc, scratch, lane);
 #pragma unroll
         for (int a = 0; a < NG; ++a) G[a] = acc[a];
 #pragma unroll
         for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
+        if (maxnorm) {
+          fconv = __all_sync(kFull, fconv);
+        } else {
+          fn.warp_combine();
+          fconv = fn.finish(m) < T(1);
+        }
+        terminate = yconv && fconv;  // _misc.py:310
+        if (p.root_near_zero) {
+          // _LstsqToRoot (_root_find.py:64-73): norm(residual at the PRE-step accepted y) < atol
+          zn.warp_combine();
+          terminate = terminate && (zn.finish(m) < atol);
+        }
+        T* t = racc;  // the trial residuals become the accepted ones
+        racc = rtry;
+        rtry = t;
       } else {
         terminate = false;
       }
@@ -251,6 +327,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32) lsq_solve_kernel(const
       if (p.step_size_out) p.step_size_out[prob] = delta;
       if (p.num_accepted) p.num_accepted[prob] = naccept;
     }
+    __syncwarp();
   }
 }
 

@@ -20,18 +20,27 @@ struct LsqArgs {
 
 int device_sm_count();
 
-template <class Model, typename T, int RPL, bool TRUST> int lsq_launch_one(const LsqParams<T>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel<Model, T, RPL, TRUST>;
-  const size_t smem = sizeof(T) * lsq_smem_elems_per_warp<Model, T, RPL>() * kLsqWarpsPerBlock;
-  static thread_local int blocks_per_sm = 0;  // per instantiation
-  if (blocks_per_sm == 0) {
-    if (smem > 48 * 1024)
-      if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
-        return B200OPT_ECUDA;
+template <class Model, typename T, bool TRUST> int lsq_launch_one(const LsqParams<T>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel<Model, T, TRUST>;
+  const size_t smem = lsq_smem_bytes<Model, T>(p.m_pad);
+  if (smem > 227 * 1024) {
+    set_error("least_squares: m=%d needs %zu bytes of shared memory per block (limit 227 KB)", p.m, smem);
+    return B200OPT_EINVAL;
+  }
+  static thread_local size_t smem_set = 0;     // per instantiation
+  static thread_local size_t occ_smem = ~size_t(0);
+  static thread_local int blocks_per_sm = 1;
+  if (smem > smem_set) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
+      return B200OPT_ECUDA;
+    smem_set = smem;
+  }
+  if (occ_smem != smem) {
     int occ = 0;
     if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy"))
       return B200OPT_ECUDA;
     blocks_per_sm = occ > 0 ? occ : 1;
+    occ_smem = smem;
   }
   const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;  // persistent: one resident wave, grid-stride
@@ -41,14 +50,7 @@ template <class Model, typename T, int RPL, bool TRUST> int lsq_launch_one(const
 }
 
 template <class Model, typename T, bool TRUST> int lsq_launch_rpl(const LsqParams<T>& p, cudaStream_t stream) {
-  const int m = p.m;
-  if (m <= 32) return lsq_launch_one<Model, T, 1, TRUST>(p, stream);
-  if (m <= 64) return lsq_launch_one<Model, T, 2, TRUST>(p, stream);
-  if (m <= 128) return lsq_launch_one<Model, T, 4, TRUST>(p, stream);
-  if (m <= 256) return lsq_launch_one<Model, T, 8, TRUST>(p, stream);
-  if (m <= 512) return lsq_launch_one<Model, T, 16, TRUST>(p, stream);
-  set_error("least_squares: m=%d exceeds the register-resident limit of 512 residuals per problem", m);
-  return B200OPT_EINVAL;
+  return lsq_launch_one<Model, T, TRUST>(p, stream);
 }
 
 template <template <typename> class ModelT, typename T> int lsq_launch_typed(const LsqArgs& a) {
@@ -69,6 +71,7 @@ template <template <typename> class ModelT, typename T> int lsq_launch_typed(con
   p.num_accepted = a.num_accepted;
   p.batch = a.batch;
   p.m = a.m;
+  p.m_pad = (a.m + 31) / 32 * 32;
   p.rtol = (T)a.opts->rtol;
   p.atol = (T)a.opts->atol;
   p.norm = a.opts->norm;

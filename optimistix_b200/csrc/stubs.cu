@@ -6,17 +6,9 @@ using namespace b200opt;
   set_error(name ": not implemented in this build"); \
   return B200OPT_ENOTIMPL;
 extern "C" {
-int32_t b200opt_root_find(int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, const void*, int64_t,
-                          const void*, const void*, const b200opt_options_t*, void*, int32_t*, int32_t*, void*) {
-  NOTIMPL("root_find")
-}
 int32_t b200opt_minimise(int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, const void*, int64_t,
                          const b200opt_options_t*, void*, int32_t*, int32_t*, void*, void*, int32_t*, void*) {
   NOTIMPL("minimise")
-}
-int32_t b200opt_root_find_host(int32_t, int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, int64_t,
-                               const void*, int64_t, const b200opt_options_t*, void*, int32_t*, int32_t*, int64_t) {
-  NOTIMPL("root_find_host")
 }
 int32_t b200opt_minimise_host(int32_t, int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, int64_t,
                               const void*, int64_t, const b200opt_options_t*, void*, int32_t*, int32_t*, int64_t) {
