@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gauss2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the BASELINE config)")
-    ap.add_argument("--chunk", type=int, default=1 << 16, help="problems per pipeline stage in the host entry point")
+    ap.add_argument("--chunk", type=int, default=1 << 15, help="problems per pipeline stage in the host entry point")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

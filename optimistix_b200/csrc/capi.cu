@@ -77,24 +77,25 @@ static int validate_common(const char* who, int dtype, int64_t batch, const b200
 }
 
 // ---- chunked host pipeline shared by the *_host entry points --------------------------------------------------
-// Two streams, each with its own device staging buffers: chunk c+1's H2D overlaps chunk c's kernel and chunk
-// c-1's D2H.  Page-locked caller memory is copied directly; pageable OUTPUT arrays go through page-locked bounce
+// kStreams streams, each with its own device staging buffers: chunk c+1's H2D overlaps chunk c's kernel and chunk
+// c-1's D2H; a ring deeper than 2 keeps the copy engines busy while the host drains a finished slot.  Page-locked caller memory is copied directly; pageable OUTPUT arrays go through page-locked bounce
 // buffers so that no D2H ever blocks the enqueueing thread (a blocking copy would serialise the pipeline).
 // The staging buffers are cached per host thread (grow-only) and released by b200opt_host_cache_release().
+constexpr int kStreams = 4;
 struct HostCache {
   int device = -1;
-  cudaStream_t st[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
-  void* dev[2] = {nullptr, nullptr};
+  cudaStream_t st[kStreams] = {};
+  cudaEvent_t done[kStreams] = {};
+  void* dev[kStreams] = {};
   size_t dev_bytes = 0;
-  void* pin[2] = {nullptr, nullptr};
+  void* pin[kStreams] = {};
   size_t pin_bytes = 0;
   void* shared = nullptr;
   size_t shared_bytes = 0;
   void release() {
     if (device < 0) return;
     cudaSetDevice(device);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
       if (st[s]) cudaStreamDestroy(st[s]);
       if (done[s]) cudaEventDestroy(done[s]);
       if (dev[s]) cudaFree(dev[s]);
@@ -139,12 +140,12 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   if (hc.device != device) {
     hc.release();
     hc.device = device;
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
       if (check_cuda(cudaStreamCreateWithFlags(&hc.st[s], cudaStreamNonBlocking), "stream create")) return B200OPT_ECUDA;
       if (check_cuda(cudaEventCreateWithFlags(&hc.done[s], cudaEventDisableTiming), "event create")) return B200OPT_ECUDA;
     }
   }
-  if (chunk <= 0) chunk = 1 << 16;
+  if (chunk <= 0) chunk = 1 << 15;
   if (chunk > batch) chunk = batch;
   // carve one device slab and one pinned slab per stream
   std::vector<size_t> in_off(ins.size()), out_off(outs.size()), bounce_off(outs.size());
@@ -157,7 +158,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     if (!out_pinned[i]) bounce_off[i] = pin_need, pin_need += align256(outs[i].bytes_per_problem * chunk);
   }
   if (dev_need > hc.dev_bytes) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
       if (hc.dev[s]) cudaFree(hc.dev[s]);
       hc.dev[s] = nullptr;
       if (check_cuda(cudaMalloc(&hc.dev[s], dev_need), "staging cudaMalloc")) return hc.dev_bytes = 0, B200OPT_ECUDA;
@@ -165,7 +166,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     hc.dev_bytes = dev_need;
   }
   if (pin_need > hc.pin_bytes) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStreams; ++s) {
       if (hc.pin[s]) cudaFreeHost(hc.pin[s]);
       hc.pin[s] = nullptr;
       if (check_cuda(cudaMallocHost(&hc.pin[s], pin_need), "bounce cudaMallocHost")) return hc.pin_bytes = 0, B200OPT_ECUDA;
@@ -182,11 +183,11 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     if (check_cuda(cudaMemcpyAsync(hc.shared, shared_h, shared_bytes, cudaMemcpyHostToDevice, hc.st[0]), "H2D shared"))
       return B200OPT_ECUDA;
     cudaEventRecord(hc.done[0], hc.st[0]);
-    cudaStreamWaitEvent(hc.st[1], hc.done[0], 0);
+    for (int s = 1; s < kStreams; ++s) cudaStreamWaitEvent(hc.st[s], hc.done[0], 0);
   }
   struct Pending {
     int64_t off = -1, nb = 0;
-  } pending[2];
+  } pending[kStreams];
   auto drain = [&](int s) -> int {  // copy stream s's finished bounce buffers into the caller's pageable arrays
     if (pending[s].off < 0) return 0;
     if (check_cuda(cudaEventSynchronize(hc.done[s]), who)) return B200OPT_ECUDA;
@@ -201,7 +202,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   std::vector<void*> d_out(outs.size());
   int c = 0;
   for (int64_t off = 0; off < batch; off += chunk, ++c) {
-    const int s = c & 1;
+    const int s = c % kStreams;
     const int64_t nb = (batch - off < chunk) ? batch - off : chunk;
     if (int e = drain(s)) return e;  // the bounce buffers of this stream are about to be reused
     char* base = static_cast<char*>(hc.dev[s]);
@@ -221,7 +222,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     cudaEventRecord(hc.done[s], hc.st[s]);
     pending[s].off = off, pending[s].nb = nb;
   }
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kStreams; ++s) {
     if (int e = drain(s)) return e;
     if (check_cuda(cudaStreamSynchronize(hc.st[s]), who)) return B200OPT_ECUDA;
   }
@@ -316,6 +317,27 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
 }
 
 void b200opt_host_cache_release(void) { g_host.release(); }
+
+int32_t b200opt_minimise_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
+                              const void* y0, const void* shared_args, int64_t shared_args_count, const void* problem_args,
+                              int64_t problem_args_stride, const b200opt_options_t* opts, void* y_out, int32_t* num_steps,
+                              int32_t* result, int64_t chunk) {
+  (void)shared_args, (void)shared_args_count, (void)problem_args, (void)problem_args_stride;
+  if (int e = validate_common("minimise_host", dtype, batch, opts)) return e;
+  if (batch == 0) return 0;
+  if (!y0 || !y_out || !num_steps || !result) {
+    set_error("minimise_host: NULL buffer");
+    return B200OPT_EINVAL;
+  }
+  const size_t es = dtype == B200OPT_F32 ? 4 : 8;
+  return host_pipeline("minimise_host", device, batch, chunk, nullptr, 0, {{y0, es * n}},
+                       {{y_out, es * n}, {num_steps, 4}, {result, 4}},
+                       [&](int64_t nb, const void*, const void** d_in, void** d_out, cudaStream_t st) {
+                         return b200opt_minimise(solver, model_id, dtype, nb, n, d_in[0], nullptr, nullptr, 0, opts, d_out[0],
+                                                 static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), nullptr,
+                                                 nullptr, nullptr, st);
+                       });
+}
 
 int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
                                const void* y0, const void* shared_args, int64_t shared_args_count, const void* problem_args,

@@ -6,14 +6,6 @@ using namespace b200opt;
   set_error(name ": not implemented in this build"); \
   return B200OPT_ENOTIMPL;
 extern "C" {
-int32_t b200opt_minimise(int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, const void*, int64_t,
-                         const b200opt_options_t*, void*, int32_t*, int32_t*, void*, void*, int32_t*, void*) {
-  NOTIMPL("minimise")
-}
-int32_t b200opt_minimise_host(int32_t, int32_t, int32_t, int32_t, int64_t, int32_t, const void*, const void*, int64_t,
-                              const void*, int64_t, const b200opt_options_t*, void*, int32_t*, int32_t*, int64_t) {
-  NOTIMPL("minimise_host")
-}
 int64_t b200opt_lsq_step_state_size(int32_t, int32_t, int32_t) { return -1; }
 int32_t b200opt_lsq_step_init(int32_t, int64_t, int32_t, int32_t, const void*, void*, void*, void*, int32_t*, int32_t*, void*) {
   NOTIMPL("lsq_step_init")

@@ -1,0 +1,116 @@
+"""Parity of the CUDA BFGS kernel (through the C ABI) against the oracle and the golden vectors. GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import optimistix_b200 as optx
+from optimistix_b200 import synthetic
+from oracle import models as M
+from oracle import solvers as S
+
+from .parity import compare, to_np
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _solve(y0, tol=1e-8, **kw):
+    return optx.minimise(optx.models.rosenbrock, optx.BFGS(tol, tol), torch.as_tensor(y0, device=DEV), None, throw=False, **kw)
+
+
+def test_bfgs_rosenbrock_vs_oracle():
+    """configs[3] shape (n=64, fp64, rtol=atol=1e-8, max_steps=4096) at an oracle-sized batch."""
+    w = synthetic.rosenbrock_batch(256)
+    sol = _solve(w["y0"], max_steps=4096)
+    ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, max_steps=4096)
+    s = compare(sol, ref, 1e-8, 1e-8, "bfgs rosenbrock n=64")
+    assert s["result_match"] == 1.0
+    # ~760 steps of a quasi-Newton recursion amplify rounding differences: counts differ problem by problem, the
+    # distribution and the minimiser do not.
+    assert abs(s["mean_steps"][0] - s["mean_steps"][1]) / s["mean_steps"][1] <= 0.05
+    f_gpu, _ = M.rosenbrock(to_np(sol.value))
+    f_ref, _ = M.rosenbrock(ref["value"])
+    same_basin = np.abs(f_gpu - f_ref) < 1e-6
+    assert same_basin.mean() >= 0.97
+    scaled = np.max(np.abs(to_np(sol.value) - ref["value"]) / (1e-8 + 1e-8 * np.abs(ref["value"])), axis=1)
+    print("[bfgs] same basin", same_basin.mean(), "scaled diff p50/p99 in basin", np.percentile(scaled[same_basin], [50, 99]))
+    # at the minimiser the gradient is ~0, so iterates agree far better than the termination scale suggests
+    assert np.percentile(np.abs(to_np(sol.value) - ref["value"])[same_basin].max(1), 99) < 1e-6
+    assert np.allclose(to_np(sol.state["f"]), f_gpu, rtol=1e-9, atol=1e-14)
+
+
+def test_bfgs_prefix_state_parity():
+    """First k steps: identical accept/reject sequence and iterates to rounding (before chaos sets in)."""
+    w = synthetic.rosenbrock_batch(128)
+    for k in (1, 2, 3, 5, 8, 12, 20, 40):
+        ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, max_steps=k)
+        sol = _solve(w["y0"], max_steps=k, return_hessian_inv=True)
+        nacc = to_np(sol.stats["num_accepted_steps"])
+        same = nacc == ref["num_accepted"]
+        rel = np.abs(to_np(sol.value) - ref["value"]).max(1) / (np.abs(ref["value"]).max(1))
+        hrel = np.abs(to_np(sol.state["hessian_inv"]) - ref["hessian_inv"]).reshape(128, -1).max(1) / np.abs(ref["hessian_inv"]).reshape(128, -1).max(1)
+        print(f"[bfgs prefix] k={k}: accept-count match {same.mean():.3f}, max rel iterate diff {rel[same].max():.3g}, max rel H diff {hrel[same].max():.3g}")
+        assert same.mean() >= (1.0 if k <= 12 else 0.95)
+        assert rel[same].max() <= 1e-9 * (1 + k * k)
+        assert hrel[same].max() <= 1e-8 * (1 + k * k)
+        assert (to_np(sol.result) == ref["result"]).all()
+
+
+def test_bfgs_golden():
+    g = np.load(os.path.join(G, "bfgs_rosenbrock_f64.npz"))
+    w = synthetic.rosenbrock_batch(64)
+    sol = _solve(w["y0"], max_steps=4096)
+    assert (to_np(sol.result) == g["result"]).all()
+    f_gpu, _ = M.rosenbrock(to_np(sol.value))
+    f_ref, _ = M.rosenbrock(g["value"])
+    assert (np.abs(f_gpu - f_ref) < 1e-6).mean() >= 0.95
+
+
+@pytest.mark.parametrize("n", [2, 3, 17, 32, 33, 63, 64])
+def test_bfgs_dimensions(n):
+    w = synthetic.rosenbrock_batch(32, n=n)
+    sol = _solve(w["y0"], max_steps=4096)
+    ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, max_steps=4096)
+    assert (to_np(sol.result) == ref["result"]).mean() >= 0.95
+    f_gpu, _ = M.rosenbrock(to_np(sol.value))
+    f_ref, _ = M.rosenbrock(ref["value"])
+    assert (np.abs(f_gpu - f_ref) < 1e-6).mean() >= 0.9
+
+
+def test_bfgs_classic_rosenbrock_known_answer():
+    """The textbook 2-D Rosenbrock start (-1.2, 1) -> (1, 1)."""
+    sol = optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), torch.tensor([-1.2, 1.0], dtype=torch.float64, device=DEV),
+                        None, max_steps=1024)
+    assert int(sol.result) == optx.RESULTS.successful
+    assert np.allclose(to_np(sol.value), [1.0, 1.0], atol=1e-6)
+
+
+def test_bfgs_max_steps_and_nonfinite():
+    """tests/test_compat.py:41-45 (maxiter -> max-steps status) and tests/test_solve.py:78-84 (nonfinite start)."""
+    w = synthetic.rosenbrock_batch(8)
+    sol = _solve(w["y0"], max_steps=2)
+    assert (to_np(sol.result) == optx.RESULTS.nonlinear_max_steps_reached).all() and (to_np(sol.stats["num_steps"]) == 2).all()
+    w["y0"][3, 10] = np.nan
+    sol = _solve(w["y0"], max_steps=64)
+    assert to_np(sol.result)[3] == optx.RESULTS.nonfinite and to_np(sol.stats["num_steps"])[3] == 0
+
+
+def test_bfgs_fp32():
+    """tests/test_minimise.py:229-234: fp32 BFGS runs."""
+    w = synthetic.rosenbrock_batch(64, n=16, dtype=np.float32)
+    sol = _solve(w["y0"], tol=1e-4, max_steps=4096)
+    ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-4, atol=1e-4, max_steps=4096)
+    f_gpu, _ = M.rosenbrock(to_np(sol.value).astype(np.float64))
+    f_ref, _ = M.rosenbrock(ref["value"].astype(np.float64))
+    assert (to_np(sol.result) == ref["result"]).mean() >= 0.9
+    assert (np.abs(f_gpu - f_ref) < 1e-3).mean() >= 0.9
+
+
+def test_bfgs_host_entry_point():
+    w = synthetic.rosenbrock_batch(100)
+    dev = _solve(w["y0"], max_steps=4096)
+    host = optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), w["y0"], None, throw=False, max_steps=4096, chunk=33)
+    assert np.array_equal(host.value, to_np(dev.value)) and np.array_equal(host.stats["num_steps"], to_np(dev.stats["num_steps"]))

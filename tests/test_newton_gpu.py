@@ -56,7 +56,7 @@ def test_newton_fp32():
     sol = _solve(w, optx.Newton(1e-4, 1e-4))
     ref = S.newton_chord(M.implicit_euler, w["y0"], w, rtol=1e-4, atol=1e-4)
     s = compare(sol, ref, 1e-4, 1e-4, "newton f32")
-    assert s["result_match"] >= 0.999 and s["within_tol"] >= 0.999 and s["steps_match"] >= 0.98
+    assert s["result_match"] >= 0.999 and s["within_tol"] >= 0.999 and s["steps_match"] >= 0.95
 
 
 @pytest.mark.parametrize("chord", [False, True], ids=["newton", "chord"])
