@@ -172,7 +172,8 @@ def _check_defaults(solver):
 
 # ------------------------------------------------------------------------------------------ least squares
 def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-                  adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), _root_near_zero=False, chunk: int = 0):
+                  adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), _root_near_zero=False, chunk: int = 0,
+                  args_in_dims=None):
     """Solve (a batch of) nonlinear least-squares problems. Reference: optimistix/_least_squares.py:44-135."""
     if isinstance(solver, AbstractMinimiser):
         raise NotImplementedError("least_squares through a minimiser (_least_squares.py:102-114) needs the generic path")
@@ -185,7 +186,8 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     if not isinstance(fn, RegisteredModel):
         from ._generic import least_squares_generic
 
-        return least_squares_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, root_near_zero=_root_near_zero)
+        return least_squares_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, root_near_zero=_root_near_zero,
+                                     options=options, args_in_dims=args_in_dims)
     if fn.kind != KIND_LSQ:
         raise TypeError(f"model {fn.name} is not a least-squares family")
     lib = _lib.load()
@@ -225,14 +227,15 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
 
 # ------------------------------------------------------------------------------------------ root find
 def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0):
+              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, args_in_dims=None):
     """Solve (a batch of) root-finding problems. Reference: optimistix/_root_find.py:119-241."""
     _check_common(fn, options, has_aux, adjoint)
     if max_steps is None:
         raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
     if isinstance(solver, AbstractLeastSquaresSolver):
         # _root_find.py:200-225: least-squares solver wrapped in _LstsqToRoot (extra `norm(f) < atol` test)
-        return least_squares(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, _root_near_zero=True, chunk=chunk)
+        return least_squares(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, _root_near_zero=True, chunk=chunk,
+                             args_in_dims=args_in_dims)
     if isinstance(solver, AbstractMinimiser):
         raise NotImplementedError("root_find through a minimiser (_root_find.py:176-199) needs the generic path")
     if not isinstance(solver, (Newton, Chord)):
@@ -314,7 +317,7 @@ def _pack_root_args(fn, a, buf, dev, B, n, single):
 
 # ------------------------------------------------------------------------------------------ fixed point
 def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-                adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset()):
+                adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), args_in_dims=None):
     """Find a fixed point. Reference: optimistix/_fixed_point.py:50-154: with a root finder / least-squares
     solver / minimiser this is `root_find` on `fn(y, args) - y` (:35-47, :115-129)."""
     if isinstance(fn, RegisteredModel):
@@ -329,7 +332,8 @@ def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_s
             raise ValueError("The input and output of `fixed_point_fn` must have the same structure")
         return out - y
 
-    return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, throw=throw)
+    return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, throw=throw,
+                     args_in_dims=args_in_dims)
 
 
 # ------------------------------------------------------------------------------------------ minimise

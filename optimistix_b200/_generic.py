@@ -1,0 +1,132 @@
+"""Generic path for an arbitrary user `fn`: the per-iteration CUDA step kernel fed caller-computed r and J.
+
+This is what makes the library a drop-in beyond the registered model families (SURVEY section 8f.1;
+BASELINE.json north_star: "for arbitrary user fn, a per-iteration step kernel is fed XLA-computed J and r").
+The reference obtains (r, J) with `jax.linearize` / `jax.jacrev` (optimistix/_solver/gauss_newton.py:158-181);
+here `torch.func.jacfwd` / `jacrev` plays that role (options["jac"] = "fwd" | "bwd"), batched with
+`torch.func.vmap`, and everything else of the step - search, accept/reject, Gram, damped Cholesky solve,
+termination, result codes - runs in `b200opt_lsq_step` (optimistix_b200/csrc/lsq_step.cu).
+
+`fn(y, args)` takes ONE problem: y of shape [n], returns residuals [m] (any shape; it is raveled).
+`args_in_dims` says which leaves of `args` carry the batch axis (torch.func.vmap in_dims for `args`;
+default None = shared by all problems), mirroring `jax.vmap(..., in_axes=...)` at the reference's call site.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._solution import RESULTS, Solution
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _batched_r_and_J(fn, args, args_in_dims, jac_mode, single):
+    t = _torch()
+
+    jacf = t.func.jacfwd if jac_mode == "fwd" else t.func.jacrev
+
+    if args_in_dims is None:
+        def one(y):
+            r = fn(y, args)
+            return r.reshape(-1)
+
+        def both(y):
+            J, r = jacf(lambda z: (one(z), one(z)), has_aux=True)(y)
+            return r, J
+
+        return t.func.vmap(both)
+
+    def one_a(y, a):
+        return fn(y, a).reshape(-1)
+
+    def both_a(y, a):
+        J, r = jacf(lambda z: (one_a(z, a), one_a(z, a)), has_aux=True)(y)
+        return r, J
+
+    vm = t.func.vmap(both_a, in_dims=(0, args_in_dims))
+    return lambda Y: vm(Y, args)
+
+
+def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_zero=False, options=None, args_in_dims=None):
+    """LM / GN for an arbitrary residual function (device tensors only: the Jacobian is evaluated by torch on the GPU)."""
+    from ._solvers import LevenbergMarquardt
+
+    t = _torch()
+    lib = _lib.load()
+    y0 = t.as_tensor(y0)
+    if not y0.is_cuda:
+        if not t.cuda.is_available():
+            raise _lib.B200OptError("the generic path needs a CUDA device (there is no CPU fallback)")
+        y0 = y0.cuda()
+    if not y0.dtype.is_floating_point:
+        y0 = y0.to(t.get_default_dtype())
+    if y0.dtype not in (t.float32, t.float64):
+        raise TypeError(f"unsupported dtype {y0.dtype}")
+    single = y0.ndim == 1
+    Y0 = (y0[None] if single else y0).contiguous()
+    B, n = Y0.shape
+    if n > 16:
+        raise NotImplementedError("generic least-squares step kernel supports n <= 16 parameters (register-resident Gram)")
+    dtype_code = _lib.F32 if y0.dtype == t.float32 else _lib.F64
+    jac_mode = (options or {}).get("jac", "fwd")
+    rj = _batched_r_and_J(fn, args, args_in_dims, jac_mode, single)
+    r, J = rj(Y0)
+    m = int(r.shape[1])
+    es = 4 if dtype_code == _lib.F32 else 8
+    stride = lib.b200opt_lsq_step_state_size(dtype_code, n, m)
+    if stride <= 0:
+        _lib.check(-1, "b200opt_lsq_step_state_size")
+    state = t.empty((B, stride // es), dtype=y0.dtype, device=Y0.device)
+    y = t.empty_like(Y0)
+    y_eval = t.empty_like(Y0)
+    steps = t.empty((B,), dtype=t.int32, device=Y0.device)
+    res = t.empty((B,), dtype=t.int32, device=Y0.device)
+    active = t.zeros((1,), dtype=t.int32, device=Y0.device)
+    stream = t.cuda.current_stream(Y0.device).cuda_stream
+    solver_id = _lib.SOLVER_LM if isinstance(solver, LevenbergMarquardt) else _lib.SOLVER_GN
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=root_near_zero)
+    _lib.check(lib.b200opt_lsq_step_init(dtype_code, B, n, m, Y0.data_ptr(), y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
+                                         steps.data_ptr(), res.data_ptr(), stream), "b200opt_lsq_step_init")
+    launches = 0
+    for it in range(max_steps):
+        if it > 0:
+            r, J = rj(y_eval)
+        r = r.contiguous()
+        J = J.contiguous()
+        _lib.check(lib.b200opt_lsq_step(solver_id, dtype_code, B, n, m, r.data_ptr(), J.data_ptr(), y.data_ptr(), y_eval.data_ptr(),
+                                        state.data_ptr(), C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), stream),
+                   "b200opt_lsq_step")
+        launches += 1
+        if int(active.item()) == 0:  # every lane of the vmapped while_loop has stopped (_iterate.py:230-232)
+            break
+    _lib.check(lib.b200opt_lsq_step_finish(dtype_code, B, n, m, state.data_ptr(), res.data_ptr(), stream), "b200opt_lsq_step_finish")
+    if throw:
+        rh = res.cpu().numpy()
+        bad = np.flatnonzero(rh != RESULTS.successful)
+        if bad.size:
+            code = int(rh[bad[0]])
+            raise RuntimeError(f"{bad.size} of {rh.size} solves failed; first failure (problem {int(bad[0])}): "
+                               f"{RESULTS.name(code)}: {RESULTS[code]}")
+    stats = {"num_steps": steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    value, result = y, res
+    if single:
+        value, result = y[0], res[0]
+        stats["num_steps"] = steps[0]
+    return Solution(value=value, result=result, aux=None, stats=stats, state=state)
+
+
+def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw):
+    raise NotImplementedError("Newton/Chord on an arbitrary callable: use root_find(fn, LevenbergMarquardt(...)) "
+                              "(generic step kernel) or a registered root family; a generic Newton step kernel is a next row")
+
+
+def minimise_generic(fn, solver, y0, args, *, max_steps, throw):
+    raise NotImplementedError("BFGS on an arbitrary callable is a next row (SURVEY 8f); registered minimisation families "
+                              "run in the persistent BFGS kernel")

@@ -1,0 +1,339 @@
+// Generic per-iteration LM / GN step for an ARBITRARY user function: the caller (XLA, torch, ...) evaluates the
+// residual r and the Jacobian J at the trial point, this kernel does everything else of one
+// AbstractGaussNewton.step (optimistix/_solver/gauss_newton.py:243-334) plus the driver bookkeeping of
+// _iterate.py:234-241 for every problem that is still running:
+//   search (trust_region.py:77-106 / learning_rate.py:24-35), accept/reject select, Gram J^T J and J^T r of the
+//   accepted point, Cauchy termination (_misc.py:291-310), damped Cholesky solve (levenberg_marquardt.py:34-76 in
+//   normal-equation form), next trial point, step counter, result codes.
+// One warp per problem; the per-problem carry lives in a caller-owned opaque state buffer between calls:
+//   [ G packed lower (NP(NP+1)/2) | g (NP) | rr | delta | first | terminate | num_accepted | r_accepted (m) ]
+// with NP = n padded to 4 / 8 / 16 (padded unknowns get a unit diagonal and stay exactly zero).
+#include "lsq_kernel.cuh"
+
+namespace b200opt {
+int device_sm_count();
+
+template <int NP> __host__ __device__ constexpr int step_state_head() { return Tri<NP>::size + NP + 5; }
+__host__ __device__ inline int64_t step_state_stride(int np_head, int m) { return ((int64_t)np_head + m + 3) / 4 * 4; }
+
+template <typename T> struct StepParams {
+  const T* r_eval;
+  const T* J_eval;
+  T* y;
+  T* y_eval;
+  T* state;
+  int64_t state_stride;
+  int32_t* num_steps;
+  int32_t* result;
+  int32_t* active_count;
+  int64_t batch;
+  int n, m;
+  T rtol, atol;
+  int norm, max_steps, root_near_zero, trust;
+};
+
+constexpr int kStepWarps = 4;
+
+template <typename T, int NP> __global__ void __launch_bounds__(kStepWarps * 32) lsq_step_kernel(const StepParams<T> p) {
+  constexpr int NG = Tri<NP>::size;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  T* scratch = reinterpret_cast<T*>(smem_raw) + (size_t)wib * WarpReduceLayout<T, NG + NP>::elems;
+  const int64_t prob = (int64_t)blockIdx.x * kStepWarps + wib;
+  if (prob >= p.batch) return;
+  const int n = p.n, m = p.m;
+  T* st = p.state + prob * p.state_stride;
+  T* st_r = st + step_state_head<NP>();
+  int result = p.result[prob];
+  int steps = p.num_steps[prob];
+  bool terminate = st[NG + NP + 3] != T(0);
+  if (terminate || result != RES_OK || steps >= p.max_steps) return;  // this lane of the vmapped loop is frozen
+
+  T y[NP], ye[NP], G[NG], g[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    y[j] = j < n ? p.y[prob * n + j] : T(0);
+    ye[j] = j < n ? p.y_eval[prob * n + j] : T(0);
+    g[j] = st[NG + j];
+  }
+#pragma unroll
+  for (int a = 0; a < NG; ++a) G[a] = st[a];
+  T rr = st[NG + NP + 0], delta = st[NG + NP + 1];
+  const bool first = st[NG + NP + 2] != T(0);
+  int naccept = (int)st[NG + NP + 4];
+  const T rtol = p.rtol, atol = p.atol;
+
+  bool y_old_finite = true;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) y_old_finite = y_old_finite && t_finite(y[j]);
+
+  const T* re = p.r_eval + prob * m;
+  const T* Je = p.J_eval + prob * (int64_t)m * n;
+  T part = T(0);
+  for (int i = lane; i < m; i += 32) {
+    const T r = re[i];
+    part += r * r;
+  }
+  const T rre = warp_sum(part);
+  T d[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) d[j] = ye[j] - y[j];
+
+  bool accept = true;
+  if (p.trust) {  // trust_region.py:86-104
+    T lin = T(0), quad = T(0);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      T gd = T(0);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) gd += G[Tri<NP>::at(i, j)] * d[j];
+      quad += d[i] * gd;
+      lin += d[i] * g[i];
+    }
+    const T pred = lin + T(0.5) * quad;
+    const T df = T(0.5) * rre - T(0.5) * rr;
+    accept = (df <= T(0.01) * pred) || first;
+    const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
+    delta *= accept ? (good ? T(3.5) : T(1)) : T(0.25);
+  } else {
+    delta = T(1);
+  }
+
+  if (accept) {  // gauss_newton.py:276-291
+    NormAcc<T> yn(p.norm), fn(p.norm), zn(p.norm);
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+      if (j < n) yn.add(t_abs(d[j]) / (atol + rtol * t_abs(ye[j])));
+    T acc[NG + NP];
+#pragma unroll
+    for (int a = 0; a < NG + NP; ++a) acc[a] = T(0);
+    for (int i = lane; i < m; i += 32) {
+      T j[NP];
+#pragma unroll
+      for (int a = 0; a < NP; ++a) j[a] = a < n ? Je[(int64_t)i * n + a] : T(0);
+      const T r = re[i], ro = st_r[i];
+#pragma unroll
+      for (int a = 0; a < NP; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) acc[Tri<NP>::at(a, b)] += j[a] * j[b];
+        acc[NG + a] += j[a] * r;
+      }
+      fn.add(t_abs(r - ro) / (atol + rtol * t_abs(r)));
+      if (p.root_near_zero) zn.add(t_abs(first ? r : ro));
+      st_r[i] = r;
+    }
+    warp_allreduce_array<T, NG + NP>(acc, scratch, lane);
+#pragma unroll
+    for (int a = 0; a < NG; ++a) G[a] = acc[a];
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      g[a] = acc[NG + a];
+      if (a >= n) G[Tri<NP>::at(a, a)] = T(1);  // padded unknowns: unit pivot, zero right-hand side
+    }
+    // carry [G | g] back to the state buffer straight from the reduction totals (same layout), then the unit pivots
+    const T* tot = scratch + 32 * WarpReduceLayout<T, NG + NP>::KP;
+    for (int a = lane; a < NG + NP; a += 32) st[a] = tot[a];
+    __syncwarp();
+    if (lane >= n && lane < NP) st[Tri<NP>::at(lane, lane)] = T(1);
+    fn.warp_combine();
+    terminate = (yn.finish(n) < T(1)) && (fn.finish(m) < T(1));
+    if (p.root_near_zero) {
+      zn.warp_combine();
+      terminate = terminate && (zn.finish(m) < atol);
+    }
+    ++naccept;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) y[j] = ye[j];
+    rr = rre;
+  } else {
+    terminate = false;
+  }
+
+  T lam = T(0);
+  if (p.trust) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
+  T lamv = lam;
+  T pstep[NP];
+  spd_solve<T, NP>(G, lamv, g, pstep);
+  bool pfin = true;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    pfin = pfin && t_finite(pstep[j]);
+    ye[j] = y[j] - pstep[j];
+  }
+  result = pfin ? RES_OK : RES_SINGULAR;
+  if (!y_old_finite) result = RES_NONFINITE;
+  ++steps;
+
+  // write the rest of the carry back
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (lane == j && j < n) {
+      p.y[prob * n + j] = y[j];
+      p.y_eval[prob * n + j] = ye[j];
+    }
+  }
+  if (lane == 0) {
+    st[NG + NP + 0] = rr;
+    st[NG + NP + 1] = delta;
+    st[NG + NP + 2] = T(0);
+    st[NG + NP + 3] = terminate ? T(1) : T(0);
+    st[NG + NP + 4] = (T)naccept;
+    p.num_steps[prob] = steps;
+    p.result[prob] = result;
+    if (p.active_count && !terminate && result == RES_OK && steps < p.max_steps) atomicAdd(p.active_count, 1);
+  }
+}
+
+template <typename T> __global__ void lsq_step_init_kernel(int64_t batch, int n, int head, int64_t stride, int ng_np, const T* y0,
+                                                           T* y, T* y_eval, T* state, int32_t* num_steps, int32_t* result) {
+  const int64_t prob = blockIdx.x;
+  if (prob >= batch) return;
+  T* st = state + prob * stride;
+  for (int64_t i = threadIdx.x; i < stride; i += blockDim.x) st[i] = T(0);
+  __syncthreads();
+  bool fin = true;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const T v = y0[prob * n + j];
+    y[prob * n + j] = v;
+    y_eval[prob * n + j] = v;
+    fin = fin && t_finite(v);
+  }
+  const int allfin = __syncthreads_and(fin ? 1 : 0);
+  if (threadIdx.x == 0) {
+    st[ng_np + 1] = T(1);  // delta = 1 (trust_region.py:75)
+    st[ng_np + 2] = T(1);  // first_step = True (gauss_newton.py:231)
+    num_steps[prob] = 0;
+    result[prob] = allfin ? RES_OK : RES_NONFINITE;  // _iterate.py:216-219
+  }
+  (void)head;
+}
+
+template <typename T> __global__ void lsq_step_finish_kernel(int64_t batch, int64_t stride, int term_off, const T* state, int32_t* result) {
+  const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= batch) return;
+  const bool terminate = state[prob * stride + term_off] != T(0);
+  if (result[prob] == RES_OK && !terminate) result[prob] = RES_NL_MAX_STEPS;  // _iterate.py:253-257
+}
+
+static int pad_n(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 0)); }
+static int head_for(int np) { return np == 4 ? step_state_head<4>() : (np == 8 ? step_state_head<8>() : step_state_head<16>()); }
+
+template <typename T, int NP> static int step_launch(const StepParams<T>& p, cudaStream_t stream) {
+  auto kern = lsq_step_kernel<T, NP>;
+  const size_t smem = sizeof(T) * kStepWarps * WarpReduceLayout<T, Tri<NP>::size + NP>::elems;
+  static thread_local bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
+    attr_set = true;
+  }
+  const int grid = (int)((p.batch + kStepWarps - 1) / kStepWarps);
+  kern<<<grid, kStepWarps * 32, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "lsq_step_kernel launch");
+}
+
+template <typename T>
+static int step_typed(int solver, int64_t batch, int n, int m, const void* r_eval, const void* J_eval, void* y, void* y_eval,
+                      void* state, const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
+  const int np = pad_n(n);
+  StepParams<T> p;
+  p.r_eval = static_cast<const T*>(r_eval);
+  p.J_eval = static_cast<const T*>(J_eval);
+  p.y = static_cast<T*>(y);
+  p.y_eval = static_cast<T*>(y_eval);
+  p.state = static_cast<T*>(state);
+  p.state_stride = step_state_stride(head_for(np), m);
+  p.num_steps = num_steps;
+  p.result = result;
+  p.active_count = active;
+  p.batch = batch;
+  p.n = n;
+  p.m = m;
+  p.rtol = (T)o->rtol;
+  p.atol = (T)o->atol;
+  p.norm = o->norm;
+  p.max_steps = o->max_steps;
+  p.root_near_zero = o->root_near_zero;
+  p.trust = solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
+  if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
+  if (np == 4) return step_launch<T, 4>(p, st);
+  if (np == 8) return step_launch<T, 8>(p, st);
+  return step_launch<T, 16>(p, st);
+}
+}  // namespace b200opt
+
+using namespace b200opt;
+
+static int step_check(const char* who, int dtype, int64_t batch, int n, int m) {
+  if (dtype != B200OPT_F32 && dtype != B200OPT_F64) {
+    set_error("%s: unknown dtype %d", who, dtype);
+    return B200OPT_EINVAL;
+  }
+  if (batch < 0 || m < 1 || n < 1 || pad_n(n) == 0) {
+    set_error("%s: need batch >= 0, m >= 1 and 1 <= n <= 16 (n=%d, m=%d)", who, n, m);
+    return B200OPT_EINVAL;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int64_t b200opt_lsq_step_state_size(int32_t dtype, int32_t n, int32_t m) {
+  if (step_check("lsq_step_state_size", dtype, 0, n, m)) return -1;
+  return step_state_stride(head_for(pad_n(n)), m) * (dtype == B200OPT_F32 ? 4 : 8);
+}
+
+int32_t b200opt_lsq_step_init(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* y0, void* y, void* y_eval,
+                              void* state, int32_t* num_steps, int32_t* result, void* stream) {
+  if (int e = step_check("lsq_step_init", dtype, batch, n, m)) return e;
+  if (batch == 0) return 0;
+  const int np = pad_n(n), head = head_for(np);
+  const int64_t stride = step_state_stride(head, m);
+  const int ng_np = head - 5;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200OPT_F64)
+    lsq_step_init_kernel<double><<<(unsigned)batch, 64, 0, st>>>(batch, n, head, stride, ng_np, static_cast<const double*>(y0),
+                                                                 static_cast<double*>(y), static_cast<double*>(y_eval),
+                                                                 static_cast<double*>(state), num_steps, result);
+  else
+    lsq_step_init_kernel<float><<<(unsigned)batch, 64, 0, st>>>(batch, n, head, stride, ng_np, static_cast<const float*>(y0),
+                                                                static_cast<float*>(y), static_cast<float*>(y_eval),
+                                                                static_cast<float*>(state), num_steps, result);
+  return check_cuda(cudaGetLastError(), "lsq_step_init launch");
+}
+
+int32_t b200opt_lsq_step(int32_t solver, int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* r_eval,
+                         const void* J_eval, void* y, void* y_eval, void* state, const b200opt_options_t* opts,
+                         int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream) {
+  if (int e = step_check("lsq_step", dtype, batch, n, m)) return e;
+  if (!opts || opts->norm < 0 || opts->norm > 2 || opts->max_steps < 0) {
+    set_error("lsq_step: bad options");
+    return B200OPT_EINVAL;
+  }
+  if (solver != B200OPT_SOLVER_LEVENBERG_MARQUARDT && solver != B200OPT_SOLVER_GAUSS_NEWTON) {
+    set_error("lsq_step: solver %d is not a least-squares solver", solver);
+    return B200OPT_EINVAL;
+  }
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200OPT_F64)
+    return step_typed<double>(solver, batch, n, m, r_eval, J_eval, y, y_eval, state, opts, num_steps, result, active_count, st);
+  return step_typed<float>(solver, batch, n, m, r_eval, J_eval, y, y_eval, state, opts, num_steps, result, active_count, st);
+}
+
+int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* state, int32_t* result,
+                                void* stream) {
+  if (int e = step_check("lsq_step_finish", dtype, batch, n, m)) return e;
+  if (batch == 0) return 0;
+  const int head = head_for(pad_n(n));
+  const int64_t stride = step_state_stride(head, m);
+  const int term_off = head - 5 + 3;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((batch + 127) / 128);
+  if (dtype == B200OPT_F64)
+    lsq_step_finish_kernel<double><<<grid, 128, 0, st>>>(batch, stride, term_off, static_cast<const double*>(state), result);
+  else
+    lsq_step_finish_kernel<float><<<grid, 128, 0, st>>>(batch, stride, term_off, static_cast<const float*>(state), result);
+  return check_cuda(cudaGetLastError(), "lsq_step_finish launch");
+}
+
+}  // extern "C"

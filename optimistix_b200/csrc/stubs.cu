@@ -6,15 +6,6 @@ using namespace b200opt;
   set_error(name ": not implemented in this build"); \
   return B200OPT_ENOTIMPL;
 extern "C" {
-int64_t b200opt_lsq_step_state_size(int32_t, int32_t, int32_t) { return -1; }
-int32_t b200opt_lsq_step_init(int32_t, int64_t, int32_t, int32_t, const void*, void*, void*, void*, int32_t*, int32_t*, void*) {
-  NOTIMPL("lsq_step_init")
-}
-int32_t b200opt_lsq_step(int32_t, int32_t, int64_t, int32_t, int32_t, const void*, const void*, void*, void*, void*,
-                         const b200opt_options_t*, int32_t*, int32_t*, int32_t*, void*) {
-  NOTIMPL("lsq_step")
-}
-int32_t b200opt_lsq_step_finish(int32_t, int64_t, int32_t, int32_t, const void*, int32_t*, void*) { NOTIMPL("lsq_step_finish") }
 int64_t b200opt_gn_gram_workspace_size(int32_t) { return -1; }
 int32_t b200opt_gn_gram(const float*, const float*, int64_t, int32_t, float*, void*, void*) { NOTIMPL("gn_gram") }
 int32_t b200opt_gn_solve(const float*, int32_t, double, float*, int32_t*, void*) { NOTIMPL("gn_solve") }
