@@ -183,12 +183,16 @@ int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t
 int64_t b200opt_gn_gram_workspace_size(int32_t n);
 int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace,
                         void* stream);
-/* Solve (G + lambda I) p = g in fp64 on one CTA; p_out [n] fp32; status_out: device int32 result code. */
-int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float* p_out, int32_t* status_out,
+/* Solve (G + lambda I) p = g in fp64 on one CTA; gram_out is the (all-reduced) output of b200opt_gn_gram;
+ * p_out [n] fp32; status_out: device int32 result code (singular if the solution is non-finite); `workspace` is
+ * the same buffer that was given to b200opt_gn_gram. */
+int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float* p_out, int32_t* status_out, void* workspace,
                          void* stream);
-/* r = J y - d for the "linear_rows" family, fused single pass (used by the GaussNewton driver for configs[4]) */
+/* r = J y - d for the "linear_rows" family (one coalesced pass over the row shard). If r_old is not NULL the
+ * f-space half of cauchy_termination (optimistix/_misc.py:306-309) is fused in: *fmax_bits (device, caller-zeroed)
+ * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */
 int32_t b200opt_linear_residual(const float* J, const float* y, const float* d, int64_t m_local, int32_t n, float* r,
-                                void* stream);
+                                const float* r_old, float rtol, float atol, uint32_t* fmax_bits, void* stream);
 
 #ifdef __cplusplus
 }

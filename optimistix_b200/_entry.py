@@ -190,6 +190,14 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
                                      options=options, args_in_dims=args_in_dims)
     if fn.kind != KIND_LSQ:
         raise TypeError(f"model {fn.name} is not a least-squares family")
+    if fn.name == "linear_rows":
+        # one large row-sharded problem: tensor-core Gram + (optional) NCCL all-reduce (BASELINE configs[4])
+        if not isinstance(solver, GaussNewton):
+            raise NotImplementedError("linear_rows runs under GaussNewton (BASELINE configs[4])")
+        from ._gn_large import gauss_newton_large
+
+        a = fn.split_args(args)
+        return gauss_newton_large(a["J"], a["d"], y0, solver, max_steps=max_steps, throw=throw)
     lib = _lib.load()
     y0, buf, single = _prepare_y0(y0)
     B, n = y0.shape

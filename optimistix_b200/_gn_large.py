@@ -1,0 +1,119 @@
+"""GaussNewton on ONE large, row-sharded least-squares problem (BASELINE configs[4]; SURVEY sections 3.4 and 8e).
+
+Each rank holds a contiguous shard of the rows of J (and of d); every rank holds the same y.  Per iteration:
+    r      = J y_eval - d                       b200opt_linear_residual (one coalesced pass, fused f-test statistic)
+    G,g,rr = J^T J, J^T r, r^T r                b200opt_gn_gram (tcgen05 tensor cores, TMA-fed, fp32 accumulate in TMEM)
+    all-reduce [G | g | rr] (sum) and the f-test statistic (max) over the ranks   -- the ONLY exchange: n^2+n+2 floats
+    p      = G^-1 g                             b200opt_gn_solve (fp64 Cholesky, identical on every rank)
+    y, y_eval = y_eval, y_eval - p
+which is AbstractGaussNewton.step with search = LearningRate(1.0) (always accept) and descent = NewtonDescent
+(optimistix/_solver/gauss_newton.py:243-334, :64-78, learning_rate.py:24-35) under the driver of
+_iterate.py:194-268, with the normal equations in place of the reference's QR (north_star).
+
+The numerical kernels are injected through `ops` so that the sharding / all-reduce / termination logic can be
+exercised on CPU with world_size > 1 (gloo) by the tests; the product always uses `CudaOps`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from ._solution import RESULTS, Solution
+
+N = 256
+
+
+class CudaOps:
+    """The CUDA kernels behind the C ABI, on torch's current stream."""
+
+    def __init__(self, device):
+        import torch
+
+        self.t = torch
+        self.lib = _lib.load()
+        self.device = device
+        nbytes = self.lib.b200opt_gn_gram_workspace_size(N)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.launches = 0
+
+    def _stream(self):
+        return self.t.cuda.current_stream(self.device).cuda_stream
+
+    def residual(self, J, y, d, r_out, r_old, rtol, atol, fmax):
+        fmax.zero_()
+        _lib.check(self.lib.b200opt_linear_residual(J.data_ptr(), y.data_ptr(), d.data_ptr(), J.shape[0], N, r_out.data_ptr(),
+                                                    r_old.data_ptr() if r_old is not None else None, rtol, atol,
+                                                    fmax.data_ptr(), self._stream()), "b200opt_linear_residual")
+        self.launches += 1
+
+    def gram(self, J, r, out):
+        _lib.check(self.lib.b200opt_gn_gram(J.data_ptr(), r.data_ptr(), J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+                                            self._stream()), "b200opt_gn_gram")
+        self.launches += 2
+
+    def solve(self, out, lam, p, status):
+        _lib.check(self.lib.b200opt_gn_solve(out.data_ptr(), N, float(lam), p.data_ptr(), status.data_ptr(), self.ws.data_ptr(),
+                                             self._stream()), "b200opt_gn_solve")
+        self.launches += 1
+
+
+def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None):
+    """Solve min_y |J y - d|^2 with this rank's row shard (J [m_local, 256] fp32, d [m_local]); returns a Solution.
+
+    `group`: a torch.distributed process group (None = the default group if initialised, else single rank)."""
+    import torch
+    import torch.distributed as dist
+
+    if getattr(solver.norm, "norm_name", "max") != "max":
+        raise NotImplementedError("the large Gauss-Newton path implements max_norm termination")
+    distributed = dist.is_available() and dist.is_initialized() and (group is not None or dist.get_world_size() > 1)
+    dev = J.device
+    if ops is None:
+        if not J.is_cuda:
+            raise _lib.B200OptError("the large Gauss-Newton path needs CUDA tensors (there is no CPU fallback)")
+        ops = CudaOps(dev)
+    if J.dtype != torch.float32 or J.ndim != 2 or J.shape[1] != N or not J.is_contiguous():
+        raise ValueError(f"J must be a contiguous float32 [m_local, {N}] tensor")
+    m_local = J.shape[0]
+    d = d.to(torch.float32).contiguous()
+    y = y0.to(device=dev, dtype=torch.float32).contiguous().clone()
+    if y.shape != (N,):
+        raise ValueError(f"y0 must have shape [{N}]")
+    rtol, atol = float(solver.rtol), float(solver.atol)
+    y_eval = y.clone()
+    r_old = torch.zeros(m_local, dtype=torch.float32, device=dev)  # gauss_newton.py:229-230: zero-filled f_info
+    r_new = torch.empty_like(r_old)
+    out = torch.empty(N * N + N + 1, dtype=torch.float32, device=dev)
+    p = torch.empty(N, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    fmax = torch.zeros(1, dtype=torch.int32, device=dev)  # IEEE bits of a non-negative float: integer max == float max
+    result = RESULTS.successful if bool(torch.isfinite(y).all()) else RESULTS.nonfinite  # _iterate.py:216-219
+    terminate = False
+    steps = 0
+    while not terminate and result == RESULTS.successful and steps < max_steps:
+        y_old_finite = bool(torch.isfinite(y).all())
+        ops.residual(J, y_eval, d, r_new, r_old, rtol, atol, fmax)  # gauss_newton.py:253 + f-space half of :280-288
+        ops.gram(J, r_new, out)
+        if distributed:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(fmax, op=dist.ReduceOp.MAX, group=group)
+        y_diff = y_eval - y
+        y_conv = bool(((y_diff.abs() / (atol + rtol * y_eval.abs())).max() < 1).item())  # _misc.py:306-308
+        f_stat = fmax.view(torch.float32)
+        f_conv = bool((f_stat < 1).item())  # NaN compares false, like jnp.max
+        terminate = y_conv and f_conv  # LearningRate always accepts (learning_rate.py:24-35)
+        ops.solve(out, 0.0, p, status)  # NewtonDescent.query: newton = G^-1 g
+        y = y_eval
+        y_eval = y - p  # gauss_newton.py:126-127 with step_size 1
+        r_old, r_new = r_new, r_old
+        result = int(status.item())  # gauss_newton.py:316-318: the linear solve's result
+        if not y_old_finite:
+            result = RESULTS.nonfinite
+        steps += 1
+    if result == RESULTS.successful and not terminate:
+        result = RESULTS.nonlinear_max_steps_reached  # _iterate.py:253-257
+    if throw and result != RESULTS.successful:
+        raise RuntimeError(f"{RESULTS.name(result)}: {RESULTS[result]}")
+    stats = {"num_steps": steps, "max_steps": max_steps, "loss": 0.5 * float(out[N * N + N].item()),
+             "gpu_launches": getattr(ops, "launches", None)}
+    return Solution(value=y, result=result, aux=None, stats=stats, state={"gram": out, "residual": r_old})

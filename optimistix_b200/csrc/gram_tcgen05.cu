@@ -1,0 +1,362 @@
+// Large row-sharded Gauss-Newton Gram on the 5th-generation tensor cores (sm_100a: tcgen05 + TMEM + TMA).
+//
+// Replaces, for ONE large least-squares problem (BASELINE configs[4]: m = 64Mi rows, n = 256 parameters), the
+// O(m n^2) part of NewtonDescent's `lx.linear_solve(J, r)` (optimistix/_solver/gauss_newton.py:64-78, which
+// resolves to a QR of the m x n operator) by the normal equations the north_star asks for:
+//     G = J^T J  (n x n),   g = J^T r  (n),   rr = r^T r
+// per row shard; the caller all-reduces [G | g | rr] across ranks (NCCL) and solves (G + lambda I) p = g.
+//
+// Kernel design (persistent, one CTA per SM, 320 threads):
+//   * J [m][256] fp32 row-major is streamed ONCE from HBM by TMA in tiles of 64 rows x 256 columns (64 KiB), as 8
+//     boxes of 32 columns (128 bytes = the SWIZZLE_128B span), 3-stage mbarrier ring (192 KiB of shared memory).
+//   * the same shared-memory tile is BOTH MMA operands: A = J_tile^T (M = parameter index) and B = J_tile
+//     (N = parameter index), both "MN-major" (the parameter index is the contiguous one), K = rows, kind::tf32
+//     (K = 8 rows per instruction), fp32 accumulation in TMEM.  Symmetry: only the blocks
+//     (rows 0-127 x cols 0-255) and (rows 128-255 x cols 128-255) are computed - 384 of 512 TMEM columns, 0.75 of
+//     the MMA work.  The accumulators stay in TMEM across ALL tiles of the CTA; there is one epilogue per CTA.
+//   * g and rr come from CUDA cores: 8 warps read the tile from shared memory (one 128-byte line per warp per row,
+//     conflict free under the swizzle) while the tensor core works on it.
+//   * per-CTA partials go to a workspace; a second small kernel adds them in a fixed order (deterministic) and
+//     mirrors the triangle.
+// Roofline: HBM-bound by construction (68.7 GB of J per pass at configs[4]); tensor pipe ~55% busy at the HBM rate.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace b200opt {
+int device_sm_count();
+
+namespace gram {
+
+constexpr int N = 256;            // parameters (columns of J)
+constexpr int KROWS = 64;         // rows of J per tile
+constexpr int STAGES = 3;
+constexpr int BOX_COLS = 32;      // 32 fp32 = 128 bytes = one SWIZZLE_128B span
+constexpr int GROUPS = N / BOX_COLS;                    // 8 column groups per tile
+constexpr int GROUP_BYTES = KROWS * 128;                // 8 KiB: one TMA box in shared memory
+constexpr int TILE_BYTES = GROUPS * GROUP_BYTES;        // 64 KiB
+constexpr int THREADS = 320;                            // warp 0: TMA, warp 1: MMA/TMEM, warps 2-9: g, rr, epilogue
+constexpr int TMEM_COLS = 512;                          // 384 used
+constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * TILE_BYTES + STAGES * KROWS * 4 + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// UMMA shared-memory descriptor, MN-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start >> 4 | [16,30) leading byte offset >> 4 (stride between 32-column groups)
+//   [32,46) stride byte offset >> 4 (stride between 8-row K groups) | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((GROUP_BYTES >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, both MN-major, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc(int n_dim) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_dim >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct Params {
+  const float* r;      // [m]
+  int64_t m;
+  float* ws;           // per-CTA partials: [grid][N*N + N + 1] (+ padding to a multiple of 4 floats)
+  int num_tiles;
+};
+constexpr int WS_STRIDE = N * N + N + 4;
+
+__global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* tiles = smem;                                             // STAGES x 64 KiB, 1024-byte aligned
+  float* rs = reinterpret_cast<float*>(smem + (size_t)STAGES * TILE_BYTES);  // STAGES x KROWS floats
+  uint64_t* full = reinterpret_cast<uint64_t*>(rs + STAGES * KROWS);       // TMA -> consumers
+  uint64_t* empty = full + STAGES;                                          // consumers -> TMA
+  uint64_t* accum_done = empty + STAGES;                                    // last MMA retired -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);        // one arrive.expect_tx by the producer (+ the TMA transaction bytes)
+      mbar_init(&empty[s], 1 + 8);   // tcgen05.commit of the MMA warp + one arrive per g-warp
+    }
+    mbar_init(accum_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is a warp-wide operation; this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (one elected lane) ================================
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+        const int64_t row0 = tile * KROWS;
+        const int64_t rows_left = p.m - row0;
+        const uint32_t r_bytes = (uint32_t)((rows_left < KROWS ? rows_left : KROWS) * 4);
+        mbar_expect_tx(&full[s], TILE_BYTES + r_bytes);   // out-of-bounds rows are zero-filled and still counted
+        unsigned char* dst = tiles + (size_t)s * TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) tma_load_2d(dst + g * GROUP_BYTES, &tmap, g * BOX_COLS, (int)row0, &full[s]);
+        bulk_load_1d(rs + s * KROWS, p.r + row0, r_bytes, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one elected lane) ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_full = make_idesc(256);
+      constexpr uint32_t idesc_half = make_idesc(128);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(tiles + (size_t)s * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < KROWS / 8; ++k) {
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          // rows 0-127 of G x all 256 columns -> TMEM columns [0, 256)
+          umma_tf32(tmem_base + 0, make_desc(base + k * 1024), make_desc(base + k * 1024), idesc_full, acc);
+          // rows 128-255 of G x columns 128-255 -> TMEM columns [256, 384)
+          umma_tf32(tmem_base + 256, make_desc(base + 4 * GROUP_BYTES + k * 1024), make_desc(base + 4 * GROUP_BYTES + k * 1024),
+                    idesc_half, acc);
+        }
+        umma_commit(&empty[s]);                     // frees the stage once these MMAs have read it
+        if (it == my_tiles - 1) umma_commit(accum_done);
+      }
+    }
+  } else {
+    // ================================ g = J^T r, rr = r^T r on CUDA cores ================================
+    const int b = threadIdx.x - 64;                 // this thread's column of J, 0..255
+    const int grp = b >> 5, unit = (b & 31) >> 2, sub = b & 3;
+    float acc_g = 0.f, acc_rr = 0.f;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t rows_left = p.m - tile * KROWS;
+      const int rows = rows_left < KROWS ? (int)rows_left : KROWS;
+      const unsigned char* gbase = tiles + (size_t)s * TILE_BYTES + grp * GROUP_BYTES;
+      const float* rt = rs + s * KROWS;
+#pragma unroll 8
+      for (int r = 0; r < rows; ++r) {
+        const float jv = *reinterpret_cast<const float*>(gbase + r * 128 + ((unit ^ (r & 7)) << 4) + (sub << 2));
+        const float rv = rt[r];
+        acc_g = fmaf(jv, rv, acc_g);
+        acc_rr = fmaf(rv, rv, acc_rr);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // ================================ epilogue: TMEM -> per-CTA partial in the workspace ================================
+    float* ws = p.ws + (size_t)blockIdx.x * WS_STRIDE;
+    ws[N * N + b] = acc_g;
+    if (b == 0) ws[N * N + N] = acc_rr;
+    if (my_tiles > 0) {
+      mbar_wait(accum_done, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3;                       // TMEM lane quarter this warp may access
+      const int half = (warp - 2) >> 2;             // which half of the 384 accumulator columns
+      const int row_lo = q * 32 + lane;             // accumulator row (TMEM lane)
+#pragma unroll 1
+      for (int c0 = half * 192; c0 < half * 192 + 192; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+              "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+              "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // columns [0,256): G[row_lo][c];  columns [256,384): G[128 + row_lo][128 + (c - 256)]
+        const int grow = c0 < 256 ? row_lo : 128 + row_lo;
+        const int gcol = c0 < 256 ? c0 : 128 + (c0 - 256);
+        float4* dst = reinterpret_cast<float4*>(ws + (size_t)grow * N + gcol);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// Deterministic reduction of the per-CTA partials, mirroring the triangle that was not computed.
+// out = [G (N*N, full symmetric) | g (N) | rr]
+__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * N + N + 1) return;
+  int src = idx;
+  if (idx < N * N) {
+    const int a = idx / N, b = idx % N;
+    if (a >= 128 && b < 128) src = b * N + a;  // lower-left block: read the transposed entry of the upper-right block
+  }
+  float s = 0.f;
+  const bool is_gram = idx < N * N;
+  const int count = is_gram ? live_parts : parts;  // CTAs without tiles never wrote their Gram block
+  for (int c = 0; c < count; ++c) s += ws[(size_t)c * WS_STRIDE + src];
+  out[idx] = s;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+}  // namespace gram
+}  // namespace b200opt
+
+using namespace b200opt;
+
+extern "C" {
+
+int64_t b200opt_gn_gram_workspace_size(int32_t n) {
+  if (n != gram::N) return -1;
+  // per-CTA partials for up to 256 CTAs + an fp64 n x n scratch for b200opt_gn_solve
+  return (int64_t)256 * gram::WS_STRIDE * 4 + (int64_t)n * n * 8 + 4096;
+}
+
+int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
+  if (n != gram::N) {
+    set_error("gn_gram: this build supports n = %d parameters only (got %d)", gram::N, n);
+    return B200OPT_EINVAL;
+  }
+  if (m_local < 0 || m_local > ((int64_t)1 << 31) - 64) {
+    set_error("gn_gram: m_local out of range");
+    return B200OPT_EINVAL;
+  }
+  if (!out || !workspace || (m_local > 0 && (!J || !r))) {
+    set_error("gn_gram: NULL buffer");
+    return B200OPT_EINVAL;
+  }
+  if ((reinterpret_cast<uintptr_t>(J) & 15) || (reinterpret_cast<uintptr_t>(r) & 15) || (m_local & 3)) {
+    set_error("gn_gram: J and r must be 16-byte aligned and m_local a multiple of 4");
+    return B200OPT_EINVAL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  const int num_tiles = (int)((m_local + gram::KROWS - 1) / gram::KROWS);
+  int grid = device_sm_count();
+  if (grid > 256) grid = 256;
+  if (num_tiles < grid) grid = num_tiles > 0 ? num_tiles : 1;
+  if (m_local == 0) {
+    if (check_cuda(cudaMemsetAsync(out, 0, sizeof(float) * (gram::N * gram::N + gram::N + 1), st), "memset")) return B200OPT_ECUDA;
+    return 0;
+  }
+  gram::EncodeTiledFn encode = gram::get_encode();
+  if (!encode) {
+    set_error("gn_gram: cuTensorMapEncodeTiled is not available from this driver");
+    return B200OPT_ECUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)gram::N, (cuuint64_t)m_local};
+  const cuuint64_t strides[1] = {(cuuint64_t)gram::N * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)gram::BOX_COLS, (cuuint32_t)gram::KROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(J), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("gn_gram: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    return B200OPT_ECUDA;
+  }
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(gram::gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram::SMEM_BYTES),
+                   "gram smem attr"))
+      return B200OPT_ECUDA;
+    attr_set = true;
+  }
+  gram::Params p{r, m_local, ws, num_tiles};
+  gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
+  if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
+  const int total = gram::N * gram::N + gram::N + 1;
+  gram::gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grid, grid, out);
+  return check_cuda(cudaGetLastError(), "gram_reduce_kernel launch");
+}
+
+}  // extern "C"

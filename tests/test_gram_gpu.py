@@ -1,0 +1,110 @@
+"""The tcgen05 Gram kernel and the large row-sharded Gauss-Newton path against fp64 references. GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import optimistix_b200 as optx
+from optimistix_b200 import _lib, synthetic
+from oracle import models as M
+from oracle import solvers as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+N = 256
+
+
+def _gram(J, r):
+    lib = _lib.load()
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    out = torch.empty(N * N + N + 1, dtype=torch.float32, device=DEV)
+    _lib.check(lib.b200opt_gn_gram(J.data_ptr(), r.data_ptr(), J.shape[0], N, out.data_ptr(), ws.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream), "gn_gram")
+    torch.cuda.synchronize()
+    return out[: N * N].view(N, N), out[N * N : N * N + N], out[N * N + N]
+
+
+@pytest.mark.parametrize("m", [64, 192, 4096, 100000, 9472 * 64 + 20])
+def test_gram_matches_fp64(m):
+    """G = J^T J in TF32 x TF32 -> FP32 (tensor cores), g = J^T r and r^T r in FP32 (CUDA cores); ragged m."""
+    m = m - m % 4
+    w = synthetic.linear_lsq_rows(m, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    r = torch.as_tensor(w["d"], device=DEV)
+    G, g, rr = _gram(J, r)
+    Jd, rd = J.double(), r.double()
+    G_ref, g_ref, rr_ref = Jd.T @ Jd, Jd.T @ rd, rd @ rd
+    scale = torch.sqrt(torch.outer(torch.diag(G_ref), torch.diag(G_ref)))
+    err = ((G.double() - G_ref).abs() / scale).max().item()
+    print(f"[gram m={m}] max |G - G_ref| / sqrt(G_ii G_jj) = {err:.3g}")
+    assert err < 2e-3                       # TF32 operands (10-bit mantissa), fp32 accumulation
+    assert torch.allclose(G, G.T)           # mirrored triangle
+    gscale = (Jd.abs().T @ rd.abs())
+    assert ((g.double() - g_ref).abs() / gscale).max().item() < 1e-5
+    assert abs(rr.item() - rr_ref.item()) / rr_ref.item() < 1e-5
+
+
+def test_gram_deterministic():
+    w = synthetic.linear_lsq_rows(200000, seed=5)
+    J = torch.as_tensor(w["J"], device=DEV)
+    r = torch.as_tensor(w["d"], device=DEV)
+    a = _gram(J, r)
+    b = _gram(J, r)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_gauss_newton_large_matches_lstsq_and_oracle():
+    """BASELINE configs[4] shape at an oracle-sized m: GaussNewton on r = J y - d, Gram on tensor cores."""
+    m = 65536
+    w = synthetic.linear_lsq_rows(m, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y0 = torch.zeros(N, dtype=torch.float32, device=DEV)
+    sol = optx.least_squares(optx.models.linear_rows, optx.GaussNewton(1e-4, 1e-4), y0, (J, d), throw=False)
+    assert sol.result == optx.RESULTS.successful
+    y_ls = np.linalg.lstsq(w["J"].astype(np.float64), w["d"].astype(np.float64), rcond=None)[0]
+    scaled = np.abs(sol.value.cpu().numpy() - y_ls) / (1e-4 + 1e-4 * np.abs(y_ls))
+    print(f"[gn large] steps {sol.stats['num_steps']}, max scaled diff vs fp64 lstsq {scaled.max():.3g}")
+    assert scaled.max() <= 1.0              # north_star: 1e-4 fp32 on solution values
+    ref = S.gauss_newton(M.linear_rows, np.zeros((1, N), np.float32), dict(J=w["J"], d=w["d"]), rtol=1e-4, atol=1e-4, linsolve="qr")
+    assert S.RESULT_NAMES[ref["result"][0]] == "successful"
+    # reference-faithful QR converges in 3 steps on a linear problem; TF32 Gram steps are ~1e-3 inexact, so the
+    # normal-equation path may need one more correction step (documented in DESIGN.md)
+    assert ref["num_steps"][0] <= sol.stats["num_steps"] <= ref["num_steps"][0] + 1
+    assert np.allclose(sol.value.cpu().numpy(), ref["value"][0], rtol=2e-4, atol=2e-4)
+
+
+def test_gn_solve_and_residual_kernels():
+    lib = _lib.load()
+    m = 4096
+    w = synthetic.linear_lsq_rows(m, seed=7)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y = torch.randn(N, device=DEV)
+    r = torch.empty(m, device=DEV)
+    r_old = torch.randn(m, device=DEV)
+    fmax = torch.zeros(1, dtype=torch.int32, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.b200opt_linear_residual(J.data_ptr(), y.data_ptr(), d.data_ptr(), m, N, r.data_ptr(), r_old.data_ptr(), 1e-4, 1e-4,
+                                           fmax.data_ptr(), st), "linear_residual")
+    r_ref = (J.double() @ y.double() - d.double())
+    assert torch.allclose(r.double(), r_ref, rtol=1e-4, atol=1e-4)
+    stat_ref = ((r - r_old).abs() / (1e-4 + 1e-4 * r.abs())).max()
+    assert torch.allclose(fmax.view(torch.float32)[0], stat_ref, rtol=1e-6)
+    # solve
+    A = torch.randn(N, N, dtype=torch.float64)
+    Gm = (A @ A.T + N * torch.eye(N, dtype=torch.float64)).float()
+    g = torch.randn(N)
+    out = torch.cat([Gm.reshape(-1), g, torch.zeros(1)]).to(DEV)
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    p = torch.empty(N, device=DEV)
+    status = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.b200opt_gn_solve(out.data_ptr(), N, 0.5, p.data_ptr(), status.data_ptr(), ws.data_ptr(), st), "gn_solve")
+    p_ref = torch.linalg.solve(Gm.double() + 0.5 * torch.eye(N, dtype=torch.float64), g.double())
+    assert int(status.item()) == 0
+    assert torch.allclose(p.cpu().double(), p_ref, rtol=1e-5, atol=1e-7)
+    # singular system -> `singular`
+    out2 = torch.zeros_like(out)
+    _lib.check(lib.b200opt_gn_solve(out2.data_ptr(), N, 0.0, p.data_ptr(), status.data_ptr(), ws.data_ptr(), st), "gn_solve")
+    assert int(status.item()) == optx.RESULTS.singular
