@@ -8,7 +8,8 @@
 //
 // Kernel design (persistent, one CTA per SM, 320 threads):
 //   * J [m][256] fp32 row-major is streamed ONCE from HBM by TMA in tiles of 64 rows x 256 columns (64 KiB), as 8
-//     boxes of 32 columns (128 bytes = the SWIZZLE_128B span), 3-stage mbarrier ring (192 KiB of shared memory).
+//     boxes of 32 columns (128 bytes = the swizzle span; CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), 3-stage mbarrier ring
+//     (192 KiB of shared memory).
 //   * the same shared-memory tile is BOTH MMA operands: A = J_tile^T (M = parameter index) and B = J_tile
 //     (N = parameter index), both "MN-major" (the parameter index is the contiguous one), K = rows, kind::tf32
 //     (K = 8 rows per instruction), fp32 accumulation in TMEM.  Symmetry: only the blocks
@@ -78,16 +79,20 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-// UMMA shared-memory descriptor, MN-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+// UMMA shared-memory descriptor, MN-major TF32 operand.  MN-major 32-bit operands have exactly one legal layout,
+// SWIZZLE_128B_BASE32B ("128-byte swizzle with 32-byte atoms": within each 128-byte row the index of the 32-byte
+// atom is XORed with (row & 3); measured with tools/umma_probe.cu - the plain SWIZZLE_128B layout yields zeros).
+// cute::UMMA::SmemDescriptor bit layout:
 //   [0,14) start >> 4 | [16,30) leading byte offset >> 4 (stride between 32-column groups)
-//   [32,46) stride byte offset >> 4 (stride between 8-row K groups) | [46,48) version = 1 | [61,64) layout = 2
+//   [32,46) stride byte offset >> 4 (stride between 4-row swizzle atoms = 512 B) | [46,48) version = 1
+//   [61,64) layout type = 1 (SWIZZLE_128B_BASE32B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((GROUP_BYTES >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, both MN-major, M = 128.
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
   } else {
     // ================================ g = J^T r, rr = r^T r on CUDA cores ================================
     const int b = threadIdx.x - 64;                 // this thread's column of J, 0..255
-    const int grp = b >> 5, unit = (b & 31) >> 2, sub = b & 3;
+    const int grp = b >> 5, atom = (b & 31) >> 3, word = b & 7;
     float acc_g = 0.f, acc_rr = 0.f;
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % STAGES;
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
       const float* rt = rs + s * KROWS;
 #pragma unroll 8
       for (int r = 0; r < rows; ++r) {
-        const float jv = *reinterpret_cast<const float*>(gbase + r * 128 + ((unit ^ (r & 7)) << 4) + (sub << 2));
+        const float jv = *reinterpret_cast<const float*>(gbase + r * 128 + ((atom ^ (r & 3)) << 5) + (word << 2));
         const float rv = rt[r];
         acc_g = fmaf(jv, rv, acc_g);
         acc_rr = fmaf(rv, rv, acc_rr);
@@ -338,7 +343,7 @@ int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t
   const cuuint32_t box[2] = {(cuuint32_t)gram::BOX_COLS, (cuuint32_t)gram::KROWS};
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(J), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("gn_gram: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);

@@ -95,20 +95,22 @@ __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T
     const Vec v0 = *reinterpret_cast<const Vec*>(rowbuf + k0);
     const T r = t_rcp(reinterpret_cast<const T*>(&v0)[k - k0]);  // getf2 scales the column by 1/pivot
     const bool elim = !done && lane != p;
-    const T l = a[k] * r;
     if (lane == p) {
       done = true;
       mycol = k;
       rinv = r;
     }
-    if (elim) a[k] = l;
+    if (elim) {  // a real (divergent) branch: rows already used as pivots idle instead of computing-and-discarding
+      const T l = a[k] * r;
+      a[k] = l;
 #pragma unroll
-    for (int j = k0; j < N; j += V) {
-      const Vec v = *reinterpret_cast<const Vec*>(rowbuf + j);
-      const T* vv = reinterpret_cast<const T*>(&v);
+      for (int j = k0; j < N; j += V) {
+        const Vec v = *reinterpret_cast<const Vec*>(rowbuf + j);
+        const T* vv = reinterpret_cast<const T*>(&v);
 #pragma unroll
-      for (int q = 0; q < V; ++q)
-        if (j + q > k && elim) a[j + q] -= l * vv[q];
+        for (int q = 0; q < V; ++q)
+          if (j + q > k) a[j + q] -= l * vv[q];  // compile-time condition after unrolling
+      }
     }
     __syncwarp();
   }
