@@ -165,6 +165,126 @@ def run_host(name, inp_host, chunk):
     return optx.minimise(fn, solver, inp_host["y0"], None, max_steps=max_steps, throw=False, chunk=chunk)
 
 
+def bench_gram(args, rank, world, local_rank):
+    """BASELINE configs[4]: one large GaussNewton problem, m rows x 256 parameters (fp32), row-sharded over the ranks
+    (strong scaling: the total row count is fixed).  A step is one Gauss-Newton iteration:
+    residual pass + tensor-core Gram + all-reduce of n^2+n+2 floats + Cholesky solve."""
+    import torch
+    import torch.distributed as dist
+
+    from optimistix_b200._gn_large import N, CudaOps
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m_total = args.rows
+    m_local = m_total // world // 64 * 64
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4 + rank)
+    scale = torch.logspace(0, -2, N, device=dev)
+    J = torch.empty((m_local, N), dtype=torch.float32, device=dev)
+    chunk = 1 << 20
+    for s0 in range(0, m_local, chunk):
+        e0 = min(m_local, s0 + chunk)
+        J[s0:e0] = torch.randn((e0 - s0, N), generator=gen, device=dev) * scale
+    y_true = torch.randn(N, generator=torch.Generator(device=dev).manual_seed(4), device=dev) / scale
+    d = torch.empty(m_local, dtype=torch.float32, device=dev)
+    for s0 in range(0, m_local, chunk):
+        e0 = min(m_local, s0 + chunk)
+        d[s0:e0] = J[s0:e0] @ y_true + 0.01 * torch.randn(e0 - s0, generator=gen, device=dev)
+    ops = CudaOps(dev)
+    y = torch.zeros(N, device=dev)
+    r = torch.empty(m_local, device=dev)
+    r_old = torch.zeros(m_local, device=dev)
+    out = torch.empty(N * N + N + 1, device=dev)
+    p = torch.empty(N, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    fmax = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    fused = not args.unfused
+
+    def step():
+        if fused:
+            ops.residual_gram(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out)
+        else:
+            ops.residual(J, y, d, r, r_old, 1e-4, 1e-4, fmax)
+            ops.gram(J, r, out)
+        if world > 1:
+            dist.all_reduce(out)
+            dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+        ops.solve(out, 0.0, p, status)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_step = t_gram = t_res = 0.0
+    for _ in range(K):
+        ev[0].record()
+        if not fused:
+            ops.residual(J, y, d, r, r_old, 1e-4, 1e-4, fmax)
+        ev[1].record()
+        if fused:
+            ops.residual_gram(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out)
+        else:
+            ops.gram(J, r, out)
+        ev[2].record()
+        if world > 1:
+            dist.all_reduce(out)
+            dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+        ops.solve(out, 0.0, p, status)
+        ev[3].record()
+        torch.cuda.synchronize()
+        t_res += ev[0].elapsed_time(ev[1])
+        t_gram += ev[1].elapsed_time(ev[2])
+        t_step += ev[0].elapsed_time(ev[3])
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([t_step, t_gram, t_res], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step, t_gram, t_res = (float(x) for x in t)
+    ms, ms_gram, ms_res = t_step / K, t_gram / K, t_res / K
+    if rank == 0:
+        rows = m_local * world
+        peak, peak_src = _peaks()
+        j_bytes = m_local * N * 4
+        tf32_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                tf32_peak = float(json.load(fh)["bf16_tflops"]) / 2
+        except Exception:  # noqa: BLE001
+            pass
+        gram_tflops = 2.0 * m_local * N * N / (ms_gram / 1e3) / 1e12  # per GPU, full (unsymmetrised) count
+        line = {"metric": "GaussNewton Gram iterations/sec (m rows x 256 params, row-sharded)", "value": 1e3 / ms, "unit": "iterations/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "tf32 x tf32 -> f32 (TMEM)", "data": "synthetic",
+                "config": {"workload": "GaussNewton least squares, J materialised row-major in HBM (BASELINE configs[4])", "rows_total": rows,
+                           "fused_residual": fused,
+                           "rows_per_gpu": m_local, "n": N, "parallelism": f"row-sharded x{world}, all-reduce of {N * N + N + 2} floats per iteration",
+                           "l2": "J shard (>= 8 GB) exceeds the 126 MB L2"},
+                "roofline": {"bound": "hbm", "achieved": j_bytes / (ms_gram / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": j_bytes / (ms_gram / 1e3) / 1e9 / peak, "traffic": None, "kernel": "gram_kernel", "peak_source": peak_src,
+                             "algorithmic_bytes_per_row": N * 4},
+                "tensor": {"achieved_tflops_full_2mn2": gram_tflops, "executed_fraction_of_full": 0.75,
+                           "peak_tflops_tf32_assumed": tf32_peak, "frac": (gram_tflops / tf32_peak) if tf32_peak else None,
+                           "note": "tf32 peak assumed = measured bf16 peak / 2 (no tf32 measurement in MEASURED_PEAKS.json)"},
+                "breakdown_ms": {"residual_pass": ms_res, "gram": ms_gram, "allreduce+solve": ms - ms_res - ms_gram},
+                "gpu_launches": (3 if fused else 4) * K, "clocks": clocks, "cpu_baseline": None, "e2e": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_reference(name, inp, sample, linsolve="qr"):
     """The reference algorithm restated on the CPU (oracle), all host threads, on the first `sample` problems."""
     from oracle import c_oracle
@@ -196,9 +316,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gauss2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="gauss2", choices=sorted(WORKLOADS) + ["gram"])
+    ap.add_argument("--rows", type=int, default=64 << 20, help="gram workload: total rows of J over all ranks")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the BASELINE config)")
     ap.add_argument("--chunk", type=int, default=1 << 15, help="problems per pipeline stage in the host entry point")
+    ap.add_argument("--unfused", action="store_true", help="gram workload: separate residual pass (J read twice per iteration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -207,6 +329,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
+    if name == "gram":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "gram workload has no CPU reference arm (68.7 GB QR); see tests/test_gram_gpu.py for parity"}))
+            return
+        return bench_gram(args, rank, world, local_rank)
     desc, batch, bytes_per_problem, dtype = WORKLOADS[name]
     if args.batch:
         batch = args.batch

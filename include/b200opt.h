@@ -183,6 +183,12 @@ int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t
 int64_t b200opt_gn_gram_workspace_size(int32_t n);
 int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace,
                         void* stream);
+/* Fused variant for the "linear_rows" family: forms r = J y - d from the same shared-memory tile the tensor core is
+ * multiplying, so J is read from HBM ONCE per Gauss-Newton iteration. Writes r_out [m_local]; if r_old is not NULL
+ * also the f-space termination statistic (see b200opt_linear_residual) into *fmax_bits (caller-zeroed). */
+int32_t b200opt_gn_gram_linear(const float* J, const float* y, const float* d, const float* r_old, float* r_out,
+                               uint32_t* fmax_bits, float rtol, float atol, int64_t m_local, int32_t n, float* out,
+                               void* workspace, void* stream);
 /* Solve (G + lambda I) p = g in fp64 on one CTA; gram_out is the (all-reduced) output of b200opt_gn_gram;
  * p_out [n] fp32; status_out: device int32 result code (singular if the solution is non-finite); `workspace` is
  * the same buffer that was given to b200opt_gn_gram. */

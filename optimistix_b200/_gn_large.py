@@ -1,8 +1,10 @@
 """GaussNewton on ONE large, row-sharded least-squares problem (BASELINE configs[4]; SURVEY sections 3.4 and 8e).
 
 Each rank holds a contiguous shard of the rows of J (and of d); every rank holds the same y.  Per iteration:
-    r      = J y_eval - d                       b200opt_linear_residual (one coalesced pass, fused f-test statistic)
-    G,g,rr = J^T J, J^T r, r^T r                b200opt_gn_gram (tcgen05 tensor cores, TMA-fed, fp32 accumulate in TMEM)
+    r      = J y_eval - d                       } b200opt_gn_gram_linear: ONE pass over J (TMA -> shared memory); the
+    G,g,rr = J^T J, J^T r, r^T r                } tile feeds the tcgen05 tensor cores (fp32 accumulate in TMEM) and the
+                                                  CUDA-core residual / J^T r / f-test statistic at the same time
+                                                  (unfused pair: b200opt_linear_residual + b200opt_gn_gram)
     all-reduce [G | g | rr] (sum) and the f-test statistic (max) over the ranks   -- the ONLY exchange: n^2+n+2 floats
     p      = G^-1 g                             b200opt_gn_solve (fp64 Cholesky, identical on every rank)
     y, y_eval = y_eval, y_eval - p
@@ -51,16 +53,26 @@ class CudaOps:
                                             self._stream()), "b200opt_gn_gram")
         self.launches += 2
 
+    def residual_gram(self, J, y, d, r_out, r_old, rtol, atol, fmax, out):
+        """Fused pass: r = J y - d, the f-space statistic, G, g and rr from ONE read of J (b200opt_gn_gram_linear)."""
+        fmax.zero_()
+        _lib.check(self.lib.b200opt_gn_gram_linear(J.data_ptr(), y.data_ptr(), d.data_ptr(),
+                                                   r_old.data_ptr() if r_old is not None else None, r_out.data_ptr(),
+                                                   fmax.data_ptr(), rtol, atol, J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+                                                   self._stream()), "b200opt_gn_gram_linear")
+        self.launches += 2
+
     def solve(self, out, lam, p, status):
         _lib.check(self.lib.b200opt_gn_solve(out.data_ptr(), N, float(lam), p.data_ptr(), status.data_ptr(), self.ws.data_ptr(),
                                              self._stream()), "b200opt_gn_solve")
         self.launches += 1
 
 
-def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None):
+def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None, fused=True):
     """Solve min_y |J y - d|^2 with this rank's row shard (J [m_local, 256] fp32, d [m_local]); returns a Solution.
 
-    `group`: a torch.distributed process group (None = the default group if initialised, else single rank)."""
+    `group`: a torch.distributed process group (None = the default group if initialised, else single rank).
+    `fused`: form the residual inside the Gram kernel (J is read once per iteration) when `ops` offers it."""
     import torch
     import torch.distributed as dist
 
@@ -80,6 +92,7 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     if y.shape != (N,):
         raise ValueError(f"y0 must have shape [{N}]")
     rtol, atol = float(solver.rtol), float(solver.atol)
+    fused = fused and hasattr(ops, "residual_gram")
     y_eval = y.clone()
     r_old = torch.zeros(m_local, dtype=torch.float32, device=dev)  # gauss_newton.py:229-230: zero-filled f_info
     r_new = torch.empty_like(r_old)
@@ -92,8 +105,11 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     steps = 0
     while not terminate and result == RESULTS.successful and steps < max_steps:
         y_old_finite = bool(torch.isfinite(y).all())
-        ops.residual(J, y_eval, d, r_new, r_old, rtol, atol, fmax)  # gauss_newton.py:253 + f-space half of :280-288
-        ops.gram(J, r_new, out)
+        if fused:
+            ops.residual_gram(J, y_eval, d, r_new, r_old, rtol, atol, fmax, out)  # one read of J per iteration
+        else:
+            ops.residual(J, y_eval, d, r_new, r_old, rtol, atol, fmax)  # gauss_newton.py:253 + f-space half of :280-288
+            ops.gram(J, r_new, out)
         if distributed:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(fmax, op=dist.ReduceOp.MAX, group=group)

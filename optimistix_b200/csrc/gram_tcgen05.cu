@@ -39,7 +39,7 @@ constexpr int GROUP_BYTES = KROWS * 128;                // 8 KiB: one TMA box in
 constexpr int TILE_BYTES = GROUPS * GROUP_BYTES;        // 64 KiB
 constexpr int THREADS = 320;                            // warp 0: TMA, warp 1: MMA/TMEM, warps 2-9: g, rr, epilogue
 constexpr int TMEM_COLS = 512;                          // 384 used
-constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * TILE_BYTES + STAGES * KROWS * 4 + 256;
+constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * TILE_BYTES + 3 * STAGES * KROWS * 4 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -115,7 +115,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 struct Params {
-  const float* r;      // [m]
+  const float* r;      // [m] residual (plain mode), or the data vector d (fused mode: r = J y - d is formed in-kernel)
+  const float* y;      // [N] fused mode: current iterate; NULL = plain mode
+  const float* r_old;  // [m] fused mode, optional: previous residual for the f-space termination statistic
+  float* r_out;        // [m] fused mode: residual written back
+  unsigned* fmax_bits; // fused mode, optional: max_i |r_i - r_old_i| / (atol + rtol |r_i|) as IEEE bits (atomicMax)
+  float rtol, atol;
   int64_t m;
   float* ws;           // per-CTA partials: [grid][N*N + N + 1] (+ padding to a multiple of 4 floats)
   int num_tiles;
@@ -126,8 +131,10 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* tiles = smem;                                             // STAGES x 64 KiB, 1024-byte aligned
-  float* rs = reinterpret_cast<float*>(smem + (size_t)STAGES * TILE_BYTES);  // STAGES x KROWS floats
-  uint64_t* full = reinterpret_cast<uint64_t*>(rs + STAGES * KROWS);       // TMA -> consumers
+  float* rs = reinterpret_cast<float*>(smem + (size_t)STAGES * TILE_BYTES);  // STAGES x KROWS: residual tile (or d tile)
+  float* ros = rs + STAGES * KROWS;                                         // STAGES x KROWS: previous residual tile
+  float* rcs = ros + STAGES * KROWS;                                        // STAGES x KROWS: residual formed in-kernel
+  uint64_t* full = reinterpret_cast<uint64_t*>(rcs + STAGES * KROWS);      // TMA -> consumers
   uint64_t* empty = full + STAGES;                                          // consumers -> TMA
   uint64_t* accum_done = empty + STAGES;                                    // last MMA retired -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
@@ -163,11 +170,13 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
         const int64_t row0 = tile * KROWS;
         const int64_t rows_left = p.m - row0;
         const uint32_t r_bytes = (uint32_t)((rows_left < KROWS ? rows_left : KROWS) * 4);
-        mbar_expect_tx(&full[s], TILE_BYTES + r_bytes);   // out-of-bounds rows are zero-filled and still counted
+        const bool with_old = p.y != nullptr && p.r_old != nullptr;
+        mbar_expect_tx(&full[s], TILE_BYTES + r_bytes * (with_old ? 2u : 1u));  // OOB rows are zero-filled and still counted
         unsigned char* dst = tiles + (size_t)s * TILE_BYTES;
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) tma_load_2d(dst + g * GROUP_BYTES, &tmap, g * BOX_COLS, (int)row0, &full[s]);
         bulk_load_1d(rs + s * KROWS, p.r + row0, r_bytes, &full[s]);
+        if (with_old) bulk_load_1d(ros + s * KROWS, p.r_old + row0, r_bytes, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -198,7 +207,27 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     // ================================ g = J^T r, rr = r^T r on CUDA cores ================================
     const int b = threadIdx.x - 64;                 // this thread's column of J, 0..255
     const int grp = b >> 5, atom = (b & 31) >> 3, word = b & 7;
-    float acc_g = 0.f, acc_rr = 0.f;
+    const bool fused = p.y != nullptr;
+    // fused mode: lane l of g-warp w forms part of r for row 8w + (l >> 2): columns {32 g + 8 (l & 3) .. +7, g = 0..7}
+    const int gw = warp - 2, my_row = 8 * gw + (lane >> 2), my_atom = lane & 3;
+    // the two 16-byte halves of a 32-byte atom are read in opposite order by odd/even rows, so that the 8 lanes of a
+    // quarter-warp (2 rows x 4 atoms) hit 8 distinct 16-byte bank groups; y is loaded in the matching order
+    const int flip = (lane >> 2) & 1;
+    float yreg[64];
+    if (fused) {
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yreg[g8 * 8 + e] = p.y[g8 * 32 + my_atom * 8 + (e ^ (flip << 2))];
+    }
+    // byte offset of (row 4k + q, column b) inside a tile is  grp * GROUP_BYTES + 512 k + goff[q]  (swizzle: the
+    // 32-byte atom index is XORed with row & 3), so the row loop needs no address arithmetic
+    uint32_t goff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) goff[q] = (uint32_t)(grp * GROUP_BYTES + q * 128 + ((atom ^ q) << 5) + (word << 2));
+    const uint32_t roff = (uint32_t)(my_row * 128 + ((my_atom ^ (my_row & 3)) << 5));
+    float acc_g[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc_rr = 0.f, worst = 0.f;
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -206,22 +235,87 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t rows_left = p.m - tile * KROWS;
       const int rows = rows_left < KROWS ? (int)rows_left : KROWS;
-      const unsigned char* gbase = tiles + (size_t)s * TILE_BYTES + grp * GROUP_BYTES;
+      const unsigned char* tbase = tiles + (size_t)s * TILE_BYTES;
       const float* rt = rs + s * KROWS;
-#pragma unroll 8
-      for (int r = 0; r < rows; ++r) {
-        const float jv = *reinterpret_cast<const float*>(gbase + r * 128 + ((atom ^ (r & 3)) << 5) + (word << 2));
-        const float rv = rt[r];
-        acc_g = fmaf(jv, rv, acc_g);
-        acc_rr = fmaf(rv, rv, acc_rr);
+      if (fused) {
+        // r = J y - d for this tile: 4 lanes per row, 64 FMAs each (4 independent chains), two 128-bit loads per atom
+        float dot[4] = {0.f, 0.f, 0.f, 0.f};
+        const unsigned char* ap = tbase + roff;
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {
+          const float4 v0 = *reinterpret_cast<const float4*>(ap + g8 * GROUP_BYTES + (flip << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(ap + g8 * GROUP_BYTES + ((flip ^ 1) << 4));
+          dot[0] = fmaf(v0.x, yreg[g8 * 8 + 0], dot[0]);
+          dot[1] = fmaf(v0.y, yreg[g8 * 8 + 1], dot[1]);
+          dot[2] = fmaf(v0.z, yreg[g8 * 8 + 2], dot[2]);
+          dot[3] = fmaf(v0.w, yreg[g8 * 8 + 3], dot[3]);
+          dot[0] = fmaf(v1.x, yreg[g8 * 8 + 4], dot[0]);
+          dot[1] = fmaf(v1.y, yreg[g8 * 8 + 5], dot[1]);
+          dot[2] = fmaf(v1.z, yreg[g8 * 8 + 6], dot[2]);
+          dot[3] = fmaf(v1.w, yreg[g8 * 8 + 7], dot[3]);
+        }
+        // combine in an order that does not depend on `flip`: (elements 0-3) + (elements 4-7) of every atom
+        float lo = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+        lo += __shfl_xor_sync(kFull, lo, 1);
+        lo += __shfl_xor_sync(kFull, lo, 2);
+        if (my_atom == 0) {
+          float rv = 0.f;
+          if (my_row < rows) {
+            rv = lo - rt[my_row];  // rt holds the d tile in fused mode
+            p.r_out[tile * KROWS + my_row] = rv;
+            if (p.r_old) worst = nan_max(worst, fabsf(rv - ros[s * KROWS + my_row]) / (p.atol + p.rtol * fabsf(rv)));
+            acc_rr = fmaf(rv, rv, acc_rr);
+          }
+          rcs[s * KROWS + my_row] = rv;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 g-warps only
+        rt = rcs + s * KROWS;
+      } else if (gw == 0) {
+        // rr = r^T r: one warp, two rows per lane
+        if (lane < rows) acc_rr = fmaf(rt[lane], rt[lane], acc_rr);
+        if (lane + 32 < rows) acc_rr = fmaf(rt[lane + 32], rt[lane + 32], acc_rr);
+      }
+      // g += J_tile^T r_tile: thread b owns column b; four rows per step (one 128-bit broadcast load of r)
+      const unsigned char* g0 = tbase + goff[0];
+      const unsigned char* g1 = tbase + goff[1];
+      const unsigned char* g2 = tbase + goff[2];
+      const unsigned char* g3 = tbase + goff[3];
+      if (rows == KROWS) {
+#pragma unroll
+        for (int k = 0; k < KROWS / 4; ++k) {
+          const float4 rv = *reinterpret_cast<const float4*>(rt + 4 * k);
+          acc_g[0] = fmaf(*reinterpret_cast<const float*>(g0 + 512 * k), rv.x, acc_g[0]);
+          acc_g[1] = fmaf(*reinterpret_cast<const float*>(g1 + 512 * k), rv.y, acc_g[1]);
+          acc_g[2] = fmaf(*reinterpret_cast<const float*>(g2 + 512 * k), rv.z, acc_g[2]);
+          acc_g[3] = fmaf(*reinterpret_cast<const float*>(g3 + 512 * k), rv.w, acc_g[3]);
+        }
+      } else {
+        for (int k = 0; k < rows / 4; ++k) {  // ragged last tile (m is a multiple of 4)
+          const float4 rv = *reinterpret_cast<const float4*>(rt + 4 * k);
+          acc_g[0] = fmaf(*reinterpret_cast<const float*>(g0 + 512 * k), rv.x, acc_g[0]);
+          acc_g[1] = fmaf(*reinterpret_cast<const float*>(g1 + 512 * k), rv.y, acc_g[1]);
+          acc_g[2] = fmaf(*reinterpret_cast<const float*>(g2 + 512 * k), rv.z, acc_g[2]);
+          acc_g[3] = fmaf(*reinterpret_cast<const float*>(g3 + 512 * k), rv.w, acc_g[3]);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+    if (fused && p.fmax_bits && my_atom == 0)
+      atomicMax(p.fmax_bits, __float_as_uint(worst != worst ? __int_as_float(0x7fc00000) : worst));
+    // rr: butterfly inside each warp, then the 8 warp totals in a fixed order (deterministic)
+    acc_rr = warp_sum(acc_rr);
+    if (lane == 0) ros[gw] = acc_rr;  // `ros` is idle by now: its last readers are before the last tile's bar.sync
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // ================================ epilogue: TMEM -> per-CTA partial in the workspace ================================
     float* ws = p.ws + (size_t)blockIdx.x * WS_STRIDE;
-    ws[N * N + b] = acc_g;
-    if (b == 0) ws[N * N + N] = acc_rr;
+    ws[N * N + b] = (acc_g[0] + acc_g[1]) + (acc_g[2] + acc_g[3]);
+    if (b == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += ros[w];
+      ws[N * N + N] = t;
+    }
     if (my_tiles > 0) {
       mbar_wait(accum_done, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -305,7 +399,31 @@ int64_t b200opt_gn_gram_workspace_size(int32_t n) {
   return (int64_t)256 * gram::WS_STRIDE * 4 + (int64_t)n * n * 8 + 4096;
 }
 
+static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
+                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream);
+
 int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
+  return gn_gram_impl(J, r, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, m_local, n, out, workspace, stream);
+}
+
+int32_t b200opt_gn_gram_linear(const float* J, const float* y, const float* d, const float* r_old, float* r_out,
+                               uint32_t* fmax_bits, float rtol, float atol, int64_t m_local, int32_t n, float* out,
+                               void* workspace, void* stream) {
+  if (!y || !d || !r_out) {
+    set_error("gn_gram_linear: NULL buffer");
+    return B200OPT_EINVAL;
+  }
+  if (r_old && (reinterpret_cast<uintptr_t>(r_old) & 15)) {
+    set_error("gn_gram_linear: r_old must be 16-byte aligned");
+    return B200OPT_EINVAL;
+  }
+  return gn_gram_impl(J, d, y, r_old, r_out, fmax_bits, rtol, atol, m_local, n, out, workspace, stream);
+}
+
+}  // extern "C"
+
+static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
+                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
   if (n != gram::N) {
     set_error("gn_gram: this build supports n = %d parameters only (got %d)", gram::N, n);
     return B200OPT_EINVAL;
@@ -356,7 +474,7 @@ int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t
       return B200OPT_ECUDA;
     attr_set = true;
   }
-  gram::Params p{r, m_local, ws, num_tiles};
+  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles};
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;
@@ -364,4 +482,4 @@ int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t
   return check_cuda(cudaGetLastError(), "gram_reduce_kernel launch");
 }
 
-}  // extern "C"
+

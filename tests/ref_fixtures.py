@@ -11,7 +11,6 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-torch.set_default_dtype(torch.float64)
 _rng = np.random.default_rng(17)
 
 

@@ -75,15 +75,67 @@ def test_gauss_newton_large_matches_lstsq_and_oracle():
     assert np.allclose(sol.value.cpu().numpy(), ref["value"][0], rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("m", [64, 4096, 100000, 9472 * 64 + 20])
+@pytest.mark.parametrize("with_old", [False, True])
+def test_fused_residual_gram_matches_unfused(m, with_old):
+    """b200opt_gn_gram_linear (one pass over J) against b200opt_linear_residual + b200opt_gn_gram and fp64."""
+    lib = _lib.load()
+    m = m - m % 4
+    w = synthetic.linear_lsq_rows(m, seed=11)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    y = torch.randn(N, dtype=torch.float32, device=DEV, generator=gen)
+    r_old = torch.randn(m, dtype=torch.float32, device=DEV, generator=gen) if with_old else None
+    st = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    out = torch.empty(N * N + N + 1, dtype=torch.float32, device=DEV)
+    r = torch.full((m,), float("nan"), dtype=torch.float32, device=DEV)
+    fmax = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.b200opt_gn_gram_linear(J.data_ptr(), y.data_ptr(), d.data_ptr(), r_old.data_ptr() if with_old else None,
+                                          r.data_ptr(), fmax.data_ptr(), 1e-4, 1e-4, m, N, out.data_ptr(), ws.data_ptr(), st),
+               "gn_gram_linear")
+    torch.cuda.synchronize()
+    Jd = J.double()
+    r_ref = Jd @ y.double() - d.double()
+    rscale = Jd.abs() @ y.double().abs() + d.double().abs()
+    assert ((r.double() - r_ref).abs() / rscale).max().item() < 1e-5
+    if with_old:
+        stat_ref = ((r - r_old).abs() / (1e-4 + 1e-4 * r.abs())).max()
+        assert torch.allclose(fmax.view(torch.float32)[0], stat_ref, rtol=1e-6)  # fma contraction of atol + rtol |r|
+    # Gram / gradient of the residual the kernel itself wrote: identical to the unfused kernel on that residual
+    G2, g2, rr2 = _gram(J, r)
+    assert torch.equal(out[: N * N].view(N, N), G2)
+    gscale = Jd.abs().T @ r.double().abs()
+    assert ((out[N * N : N * N + N].double() - Jd.T @ r.double()).abs() / gscale).max().item() < 1e-5
+    assert abs(out[N * N + N].item() - rr2.item()) <= 1e-5 * rr2.item()
+
+
+def test_gauss_newton_large_fused_equals_unfused():
+    from optimistix_b200._gn_large import gauss_newton_large
+
+    m = 65536
+    w = synthetic.linear_lsq_rows(m, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y0 = torch.zeros(N, dtype=torch.float32, device=DEV)
+    a = gauss_newton_large(J, d, y0, optx.GaussNewton(1e-4, 1e-4), throw=False, fused=True)
+    b = gauss_newton_large(J, d, y0, optx.GaussNewton(1e-4, 1e-4), throw=False, fused=False)
+    assert a.result == b.result == optx.RESULTS.successful
+    assert a.stats["num_steps"] == b.stats["num_steps"]
+    assert torch.allclose(a.value, b.value, rtol=1e-5, atol=1e-6)
+    assert a.stats["gpu_launches"] < b.stats["gpu_launches"]
+
+
 def test_gn_solve_and_residual_kernels():
     lib = _lib.load()
     m = 4096
     w = synthetic.linear_lsq_rows(m, seed=7)
     J = torch.as_tensor(w["J"], device=DEV)
     d = torch.as_tensor(w["d"], device=DEV)
-    y = torch.randn(N, device=DEV)
-    r = torch.empty(m, device=DEV)
-    r_old = torch.randn(m, device=DEV)
+    y = torch.randn(N, dtype=torch.float32, device=DEV)
+    r = torch.empty(m, dtype=torch.float32, device=DEV)
+    r_old = torch.randn(m, dtype=torch.float32, device=DEV)
     fmax = torch.zeros(1, dtype=torch.int32, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(lib.b200opt_linear_residual(J.data_ptr(), y.data_ptr(), d.data_ptr(), m, N, r.data_ptr(), r_old.data_ptr(), 1e-4, 1e-4,
@@ -95,10 +147,10 @@ def test_gn_solve_and_residual_kernels():
     # solve
     A = torch.randn(N, N, dtype=torch.float64)
     Gm = (A @ A.T + N * torch.eye(N, dtype=torch.float64)).float()
-    g = torch.randn(N)
-    out = torch.cat([Gm.reshape(-1), g, torch.zeros(1)]).to(DEV)
+    g = torch.randn(N, dtype=torch.float32)
+    out = torch.cat([Gm.reshape(-1), g, torch.zeros(1, dtype=torch.float32)]).to(DEV)
     ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
-    p = torch.empty(N, device=DEV)
+    p = torch.empty(N, dtype=torch.float32, device=DEV)
     status = torch.full((1,), -1, dtype=torch.int32, device=DEV)
     _lib.check(lib.b200opt_gn_solve(out.data_ptr(), N, 0.5, p.data_ptr(), status.data_ptr(), ws.data_ptr(), st), "gn_solve")
     p_ref = torch.linalg.solve(Gm.double() + 0.5 * torch.eye(N, dtype=torch.float64), g.double())
