@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200opt.so")
+LIB_PATH = os.environ.get("B200OPT_LIB") or os.path.join(_HERE, "libb200opt.so")  # env: tuning builds (tools/gram_variants.sh)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200opt.h")
 
 F32, F64 = 0, 1

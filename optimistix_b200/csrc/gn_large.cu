@@ -1,5 +1,5 @@
 // Support kernels of the single large Gauss-Newton problem (BASELINE configs[4]):
-//   b200opt_gn_solve        (G + lambda I) p = g by Cholesky in fp64, one CTA (n = 256: 5.6 Mflop, latency bound)
+//   b200opt_gn_solve        (G + lambda I) p = g by blocked Cholesky in fp64, one CTA (n = 256: 5.6 Mflop, barrier-latency bound)
 //   b200opt_linear_residual r = J y - d for the "linear_rows" family, one warp per row, coalesced float4 reads,
 //                           fused with the f-space half of cauchy_termination (optimistix/_misc.py:306-309):
 //                           max_i |r_new_i - r_old_i| / (atol + rtol |r_new_i|)
@@ -7,53 +7,179 @@
 
 namespace b200opt {
 
-// Right-looking Cholesky on an n x n fp64 matrix held in global memory (L2 resident, 512 KiB at n = 256).
+// Blocked right-looking Cholesky + both triangular solves on ONE CTA (the whole problem is 5.6 Mflop; what matters is
+// the number of block-wide barriers on the critical path, not the flop rate):
+//   * panels of 32 columns live in shared memory (unscaled working copy P and the finished, scaled factor Lp);
+//     a column step costs ONE barrier: the scaled column is written to Lp / the forward substitution is applied to z
+//     while the remaining panel columns are updated from the unscaled values, and the thread that produces the next
+//     pivot also produces its reciprocal square root;
+//   * the trailing matrix (fp64, global memory, L2 resident) is updated once per panel (rank-32) with 64x64 tiles of
+//     4x4 register micro-tiles;
+//   * the backward substitution walks the panels in reverse: a parallel mat-vec with the already known part of p,
+//     then a 32-step in-warp substitution on the diagonal block using the saved reciprocals.
+// A non-positive pivot gives NaN/inf, which propagates to p and is reported as `singular` (as lineax does).
+constexpr int SOLVE_PW = 32;                 // panel width
+constexpr int SOLVE_LD = SOLVE_PW + 1;       // row pitch of the panel buffers (odd: conflict-free row and column access)
+constexpr size_t SOLVE_SMEM = (size_t)(256 * SOLVE_LD + 3 * 256 + 3 * SOLVE_PW + 8) * sizeof(double);
+
 __global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out, int n, double lambda, double* A, float* p_out,
                                                            int32_t* status) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  __shared__ double colk[256];
-  __shared__ double z[256];
+  extern __shared__ double sm[];
+  double* Lp = sm;                          // [256][SOLVE_LD] finished panel of the factor (rows c0..n-1 used)
+  double* z = Lp + 256 * SOLVE_LD;          // [256] right-hand side -> L^-1 g
+  double* rinv = z + 256;                   // [256] 1 / L_kk
+  double* pv = rinv + 256;                  // [256] solution
+  double* zs = pv + 256;                    // [SOLVE_PW] panel right-hand side of the backward sweep
+  double* colbuf = zs + SOLVE_PW;           // [2][SOLVE_PW] unscaled column of the diagonal block (ping-pong)
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  // lower triangle of G + lambda I in fp64
   for (int e = tid; e < n * n; e += nt) {
-    const int i = e / n, j = e % n;
-    A[e] = (double)gram_out[e] + (i == j ? lambda : 0.0);
+    const int i = e / n, j = e - i * n;
+    if (j <= i) A[e] = (double)gram_out[e] + (i == j ? lambda : 0.0);
   }
-  __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    if (tid == 0) colk[k] = sqrt(A[k * n + k]);  // NaN for a non-positive pivot -> non-finite solution -> singular
-    __syncthreads();
-    const double dk = colk[k];
-    for (int i = k + 1 + tid; i < n; i += nt) colk[i] = A[i * n + k] / dk;
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
-    const int rem = n - k - 1;
-    for (int e = tid; e < rem * rem; e += nt) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) A[i * n + j] -= colk[i] * colk[j];
-    }
-    for (int i = k + tid; i < n; i += nt) A[i * n + k] = colk[i];  // store column k of L
-    __syncthreads();
-  }
-  // forward / backward substitution (sequential in k, parallel over rows)
   for (int i = tid; i < n; i += nt) z[i] = (double)gram_out[n * n + i];
   __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    if (tid == 0) z[k] = z[k] / A[k * n + k];
+
+  const int npanels = (n + SOLVE_PW - 1) / SOLVE_PW;
+  for (int pb = 0; pb < npanels; ++pb) {
+    const int c0 = pb * SOLVE_PW;
+    const int pw = min(SOLVE_PW, n - c0);
+    // ---- the panel lives in REGISTERS: thread t holds columns 8 cg .. 8 cg + 7 of row c0 + t / 4 (cg = t % 4), so
+    // the four threads of a row are adjacent lanes.  Column step c (k = c0 + c), ONE barrier:
+    //   l_i   = P[i][c] / sqrt(pivot): from the owner lane of the row by shuffle; the owner also stores it to Lp and
+    //           applies the fused forward substitution to z[i]
+    //   P[i][cp] -= l_i * l_(c0+cp)  for cp > c: the unscaled column-c entries of the 32 diagonal-block rows were
+    //           published to `colbuf` by their owners at the end of step c - 1 (after their last update), together
+    //           with the reciprocal square root of the next pivot
+    const int prow = c0 + (tid >> 2), cg = tid & 3;
+    const bool prow_on = prow < n;
+    double pr[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int cp = 8 * cg + e;
+      pr[e] = (prow_on && cp < pw && c0 + cp <= prow) ? A[(size_t)prow * n + c0 + cp] : 0.0;
+    }
+    if (prow_on && prow - c0 < SOLVE_PW && cg == 0) {
+      colbuf[prow - c0] = pr[0];
+      if (prow == c0) rinv[c0] = rsqrt(pr[0]);
+    }
     __syncthreads();
-    const double zk = z[k];
-    for (int i = k + 1 + tid; i < n; i += nt) z[i] -= A[i * n + k] * zk;
+#pragma unroll
+    for (int cgc = 0; cgc < 4; ++cgc) {
+#pragma unroll
+      for (int ec = 0; ec < 8; ++ec) {
+        const int c = 8 * cgc + ec;
+        if (c < pw) {                              // block-uniform
+          const int k = c0 + c;
+          const double* cb = colbuf + (c & 1) * SOLVE_PW;
+          double* cbn = colbuf + ((c + 1) & 1) * SOLVE_PW;
+          const double inv = rinv[k];
+          const double zk = z[k] * inv;
+          const double li = __shfl_sync(kFull, pr[ec], (lane & ~3) | cgc) * inv;   // L[prow][k]
+          if (prow_on && prow >= k) {
+            if (cg == cgc) {
+              Lp[prow * SOLVE_LD + c] = li;
+              if (prow > k) z[prow] -= li * zk;
+              else pv[k] = zk;                       // pv holds L^-1 g until the backward sweep overwrites it
+            }
+            if (prow > k) {
+              const double lis = li * inv;           // l_i / sqrt(pivot): the published column entries are unscaled
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int cp = 8 * cg + e;
+                if (cp > c) pr[e] = fma(-lis, cb[cp], pr[e]);
+              }
+              // publish column c + 1 of the diagonal-block rows (now final) and the next reciprocal pivot root
+              if (c + 1 < pw && prow - c0 < SOLVE_PW && cg == ((c + 1) >> 3)) {
+                const double v = pr[(ec + 1) & 7];
+                cbn[prow - c0] = v;
+                if (prow == k + 1) rinv[k + 1] = rsqrt(v);
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    // ---- store the finished panel (needed by the backward sweep) and apply the rank-pw update to the trailing matrix
+    for (int e = tid; e < (n - c0) * SOLVE_PW; e += nt) {
+      const int i = c0 + (e >> 5), c = e & 31;
+      if (c < pw && c0 + c <= i) A[(size_t)i * n + c0 + c] = Lp[i * SOLVE_LD + c];
+    }
+    const int t0 = c0 + pw;                      // first trailing row / column
+    const int R = n - t0;
+    if (R > 0) {
+      const int nbt = (R + 63) >> 6;             // 64 x 64 tiles, lower block triangle
+      const int ntiles = nbt * (nbt + 1) / 2;
+      const int quarter = tid >> 8, t256 = tid & 255, tx = t256 & 15, ty = t256 >> 4;
+      for (int tile = quarter; tile < ntiles; tile += 4) {
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
+        const int bj = tile - bi * (bi + 1) / 2;
+        const int i0 = t0 + 64 * bi + ty, j0 = t0 + 64 * bj + tx;  // lanes run along j: A accesses are coalesced
+        double acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+        for (int c = 0; c < pw; ++c) {
+          double li[4], lj[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i0 + 16 * e, j = j0 + 16 * e;
+            li[e] = i < n ? Lp[i * SOLVE_LD + c] : 0.0;
+            lj[e] = j < n ? Lp[j * SOLVE_LD + c] : 0.0;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = fma(li[e], lj[f], acc[e][f]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int i = i0 + 16 * e, j = j0 + 16 * f;
+            if (i < n && j <= i) A[(size_t)i * n + j] -= acc[e][f];
+          }
+      }
+    }
     __syncthreads();
   }
-  for (int k = n - 1; k >= 0; --k) {
-    if (tid == 0) z[k] = z[k] / A[k * n + k];
+
+  // ---- backward sweep: L^T p = z  (pv currently holds z = L^-1 g)
+  for (int pb = npanels - 1; pb >= 0; --pb) {
+    const int c0 = pb * SOLVE_PW;
+    const int pw = min(SOLVE_PW, n - c0);
+    for (int e = tid; e < (n - c0) * SOLVE_PW; e += nt) {
+      const int i = c0 + (e >> 5), c = e & 31;
+      Lp[i * SOLVE_LD + c] = (c < pw && c0 + c <= i) ? A[(size_t)i * n + c0 + c] : 0.0;
+    }
     __syncthreads();
-    const double zk = z[k];
-    for (int i = tid; i < k; i += nt) z[i] -= A[k * n + i] * zk;
+    {  // warp c: s_c = sum_{i >= c0 + pw} L[i][c0 + c] p_i
+      const int c = warp;
+      double sacc = 0.0;
+      if (c < pw)
+        for (int i = c0 + pw + lane; i < n; i += 32) sacc = fma(Lp[i * SOLVE_LD + c], pv[i], sacc);
+      sacc = warp_sum(sacc);
+      if (lane == 0 && c < pw) zs[c] = pv[c0 + c] - sacc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x = lane < pw ? zs[lane] : 0.0;
+      for (int c = pw - 1; c >= 0; --c) {
+        const double pc = __shfl_sync(kFull, x, c) * rinv[c0 + c];
+        if (lane < c) x -= Lp[(c0 + c) * SOLVE_LD + lane] * pc;   // (L^T)[lane][c] = L[c][lane]
+        if (lane == c) x = pc;
+      }
+      if (lane < pw) pv[c0 + lane] = x;
+    }
     __syncthreads();
   }
   int ok = 1;
   for (int i = tid; i < n; i += nt) {
-    p_out[i] = (float)z[i];
-    if (!isfinite(z[i])) ok = 0;
+    p_out[i] = (float)pv[i];
+    if (!isfinite(pv[i])) ok = 0;
   }
   ok = __syncthreads_and(ok);
   if (tid == 0 && status) *status = ok ? RES_OK : RES_SINGULAR;  // lineax: non-finite solution => singular
@@ -107,7 +233,14 @@ int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float*
   }
   // the fp64 scratch sits after the per-CTA partials of b200opt_gn_gram in the same workspace
   double* A = reinterpret_cast<double*>(static_cast<char*>(workspace) + (size_t)256 * (256 * 256 + 256 + 4) * 4);
-  gn_solve_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(gram_out, n, lambda, A, p_out, status_out);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(gn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM),
+                   "cudaFuncSetAttribute(gn_solve_kernel)"))
+      return B200OPT_ECUDA;
+    attr_set = true;
+  }
+  gn_solve_kernel<<<1, 1024, SOLVE_SMEM, static_cast<cudaStream_t>(stream)>>>(gram_out, n, lambda, A, p_out, status_out);
   return check_cuda(cudaGetLastError(), "gn_solve_kernel launch");
 }
 

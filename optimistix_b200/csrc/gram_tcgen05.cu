@@ -22,6 +22,7 @@
 // Roofline: HBM-bound by construction (68.7 GB of J per pass at configs[4]); tensor pipe ~55% busy at the HBM rate.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -31,15 +32,28 @@ int device_sm_count();
 namespace gram {
 
 constexpr int N = 256;            // parameters (columns of J)
-constexpr int KROWS = 64;         // rows of J per tile
-constexpr int STAGES = 3;
+#ifndef GRAM_KROWS
+#define GRAM_KROWS 64
+#endif
+#ifndef GRAM_STAGES
+#define GRAM_STAGES 3
+#endif
+constexpr int KROWS = GRAM_KROWS;   // rows of J per tile
+constexpr int STAGES = GRAM_STAGES; // STAGES * KROWS * 1 KiB of shared memory in flight per SM
 constexpr int BOX_COLS = 32;      // 32 fp32 = 128 bytes = one SWIZZLE_128B span
 constexpr int GROUPS = N / BOX_COLS;                    // 8 column groups per tile
 constexpr int GROUP_BYTES = KROWS * 128;                // 8 KiB: one TMA box in shared memory
 constexpr int TILE_BYTES = GROUPS * GROUP_BYTES;        // 64 KiB
 constexpr int THREADS = 320;                            // warp 0: TMA, warp 1: MMA/TMEM, warps 2-9: g, rr, epilogue
 constexpr int TMEM_COLS = 512;                          // 384 used
-constexpr size_t SMEM_BYTES = 1024 /*align*/ + (size_t)STAGES * TILE_BYTES + 3 * STAGES * KROWS * 4 + 256;
+constexpr int GRED_FLOATS = 8 * N + 8;                   // end-of-kernel reduction of g and rr over the 8 g-warps
+constexpr size_t SMEM_PAYLOAD = (size_t)STAGES * TILE_BYTES + 2 * STAGES * KROWS * 4 + GRED_FLOATS * 4 + 256;
+// the tiles need 1024-byte alignment (swizzle atom); reserve slack for rounding the base up unless that would exceed the
+// 227 KiB limit, in which case the kernel traps if the dynamic shared-memory window is not already aligned
+constexpr size_t SMEM_ALIGN_SLACK = (SMEM_PAYLOAD + 1024 <= 232448) ? 1024 : 0;
+constexpr size_t SMEM_BYTES = SMEM_ALIGN_SLACK + SMEM_PAYLOAD;
+static_assert(SMEM_BYTES <= 232448, "tile ring does not fit the 227 KiB of shared memory per CTA");
+static_assert(KROWS % 32 == 0, "a g-warp pass covers 32 rows of the tile");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -124,17 +138,20 @@ struct Params {
   int64_t m;
   float* ws;           // per-CTA partials: [grid][N*N + N + 1] (+ padding to a multiple of 4 floats)
   int num_tiles;
+  int debug;            // ablation switches for profiling only (env B200OPT_GRAM_DEBUG): 1 no MMA, 2 no g loop, 4 no fused r
 };
 constexpr int WS_STRIDE = N * N + N + 4;
 
 __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if (SMEM_ALIGN_SLACK) smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  else if (smem_u32(smem_raw) & 1023u) __trap();
   unsigned char* tiles = smem;                                             // STAGES x 64 KiB, 1024-byte aligned
   float* rs = reinterpret_cast<float*>(smem + (size_t)STAGES * TILE_BYTES);  // STAGES x KROWS: residual tile (or d tile)
   float* ros = rs + STAGES * KROWS;                                         // STAGES x KROWS: previous residual tile
-  float* rcs = ros + STAGES * KROWS;                                        // STAGES x KROWS: residual formed in-kernel
-  uint64_t* full = reinterpret_cast<uint64_t*>(rcs + STAGES * KROWS);      // TMA -> consumers
+  float* gred = ros + STAGES * KROWS;                                       // [8][N] + 8: g-warp partials of g and rr
+  uint64_t* full = reinterpret_cast<uint64_t*>(gred + GRED_FLOATS);        // TMA -> consumers
   uint64_t* empty = full + STAGES;                                          // consumers -> TMA
   uint64_t* accum_done = empty + STAGES;                                    // last MMA retired -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
@@ -162,9 +179,9 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer (one elected lane) ================================
     if (lane == 0) {
-      for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it, s = (s + 1 == STAGES) ? 0 : s + 1, ph ^= (s == 0)) {
         mbar_wait(&empty[s], ph ^ 1);
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
         const int64_t row0 = tile * KROWS;
@@ -184,14 +201,14 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_full = make_idesc(256);
       constexpr uint32_t idesc_half = make_idesc(128);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it, s = (s + 1 == STAGES) ? 0 : s + 1, ph ^= (s == 0)) {
         mbar_wait(&full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t base = smem_u32(tiles + (size_t)s * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < KROWS / 8; ++k) {
+        for (int k = 0; k < ((p.debug & 1) ? 0 : KROWS / 8); ++k) {
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           // rows 0-127 of G x all 256 columns -> TMEM columns [0, 256)
           umma_tf32(tmem_base + 0, make_desc(base + k * 1024), make_desc(base + k * 1024), idesc_full, acc);
@@ -205,116 +222,118 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     }
   } else {
     // ================================ g = J^T r, rr = r^T r on CUDA cores ================================
-    const int b = threadIdx.x - 64;                 // this thread's column of J, 0..255
-    const int grp = b >> 5, atom = (b & 31) >> 3, word = b & 7;
+    // ONE pass over the tile per g-warp: a lane keeps 32 columns of one row in registers, forms its share of the row's
+    // dot product with y (fused mode), gets the row's residual with a 3-step butterfly over the 8 lanes of the row, and
+    // immediately accumulates J[row][c] * r[row] into its 32 column partials of g.  Shared memory is read exactly once
+    // (512 wavefronts per 64 KiB tile) - it is the contended resource: the tensor core streams its operands from it too.
+    const int b = threadIdx.x - 64;                 // 0..255
     const bool fused = p.y != nullptr;
-    // fused mode: lane l of g-warp w forms part of r for row 8w + (l >> 2): columns {32 g + 8 (l & 3) .. +7, g = 0..7}
-    const int gw = warp - 2, my_row = 8 * gw + (lane >> 2), my_atom = lane & 3;
-    // the two 16-byte halves of a 32-byte atom are read in opposite order by odd/even rows, so that the 8 lanes of a
-    // quarter-warp (2 rows x 4 atoms) hit 8 distinct 16-byte bank groups; y is loaded in the matching order
-    const int flip = (lane >> 2) & 1;
-    float yreg[64];
-    if (fused) {
+    constexpr int LPR = 8;                          // lanes per row
+    constexpr int RPP = 32 / LPR;                   // rows per warp per pass (4)
+    constexpr int PASSES = KROWS / (8 * RPP);       // passes per tile (2 for 64-row tiles)
+    constexpr int NGRP = GROUPS / 2;                // column groups per lane (4): {gsel, gsel + 2, gsel + 4, gsel + 6}
+    const int gw = warp - 2, sub = lane % LPR, rlane = lane / LPR, my_atom = sub & 3, gsel = sub >> 2;
+    // the two 16-byte halves of a 32-byte atom are read in opposite order by the two half-rows, so that the 8 lanes of
+    // a quarter-warp (= one row) hit 8 distinct 16-byte bank groups; y is loaded in the matching order
+    const int flip = gsel;
+    float yreg[NGRP * 8];
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8)
+    for (int j = 0; j < NGRP; ++j)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) yreg[g8 * 8 + e] = p.y[g8 * 32 + my_atom * 8 + (e ^ (flip << 2))];
-    }
-    // byte offset of (row 4k + q, column b) inside a tile is  grp * GROUP_BYTES + 512 k + goff[q]  (swizzle: the
-    // 32-byte atom index is XORed with row & 3), so the row loop needs no address arithmetic
-    uint32_t goff[4];
+      for (int e = 0; e < 8; ++e) yreg[j * 8 + e] = fused ? p.y[(gsel + 2 * j) * 32 + my_atom * 8 + (e ^ (flip << 2))] : 0.f;
+    float acc_g[NGRP * 8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) goff[q] = (uint32_t)(grp * GROUP_BYTES + q * 128 + ((atom ^ q) << 5) + (word << 2));
-    const uint32_t roff = (uint32_t)(my_row * 128 + ((my_atom ^ (my_row & 3)) << 5));
-    float acc_g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < NGRP * 8; ++c) acc_g[c] = 0.f;
     float acc_rr = 0.f, worst = 0.f;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(&full[s], ph);
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t rows_left = p.m - tile * KROWS;
       const int rows = rows_left < KROWS ? (int)rows_left : KROWS;
       const unsigned char* tbase = tiles + (size_t)s * TILE_BYTES;
       const float* rt = rs + s * KROWS;
-      if (fused) {
-        // r = J y - d for this tile: 4 lanes per row, 64 FMAs each (4 independent chains), two 128-bit loads per atom
-        float dot[4] = {0.f, 0.f, 0.f, 0.f};
-        const unsigned char* ap = tbase + roff;
+      if (!(p.debug & 2)) {
 #pragma unroll
-        for (int g8 = 0; g8 < 8; ++g8) {
-          const float4 v0 = *reinterpret_cast<const float4*>(ap + g8 * GROUP_BYTES + (flip << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(ap + g8 * GROUP_BYTES + ((flip ^ 1) << 4));
-          dot[0] = fmaf(v0.x, yreg[g8 * 8 + 0], dot[0]);
-          dot[1] = fmaf(v0.y, yreg[g8 * 8 + 1], dot[1]);
-          dot[2] = fmaf(v0.z, yreg[g8 * 8 + 2], dot[2]);
-          dot[3] = fmaf(v0.w, yreg[g8 * 8 + 3], dot[3]);
-          dot[0] = fmaf(v1.x, yreg[g8 * 8 + 4], dot[0]);
-          dot[1] = fmaf(v1.y, yreg[g8 * 8 + 5], dot[1]);
-          dot[2] = fmaf(v1.z, yreg[g8 * 8 + 6], dot[2]);
-          dot[3] = fmaf(v1.w, yreg[g8 * 8 + 7], dot[3]);
-        }
-        // combine in an order that does not depend on `flip`: (elements 0-3) + (elements 4-7) of every atom
-        float lo = (dot[0] + dot[1]) + (dot[2] + dot[3]);
-        lo += __shfl_xor_sync(kFull, lo, 1);
-        lo += __shfl_xor_sync(kFull, lo, 2);
-        if (my_atom == 0) {
-          float rv = 0.f;
-          if (my_row < rows) {
-            rv = lo - rt[my_row];  // rt holds the d tile in fused mode
-            p.r_out[tile * KROWS + my_row] = rv;
-            if (p.r_old) worst = nan_max(worst, fabsf(rv - ros[s * KROWS + my_row]) / (p.atol + p.rtol * fabsf(rv)));
+        for (int pass = 0; pass < PASSES; ++pass) {
+          const int row = pass * 8 * RPP + gw * RPP + rlane;
+          const unsigned char* ap = tbase + gsel * GROUP_BYTES + row * 128 + ((my_atom ^ (row & 3)) << 5);
+          float4 v[NGRP * 2];
+#pragma unroll
+          for (int j = 0; j < NGRP; ++j) {
+            v[2 * j] = *reinterpret_cast<const float4*>(ap + j * 2 * GROUP_BYTES + (flip << 4));
+            v[2 * j + 1] = *reinterpret_cast<const float4*>(ap + j * 2 * GROUP_BYTES + ((flip ^ 1) << 4));
+          }
+          float rv = rt[row];                        // plain mode: the residual; fused mode: the data value d
+          if (fused) {
+            float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < NGRP * 2; ++q) {
+              dot[0] = fmaf(v[q].x, yreg[4 * q + 0], dot[0]);
+              dot[1] = fmaf(v[q].y, yreg[4 * q + 1], dot[1]);
+              dot[2] = fmaf(v[q].z, yreg[4 * q + 2], dot[2]);
+              dot[3] = fmaf(v[q].w, yreg[4 * q + 3], dot[3]);
+            }
+            // the partial of a lane is summed in an order that does not depend on `flip`; the butterfly leaves the
+            // same bits in all 8 lanes of the row
+            float lo = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+            lo += __shfl_xor_sync(kFull, lo, 1);
+            lo += __shfl_xor_sync(kFull, lo, 2);
+            lo += __shfl_xor_sync(kFull, lo, 4);
+            rv = lo - rv;
+          }
+          if (row >= rows) rv = 0.f;                 // ragged last tile: J rows are zero-filled, r / d rows are stale
+          if (sub == 0 && row < rows) {
+            if (fused) {
+              p.r_out[tile * KROWS + row] = rv;
+              if (p.r_old) worst = nan_max(worst, fabsf(rv - ros[s * KROWS + row]) / (p.atol + p.rtol * fabsf(rv)));
+            }
             acc_rr = fmaf(rv, rv, acc_rr);
           }
-          rcs[s * KROWS + my_row] = rv;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 g-warps only
-        rt = rcs + s * KROWS;
-      } else if (gw == 0) {
-        // rr = r^T r: one warp, two rows per lane
-        if (lane < rows) acc_rr = fmaf(rt[lane], rt[lane], acc_rr);
-        if (lane + 32 < rows) acc_rr = fmaf(rt[lane + 32], rt[lane + 32], acc_rr);
-      }
-      // g += J_tile^T r_tile: thread b owns column b; four rows per step (one 128-bit broadcast load of r)
-      const unsigned char* g0 = tbase + goff[0];
-      const unsigned char* g1 = tbase + goff[1];
-      const unsigned char* g2 = tbase + goff[2];
-      const unsigned char* g3 = tbase + goff[3];
-      if (rows == KROWS) {
 #pragma unroll
-        for (int k = 0; k < KROWS / 4; ++k) {
-          const float4 rv = *reinterpret_cast<const float4*>(rt + 4 * k);
-          acc_g[0] = fmaf(*reinterpret_cast<const float*>(g0 + 512 * k), rv.x, acc_g[0]);
-          acc_g[1] = fmaf(*reinterpret_cast<const float*>(g1 + 512 * k), rv.y, acc_g[1]);
-          acc_g[2] = fmaf(*reinterpret_cast<const float*>(g2 + 512 * k), rv.z, acc_g[2]);
-          acc_g[3] = fmaf(*reinterpret_cast<const float*>(g3 + 512 * k), rv.w, acc_g[3]);
-        }
-      } else {
-        for (int k = 0; k < rows / 4; ++k) {  // ragged last tile (m is a multiple of 4)
-          const float4 rv = *reinterpret_cast<const float4*>(rt + 4 * k);
-          acc_g[0] = fmaf(*reinterpret_cast<const float*>(g0 + 512 * k), rv.x, acc_g[0]);
-          acc_g[1] = fmaf(*reinterpret_cast<const float*>(g1 + 512 * k), rv.y, acc_g[1]);
-          acc_g[2] = fmaf(*reinterpret_cast<const float*>(g2 + 512 * k), rv.z, acc_g[2]);
-          acc_g[3] = fmaf(*reinterpret_cast<const float*>(g3 + 512 * k), rv.w, acc_g[3]);
+          for (int q = 0; q < NGRP * 2; ++q) {
+            acc_g[4 * q + 0] = fmaf(v[q].x, rv, acc_g[4 * q + 0]);
+            acc_g[4 * q + 1] = fmaf(v[q].y, rv, acc_g[4 * q + 1]);
+            acc_g[4 * q + 2] = fmaf(v[q].z, rv, acc_g[4 * q + 2]);
+            acc_g[4 * q + 3] = fmaf(v[q].w, rv, acc_g[4 * q + 3]);
+          }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
-    if (fused && p.fmax_bits && my_atom == 0)
+    if (fused && p.fmax_bits && sub == 0)
       atomicMax(p.fmax_bits, __float_as_uint(worst != worst ? __int_as_float(0x7fc00000) : worst));
-    // rr: butterfly inside each warp, then the 8 warp totals in a fixed order (deterministic)
+    // ---- g: rows of a warp (xor 8, 16), then the 8 warps through shared memory in a fixed order (deterministic)
+#pragma unroll
+    for (int c = 0; c < NGRP * 8; ++c) {
+      acc_g[c] += __shfl_xor_sync(kFull, acc_g[c], 8);
+      acc_g[c] += __shfl_xor_sync(kFull, acc_g[c], 16);
+    }
+    if (rlane == 0) {
+#pragma unroll
+      for (int j = 0; j < NGRP; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gred[gw * N + (gsel + 2 * j) * 32 + my_atom * 8 + (e ^ (flip << 2))] = acc_g[j * 8 + e];
+    }
     acc_rr = warp_sum(acc_rr);
-    if (lane == 0) ros[gw] = acc_rr;  // `ros` is idle by now: its last readers are before the last tile's bar.sync
+    if (lane == 0) gred[8 * N + gw] = acc_rr;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     // ================================ epilogue: TMEM -> per-CTA partial in the workspace ================================
     float* ws = p.ws + (size_t)blockIdx.x * WS_STRIDE;
-    ws[N * N + b] = (acc_g[0] + acc_g[1]) + (acc_g[2] + acc_g[3]);
-    if (b == 0) {
-      float t = 0.f;
+    {
+      float tg = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += ros[w];
-      ws[N * N + N] = t;
+      for (int w = 0; w < 8; ++w) tg += gred[w * N + b];
+      ws[N * N + b] = tg;
+      if (b == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += gred[8 * N + w];
+        ws[N * N + N] = t;
+      }
     }
     if (my_tiles > 0) {
       mbar_wait(accum_done, 0);
@@ -474,7 +493,8 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
       return B200OPT_ECUDA;
     attr_set = true;
   }
-  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles};
+  static const int debug = getenv("B200OPT_GRAM_DEBUG") ? atoi(getenv("B200OPT_GRAM_DEBUG")) : 0;
+  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, debug};
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;
