@@ -50,6 +50,18 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(key: str, units: int):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), scaled per unit to this launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)[key]
+        per_unit = t["dram_bytes"] / t["units"]
+        return per_unit * units, (f"ncu --set full capture profiles/{t['report']}.csv: {t['dram_bytes'] / 1e6:.1f} MB for {t['units']} {t['unit']}s "
+                                  f"= {per_unit:.0f} B/{t['unit']} (algorithmic {t['algorithmic_bytes_per_unit']}), scaled to this launch's {units} {t['unit']}s")
+    except Exception:  # noqa: BLE001
+        return None, "no ncu capture for this kernel in profiles/traffic.json"
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML during the timed region (B200_PROFILING.md recipe)."""
 
@@ -257,7 +269,9 @@ def bench_gram(args, rank, world, local_rank):
     if rank == 0:
         rows = m_local * world
         peak, peak_src = _peaks()
-        j_bytes = m_local * N * 4
+        # algorithmic bytes per row: J 1024 (+ d, r_old read and r written when the residual is fused; + r read when not)
+        alg_bytes = m_local * (N * 4 + (12 if fused else 4))
+        traffic, traffic_note = _traffic("gram_kernel(fused)", m_local) if fused else (None, "no capture of the unfused variant this round")
         tf32_peak = None
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -272,9 +286,9 @@ def bench_gram(args, rank, world, local_rank):
                            "fused_residual": fused,
                            "rows_per_gpu": m_local, "n": N, "parallelism": f"row-sharded x{world}, all-reduce of {N * N + N + 2} floats per iteration",
                            "l2": "J shard (>= 8 GB) exceeds the 126 MB L2"},
-                "roofline": {"bound": "hbm", "achieved": j_bytes / (ms_gram / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": j_bytes / (ms_gram / 1e3) / 1e9 / peak, "traffic": None, "kernel": "gram_kernel", "peak_source": peak_src,
-                             "algorithmic_bytes_per_row": N * 4},
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_gram / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg_bytes / (ms_gram / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note,
+                             "kernel": "gram_kernel", "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes // m_local},
                 "tensor": {"achieved_tflops_full_2mn2": gram_tflops, "executed_fraction_of_full": 0.75,
                            "peak_tflops_tf32_assumed": tf32_peak, "frac": (gram_tflops / tf32_peak) if tf32_peak else None,
                            "note": "tf32 peak assumed = measured bf16 peak / 2 (no tf32 measurement in MEASURED_PEAKS.json)"},
@@ -291,11 +305,16 @@ def cpu_reference(name, inp, sample, linsolve="qr"):
 
     if name in ("gauss2", "exp_decay"):
         tol = 1e-4 if name == "gauss2" else 1e-8
+        # all host threads this process may run on (torchrun exports OMP_NUM_THREADS=1, so ask the OS, not OpenMP)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
         t0 = time.perf_counter()
         out = c_oracle.levenberg_marquardt(name, inp["y0"][:sample], inp["shared"], inp["prob"][:sample], rtol=tol, atol=tol,
-                                           max_steps=256, linsolve=linsolve)
+                                           max_steps=256, linsolve=linsolve, nthreads=cores)
         dt = time.perf_counter() - t0
-        return out, dt, c_oracle.max_threads(), "C+OpenMP restatement (oracle/c), augmented-QR solve as in the reference"
+        return out, dt, cores, "C+OpenMP restatement (oracle/c), augmented-QR solve as in the reference"
     from oracle import models as M
     from oracle import solvers as S
 
@@ -456,7 +475,11 @@ def main():
     # ---- roofline of the dominant (only) kernel
     peak, peak_src = _peaks()
     achieved = bytes_per_problem * batch / (ms_per_step / 1e3) / 1e9  # GB/s per GPU (per launch)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    tkey = {"gauss2": "lsq_solve_kernel<Gauss2<float>>", "newton": "root_solve_kernel<ImplicitEuler<double>>",
+            "bfgs": "bfgs_solve_kernel<Rosenbrock<double>>"}.get(name, "")
+    traffic, traffic_note = _traffic(tkey, batch)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "kernel": "lsq_solve_kernel" if name in ("gauss2", "exp_decay") else name,
                 "algorithmic_bytes_per_problem": bytes_per_problem, "peak_source": peak_src,
                 "note": "HBM is NOT the binding roof for this path (SURVEY F8): state is on-chip, ~0.5 Mflop per 1.1 KB; see 'fp'"}
