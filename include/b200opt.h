@@ -175,6 +175,36 @@ int32_t b200opt_lsq_step(int32_t solver, int32_t dtype, int64_t batch, int32_t n
 int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* state, int32_t* result,
                                 void* stream);
 
+/* ---- generic per-iteration step, root finding (Newton / Chord) for an arbitrary user `fn` -------------------
+ * One call = one _AbstractNewtonChord.step + terminate (optimistix/_solver/newton_chord.py:103-196) for every
+ * still-running problem; n <= 32.  f_eval [batch][n] = fn(y), J_eval [batch][n][n] = d fn / d y (row-major) at the
+ * CURRENT y for Newton; for Chord the caller passes the Jacobian at y0 on every call (newton_chord.py:80-87).
+ * lower / upper: optional [n] clip bounds.  y [batch][n] is updated in place.  `state`: opaque carry of
+ * b200opt_root_step_state_size bytes per problem.  opts: rtol, atol, norm, max_steps, cauchy_termination, kappa. */
+int64_t b200opt_root_step_state_size(int32_t dtype, int32_t n);
+int32_t b200opt_root_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* state,
+                               int32_t* num_steps, int32_t* result, void* stream);
+int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* J_eval,
+                          const void* lower, const void* upper, void* y, void* state, const b200opt_options_t* opts,
+                          int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream);
+int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result,
+                                 void* stream);
+
+/* ---- generic per-iteration step, minimisation (BFGS, inverse Hessian, backtracking Armijo) -------------------
+ * One call = one AbstractQuasiNewton.step (optimistix/_solver/quasi_newton.py:204-300, :342-415; backtracking.py:
+ * 79-99) for every still-running problem; n <= 1024.  f_eval [batch] = fn(y_eval), g_eval [batch][n] = its gradient.
+ * root_norm: optional [batch], norm of the root function at the pre-step y: adds the `norm(f) < atol` condition of
+ * root_find-through-a-minimiser (_root_find.py:64-73).  The carry (H^-1 n x n, gradient, direction, f, step size,
+ * flags) lives in `state` (b200opt_bfgs_step_state_size bytes per problem), initialised by _init. */
+int64_t b200opt_bfgs_step_state_size(int32_t dtype, int32_t n);
+int32_t b200opt_bfgs_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* y_eval,
+                               void* state, int32_t* num_steps, int32_t* result, void* stream);
+int32_t b200opt_bfgs_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* g_eval,
+                          const void* root_norm, void* y, void* y_eval, void* state, const b200opt_options_t* opts,
+                          int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream);
+int32_t b200opt_bfgs_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result,
+                                 void* stream);
+
 /* ---- large row-sharded Gauss-Newton Gram on tcgen05 tensor cores (TF32 in, FP32 accumulate in TMEM) ----
  * J [m_local][n] row-major fp32 (n == 256 in this build), r [m_local] fp32.
  * out [n*n + n + 1] fp32: G = J^T J (row-major, full symmetric), then g = J^T r, then r^T r.

@@ -176,7 +176,12 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
                   args_in_dims=None):
     """Solve (a batch of) nonlinear least-squares problems. Reference: optimistix/_least_squares.py:44-135."""
     if isinstance(solver, AbstractMinimiser):
-        raise NotImplementedError("least_squares through a minimiser (_least_squares.py:102-114) needs the generic path")
+        # _least_squares.py:36-41,102-114: minimise 0.5 * sum(residual^2)
+        if isinstance(fn, RegisteredModel):
+            raise NotImplementedError("least_squares through a minimiser takes a Python callable (generic path)")
+        _check_common(fn, options, has_aux, adjoint)
+        return minimise(lambda y, a: 0.5 * (fn(y, a).reshape(-1) ** 2).sum(), solver, y0, args, options, max_steps=max_steps,
+                        throw=throw, args_in_dims=args_in_dims)
     if not isinstance(solver, (LevenbergMarquardt, GaussNewton)):
         raise TypeError(f"least_squares: unsupported solver {type(solver).__name__}")
     _check_common(fn, options, has_aux, adjoint)
@@ -245,13 +250,21 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
         return least_squares(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, _root_near_zero=True, chunk=chunk,
                              args_in_dims=args_in_dims)
     if isinstance(solver, AbstractMinimiser):
-        raise NotImplementedError("root_find through a minimiser (_root_find.py:176-199) needs the generic path")
+        # _root_find.py:39-41,45-80,176-199: minimise norm(fn), terminate only once norm(fn) < atol as well
+        if isinstance(fn, RegisteredModel):
+            raise NotImplementedError("root_find through a minimiser takes a Python callable (generic path)")
+        _check_defaults(solver)
+        from ._generic import minimise_generic
+
+        norm = solver.norm
+        return minimise_generic(lambda y, a: norm(fn(y, a).reshape(-1)), solver, y0, args, max_steps=max_steps,
+                                throw=throw, args_in_dims=args_in_dims, root_fn=fn)
     if not isinstance(solver, (Newton, Chord)):
         raise TypeError(f"root_find: unsupported solver {type(solver).__name__}")
     if not isinstance(fn, RegisteredModel):
         from ._generic import root_find_generic
 
-        return root_find_generic(fn, solver, y0, args, options, max_steps=max_steps, throw=throw)
+        return root_find_generic(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims)
     if fn.kind != KIND_ROOT:
         raise TypeError(f"model {fn.name} is not a root-finding family")
     lib = _lib.load()
@@ -346,7 +359,8 @@ def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_s
 
 # ------------------------------------------------------------------------------------------ minimise
 def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-             adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False):
+             adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False,
+             args_in_dims=None):
     """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
     _check_common(fn, options, has_aux, adjoint)
     if not isinstance(solver, BFGS):
@@ -357,7 +371,8 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
     if not isinstance(fn, RegisteredModel):
         from ._generic import minimise_generic
 
-        return minimise_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw)
+        return minimise_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims,
+                                return_hessian_inv=return_hessian_inv)
     if fn.kind != KIND_MIN:
         raise TypeError(f"model {fn.name} is not a minimisation family")
     lib = _lib.load()

@@ -122,11 +122,167 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
     return Solution(value=value, result=result, aux=None, stats=stats, state=state)
 
 
-def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw):
-    raise NotImplementedError("Newton/Chord on an arbitrary callable: use root_find(fn, LevenbergMarquardt(...)) "
-                              "(generic step kernel) or a registered root family; a generic Newton step kernel is a next row")
+def _prep_y0(y0):
+    t = _torch()
+    y0 = t.as_tensor(y0)
+    if not y0.is_cuda:
+        if not t.cuda.is_available():
+            raise _lib.B200OptError("the generic path needs a CUDA device (there is no CPU fallback)")
+        y0 = y0.cuda()
+    if not y0.dtype.is_floating_point:
+        y0 = y0.to(t.get_default_dtype())
+    if y0.dtype not in (t.float32, t.float64):
+        raise TypeError(f"unsupported dtype {y0.dtype}")
+    single = y0.ndim == 1
+    if y0.ndim not in (1, 2):
+        raise ValueError("y0 must have shape [n] (one problem) or [batch, n]")
+    Y0 = (y0[None] if single else y0).contiguous()
+    return Y0, single, (_lib.F32 if y0.dtype == t.float32 else _lib.F64)
 
 
-def minimise_generic(fn, solver, y0, args, *, max_steps, throw):
-    raise NotImplementedError("BFGS on an arbitrary callable is a next row (SURVEY 8f); registered minimisation families "
-                              "run in the persistent BFGS kernel")
+def _throw_if_failed(res):
+    rh = res.cpu().numpy()
+    bad = np.flatnonzero(rh != RESULTS.successful)
+    if bad.size:
+        code = int(rh[bad[0]])
+        raise RuntimeError(f"{bad.size} of {rh.size} solves failed; first failure (problem {int(bad[0])}): "
+                           f"{RESULTS.name(code)}: {RESULTS[code]}")
+
+
+def _vmapped(f, args, args_in_dims):
+    """vmap f(y, args) over the batch axis of y (and of the leaves of args selected by args_in_dims)."""
+    t = _torch()
+    if args_in_dims is None:
+        vm = t.func.vmap(lambda y: f(y, args))
+        return vm
+    vm = t.func.vmap(f, in_dims=(0, args_in_dims))
+    return lambda Y: vm(Y, args)
+
+
+def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_in_dims=None):
+    """Newton / Chord for an arbitrary `fn(y, args) -> [n]`: torch evaluates f and the n x n Jacobian (the role of
+    jax.linearize / jacfwd at newton_chord.py:116-119; Chord: once, at y0, :80-87), `b200opt_root_step` does the LU
+    solve with partial pivoting, the update, clipping, termination and result codes."""
+    from ._solvers import Chord
+
+    t = _torch()
+    lib = _lib.load()
+    Y0, single, dtype_code = _prep_y0(y0)
+    B, n = Y0.shape
+    if n > 32:
+        raise NotImplementedError("generic Newton/Chord step kernel supports n <= 32 unknowns (row-per-lane LU)")
+    dev = Y0.device
+
+    def one(y, a):
+        out = fn(y, a).reshape(-1)
+        if out.shape[0] != n:
+            raise ValueError("root_find: fn must map [n] -> [n]")
+        return out
+
+    f_only = _vmapped(one, args, args_in_dims)
+    f_and_J = _vmapped(lambda y, a: tuple(reversed(t.func.jacfwd(lambda z: (one(z, a), one(z, a)), has_aux=True)(y))), args,
+                       args_in_dims)
+    lower = upper = None
+    if options:
+        if options.get("lower") is not None:
+            lower = t.broadcast_to(t.as_tensor(options["lower"], dtype=Y0.dtype, device=dev), (n,)).contiguous()
+        if options.get("upper") is not None:
+            upper = t.broadcast_to(t.as_tensor(options["upper"], dtype=Y0.dtype, device=dev), (n,)).contiguous()
+    es = 4 if dtype_code == _lib.F32 else 8
+    stride = lib.b200opt_root_step_state_size(dtype_code, n)
+    state = t.empty((B, stride // es), dtype=Y0.dtype, device=dev)
+    y = t.empty_like(Y0)
+    steps = t.empty((B,), dtype=t.int32, device=dev)
+    res = t.empty((B,), dtype=t.int32, device=dev)
+    active = t.zeros((1,), dtype=t.int32, device=dev)
+    stream = t.cuda.current_stream(dev).cuda_stream
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, cauchy_termination=solver.cauchy_termination,
+                             kappa=solver.kappa)
+    _lib.check(lib.b200opt_root_step_init(dtype_code, B, n, Y0.data_ptr(), y.data_ptr(), state.data_ptr(), steps.data_ptr(),
+                                          res.data_ptr(), stream), "b200opt_root_step_init")
+    chord = isinstance(solver, Chord)
+    J_fixed = None
+    launches = 0
+    for _ in range(max_steps):
+        if chord:
+            if J_fixed is None:
+                f, J_fixed = f_and_J(y)
+                J_fixed = J_fixed.contiguous()
+            else:
+                f = f_only(y)
+            J = J_fixed
+        else:
+            f, J = f_and_J(y)
+            J = J.contiguous()
+        f = f.contiguous()
+        _lib.check(lib.b200opt_root_step(dtype_code, B, n, f.data_ptr(), J.data_ptr(), lower.data_ptr() if lower is not None else None,
+                                         upper.data_ptr() if upper is not None else None, y.data_ptr(), state.data_ptr(),
+                                         C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), stream),
+                   "b200opt_root_step")
+        launches += 1
+        if int(active.item()) == 0:
+            break
+    _lib.check(lib.b200opt_root_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_root_step_finish")
+    if throw:
+        _throw_if_failed(res)
+    stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=state)
+
+
+def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=None, root_fn=None, return_hessian_inv=False):
+    """BFGS (inverse Hessian, backtracking Armijo) for an arbitrary scalar `fn(y, args)`: torch evaluates f and its
+    gradient (jax.linearize + linear_transpose at quasi_newton.py:214-227), `b200opt_bfgs_step` does the rest.
+
+    root_fn: when minimising 0.5 |root_fn|^2 on behalf of root_find (_root_find.py:45-80), the extra
+    `norm(root_fn(y)) < atol` termination condition is evaluated on the pre-step y."""
+    t = _torch()
+    lib = _lib.load()
+    Y0, single, dtype_code = _prep_y0(y0)
+    B, n = Y0.shape
+    dev = Y0.device
+
+    def one(y, a):
+        out = fn(y, a)
+        if out.numel() != 1:
+            raise ValueError("minimise function must output a single scalar.")  # _minimise.py:97-104
+        return out.reshape(())
+
+    gv = _vmapped(lambda y, a: t.func.grad_and_value(lambda z: one(z, a))(y), args, args_in_dims)
+    rootv = None
+    if root_fn is not None:
+        norm = solver.norm
+        rootv = _vmapped(lambda y, a: norm(root_fn(y, a).reshape(-1)), args, args_in_dims)
+    es = 4 if dtype_code == _lib.F32 else 8
+    nbytes = lib.b200opt_bfgs_step_state_size(dtype_code, n)
+    if nbytes <= 0:
+        _lib.check(-1, "b200opt_bfgs_step_state_size")
+    state = t.empty((B, nbytes // es), dtype=Y0.dtype, device=dev)
+    y = t.empty_like(Y0)
+    y_eval = t.empty_like(Y0)
+    steps = t.empty((B,), dtype=t.int32, device=dev)
+    res = t.empty((B,), dtype=t.int32, device=dev)
+    active = t.zeros((1,), dtype=t.int32, device=dev)
+    stream = t.cuda.current_stream(dev).cuda_stream
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps)
+    _lib.check(lib.b200opt_bfgs_step_init(dtype_code, B, n, Y0.data_ptr(), y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
+                                          steps.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_init")
+    launches = 0
+    for _ in range(max_steps):
+        g, f = gv(y_eval)
+        g, f = g.contiguous(), f.contiguous()
+        rn = rootv(y).to(Y0.dtype).contiguous() if rootv is not None else None
+        _lib.check(lib.b200opt_bfgs_step(dtype_code, B, n, f.data_ptr(), g.data_ptr(), rn.data_ptr() if rn is not None else None,
+                                         y.data_ptr(), y_eval.data_ptr(), state.data_ptr(), C.byref(opts), steps.data_ptr(),
+                                         res.data_ptr(), active.data_ptr(), stream), "b200opt_bfgs_step")
+        launches += 1
+        if int(active.item()) == 0:
+            break
+    _lib.check(lib.b200opt_bfgs_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_finish")
+    if throw:
+        _throw_if_failed(res)
+    stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches,
+             "num_accepted_steps": state[:, n * n + 2 * n + 4].to(t.int32)}
+    st = {"f": state[:, n * n + 2 * n]}
+    if return_hessian_inv:
+        st["hessian_inv"] = state[:, : n * n].reshape(B, n, n)
+    return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=st)

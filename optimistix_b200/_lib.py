@@ -69,6 +69,14 @@ _SIGNATURES = {
     "b200opt_lsq_step_init": (_i32, [_i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_lsq_step": (_i32, [_i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp]),
     "b200opt_lsq_step_finish": (_i32, [_i32, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "b200opt_root_step_state_size": (_i64, [_i32, _i32]),
+    "b200opt_root_step_init": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_root_step": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_root_step_finish": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp]),
+    "b200opt_bfgs_step_state_size": (_i64, [_i32, _i32]),
+    "b200opt_bfgs_step_init": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_bfgs_step": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_bfgs_step_finish": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_gram_workspace_size": (_i64, [_i32]),
     "b200opt_gn_gram": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_gram_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i64, _i32, _vp, _vp, _vp]),

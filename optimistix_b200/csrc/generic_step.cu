@@ -1,0 +1,507 @@
+// Generic per-iteration steps for an ARBITRARY user function, root finding and minimisation (the least-squares
+// counterpart is lsq_step.cu).  The caller (XLA, torch, ...) evaluates the function and its derivative at the current
+// point; these kernels do everything else of one solver step plus the driver bookkeeping of _iterate.py:234-241 for
+// every problem that is still running.
+//
+//   root_step   one _AbstractNewtonChord.step + terminate (optimistix/_solver/newton_chord.py:103-196): in-warp LU with
+//               partial pivoting of the caller's Jacobian (Newton: J(y); Chord: J(y0), passed again on every call),
+//               y <- y - J^-1 f, optional clip to [lower, upper], scaled step size, Cauchy or Hairer-Wanner
+//               termination, result codes.  One warp per problem, n <= 32.
+//   bfgs_step   one AbstractQuasiNewton.step (quasi_newton.py:204-300) with BacktrackingArmijo (backtracking.py:79-99),
+//               the inverse BFGS update (quasi_newton.py:342-415, skipped when q.s <= eps) and NewtonDescent
+//               (gauss_newton.py:60-62,126-127).  One CTA per problem; H^-1 (n x n) is carried in the caller-owned state
+//               buffer in HBM between calls (a per-iteration kernel cannot keep it on chip), read twice and written
+//               once per ACCEPTED step, untouched by a rejected one.
+#include "newton_kernel.cuh"
+
+namespace b200opt {
+
+// =============================================================================================== root step
+// state per problem (elements of T): [diffsize | nstep | terminate | pad]
+constexpr int kRootStateElems = 4;
+
+template <typename T> struct RootStepParams {
+  const T* f_eval;  // [batch][n]      fn(y)
+  const T* J_eval;  // [batch][n][n]   d fn / d y  (row-major)
+  const T* lower;   // optional [n]
+  const T* upper;   // optional [n]
+  T* y;             // [batch][n] in/out
+  T* state;
+  int32_t* num_steps;
+  int32_t* result;
+  int32_t* active_count;
+  int64_t batch;
+  int n;
+  T rtol, atol, kappa;
+  int norm, max_steps, cauchy;
+};
+
+constexpr int kRootStepWarps = 4;
+
+template <typename T, int N> __global__ void __launch_bounds__(kRootStepWarps * 32) root_step_kernel(const RootStepParams<T> p) {
+  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N];
+  __shared__ unsigned char piv_all[kRootStepWarps][N];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t prob = (int64_t)blockIdx.x * kRootStepWarps + wib;
+  if (prob >= p.batch) return;
+  const int n = p.n;
+  T* st = p.state + prob * kRootStateElems;
+  int result = p.result[prob];
+  int steps = p.num_steps[prob];
+  bool terminate = st[2] != T(0);
+  if (terminate || result != RES_OK || steps >= p.max_steps) return;  // this lane of the vmapped loop is frozen
+  const bool act = lane < n;
+  const T rtol = p.rtol, atol = p.atol;
+  T small_tol = T(1);  // 10^(2 - precision), newton_chord.py:25-29
+  for (int i = 0; i < Num<T>::precision - 2; ++i) small_tol *= T(0.1);
+
+  const T y = act ? p.y[prob * n + lane] : T(0);
+  const T fx = act ? p.f_eval[prob * n + lane] : T(0);
+  const bool y_old_finite = __all_sync(kFull, !act || t_finite(y));
+  // row `lane` of the Jacobian, padded with the identity to N x N
+  T a[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = (act && j < n) ? p.J_eval[(prob * n + lane) * (int64_t)n + j] : ((j == lane) ? T(1) : T(0));
+  int mycol;
+  T rinv;
+  warp_lu_factor<T, N>(a, mycol, rinv, rowbuf_all[wib], piv_all[wib], lane);
+  const T sol = warp_lu_solve<T, N>(a, mycol, rinv, fx, piv_all[wib], lane);
+  const int lin_result = __all_sync(kFull, !act || t_finite(sol)) ? RES_OK : RES_SINGULAR;  // lineax: non-finite => singular
+  const T lo = (p.lower && act) ? p.lower[lane] : -Num<T>::inf();
+  const T hi = (p.upper && act) ? p.upper[lane] : Num<T>::inf();
+  T new_y = y - sol;  // newton_chord.py:129
+  T d = sol;
+  if (p.lower != nullptr || p.upper != nullptr) {
+    new_y = new_y < lo ? lo : new_y;  // :130-133
+    new_y = new_y > hi ? hi : new_y;
+    d = y - new_y;  // :134-135
+  }
+  NormAcc<T> ds(p.norm);
+  if (act) ds.add(t_abs(d / (atol + rtol * t_abs(new_y))));  // :136-138
+  ds.warp_combine();
+  const T diffsize_prev = st[0];
+  const T diffsize = ds.finish(n);
+  const int nstep = (int)st[1] + 1;
+  // ---- terminate, evaluated with the PRE-step y (:154-196, _iterate.py:238)
+  int term_result = RES_OK;
+  if (p.cauchy) {
+    NormAcc<T> yn(p.norm), fn(p.norm);
+    if (act) {
+      yn.add(t_abs(d) / (atol + rtol * t_abs(y)));
+      fn.add(t_abs(fx) / atol);  // f_scale = atol + rtol * |0|
+    }
+    yn.warp_combine();
+    fn.warp_combine();
+    terminate = (yn.finish(n) < T(1)) && (fn.finish(n) < T(1));
+  } else {
+    const bool at_least_two = nstep >= 2;
+    const T rate = diffsize / diffsize_prev;
+    const T factor = diffsize * rate / (T(1) - rate);
+    const bool small = diffsize < small_tol;
+    const bool diverged = !t_finite(rate) || rate > T(2);
+    const bool converged = factor > T(0) && factor < p.kappa;
+    terminate = at_least_two && (small || diverged || converged);
+    if (at_least_two && !small && diverged) term_result = RES_DIVERGED;
+  }
+  const bool fail = lin_result != RES_OK;
+  result = fail ? lin_result : term_result;
+  terminate = terminate || fail;
+  if (!y_old_finite) result = RES_NONFINITE;
+  ++steps;
+  if (act) p.y[prob * n + lane] = new_y;
+  if (lane == 0) {
+    st[0] = diffsize;
+    st[1] = (T)nstep;
+    st[2] = terminate ? T(1) : T(0);
+    p.num_steps[prob] = steps;
+    p.result[prob] = result;
+    if (p.active_count && !terminate && result == RES_OK && steps < p.max_steps) atomicAdd(p.active_count, 1);
+  }
+}
+
+template <typename T> __global__ void root_step_init_kernel(int64_t batch, int n, const T* y0, T* y, T* state, int32_t* num_steps,
+                                                            int32_t* result) {
+  const int64_t prob = blockIdx.x;
+  if (prob >= batch) return;
+  bool fin = true;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const T v = y0[prob * n + j];
+    y[prob * n + j] = v;
+    fin = fin && t_finite(v);
+  }
+  const int allfin = __syncthreads_and(fin ? 1 : 0);
+  if (threadIdx.x == 0) {
+    T* st = state + prob * kRootStateElems;
+    st[0] = Num<T>::inf();  // diffsize (:93), so that diffsize_prev of the second step is inf as in the reference carry
+    st[1] = T(0);           // step
+    st[2] = T(0);           // terminate
+    st[3] = T(0);
+    num_steps[prob] = 0;
+    result[prob] = allfin ? RES_OK : RES_NONFINITE;  // _iterate.py:216-219
+  }
+}
+
+// =============================================================================================== BFGS step
+// state per problem (elements of T): [H^-1 (n*n) | g (n) | newton (n) | f | alpha | first | terminate | num_accepted | pad..]
+__host__ __device__ inline int64_t bfgs_state_stride(int n) { return ((int64_t)n * n + 2 * n + 5 + 3) / 4 * 4; }
+
+template <typename T> struct BfgsStepParams {
+  const T* f_eval;       // [batch]     fn(y_eval)
+  const T* g_eval;       // [batch][n]  grad fn(y_eval)
+  const T* root_norm;    // optional [batch]: norm of the root function at the pre-step y (root_find through a minimiser)
+  T* y;                  // [batch][n] in/out: last accepted point
+  T* y_eval;             // [batch][n] in/out: next trial point
+  T* state;
+  int64_t state_stride;
+  int32_t* num_steps;
+  int32_t* result;
+  int32_t* active_count;
+  int64_t batch;
+  int n;
+  T rtol, atol;
+  int norm, max_steps;
+};
+
+constexpr int kBfgsStepThreads = 128;
+
+// deterministic CTA-wide sum: butterfly inside each warp, then the warp totals in a fixed order; every thread gets the total
+template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
+  v = warp_sum(v);
+  __syncthreads();  // `red` may still be read from a previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T t = T(0);
+#pragma unroll
+  for (int w = 0; w < kBfgsStepThreads / 32; ++w) t += red[w];
+  return t;
+}
+template <typename T> __device__ __forceinline__ T block_nanmax(T v, T* red) {
+  v = warp_nanmax(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T t = T(0);
+#pragma unroll
+  for (int w = 0; w < kBfgsStepThreads / 32; ++w) t = nan_max(t, red[w]);
+  return t;
+}
+
+template <typename T> __global__ void __launch_bounds__(kBfgsStepThreads) bfgs_step_kernel(const BfgsStepParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T red[kBfgsStepThreads / 32];
+  const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kBfgsStepThreads / 32;
+  T* vd = reinterpret_cast<T*>(smem_raw);  // s = y_eval - y
+  T* vq = vd + n;                          // q = grad_new - grad
+  T* vg = vq + n;                          // grad_new
+  T* vhq = vg + n;                         // H^-1 q
+  const int64_t prob = blockIdx.x;
+  T* st = p.state + prob * p.state_stride;
+  T* H = st;
+  T* gst = st + (int64_t)n * n;
+  T* nst = gst + n;
+  T* sc = nst + n;  // f, alpha, first, terminate, num_accepted
+  int result = p.result[prob];
+  int steps = p.num_steps[prob];
+  bool terminate = sc[3] != T(0);
+  if (terminate || result != RES_OK || steps >= p.max_steps) return;  // block-uniform
+  const T rtol = p.rtol, atol = p.atol;
+  const T f = sc[0];
+  T alpha = sc[1];
+  const bool first = sc[2] != T(0);
+  const T fe = p.f_eval[prob];
+
+  // ---- vectors; BacktrackingArmijo.step (backtracking.py:79-99)
+  T part_pred = T(0), part_inner = T(0);
+  bool fin = true;
+  for (int j = tid; j < n; j += kBfgsStepThreads) {
+    const T yj = p.y[prob * n + j], yej = p.y_eval[prob * n + j], gj = gst[j], gej = p.g_eval[prob * n + j];
+    const T dj = yej - yj, qj = gej - gj;
+    vd[j] = dj;
+    vq[j] = qj;
+    vg[j] = gej;
+    part_pred += gj * dj;
+    part_inner += qj * dj;
+    fin = fin && t_finite(yj);
+  }
+  const bool y_old_finite = __syncthreads_and(fin ? 1 : 0) != 0;
+  const T pred = block_sum(part_pred, red);
+  const T df = fe - f;
+  const bool accept = first || ((df <= T(0.1) * pred) && (pred <= T(0)));
+  alpha = accept ? T(1) : T(0.5) * alpha;
+  if (accept) {
+    // ---- update_hessian (quasi_newton.py:342-415, inverse branch :371-385)
+    const T inner = block_sum(part_inner, red);
+    const bool update = inner > Num<T>::eps();  // :360
+    T c1 = T(0), c2 = T(0);
+    if (update) {
+      // pass 1: inv_mvp = H q (one warp per row, coalesced)
+      for (int i = warp; i < n; i += NW) {
+        T acc = T(0);
+        for (int j = lane; j < n; j += 32) acc += H[(int64_t)i * n + j] * vq[j];
+        acc = warp_sum(acc);
+        if (lane == 0) vhq[i] = acc;
+      }
+      __syncthreads();
+      T part = T(0);
+      for (int j = tid; j < n; j += kBfgsStepThreads) part += vq[j] * vhq[j];
+      const T mvp_inner = block_sum(part, red);
+      c1 = (inner + mvp_inner) / (inner * inner);  // term1 coefficient (:379)
+      c2 = T(1) / inner;                           // term2 coefficient (:380)
+    }
+    // pass 2: H' = H + c1 s s^T - c2 (Hq s^T + s Hq^T), fused with newton = H' grad_new (gauss_newton.py:60-61)
+    for (int i = warp; i < n; i += NW) {
+      const T s_i = vd[i], hq_i = update ? vhq[i] : T(0);
+      T acc = T(0);
+      for (int j = lane; j < n; j += 32) {
+        T h = H[(int64_t)i * n + j];
+        if (update) {
+          h = h + c1 * (s_i * vd[j]) - c2 * (hq_i * vd[j] + s_i * vhq[j]);
+          H[(int64_t)i * n + j] = h;
+        }
+        acc += h * vg[j];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) nst[i] = acc;
+    }
+    // ---- termination (quasi_newton.py:244-249): cauchy_termination on y and on the scalar f, never on the first step
+    NormAcc<T> yn(p.norm);
+    for (int j = tid; j < n; j += kBfgsStepThreads) yn.add(t_abs(vd[j]) / (atol + rtol * t_abs(p.y_eval[prob * n + j])));
+    const T ynorm_acc = (p.norm == B200OPT_NORM_MAX) ? block_nanmax(yn.v, red) : block_sum(yn.v, red);
+    yn.v = ynorm_acc;
+    NormAcc<T> fnrm(p.norm);
+    fnrm.add(t_abs(df) / (atol + rtol * t_abs(fe)));
+    terminate = (yn.finish(n) < T(1)) && (fnrm.finish(1) < T(1)) && !first;
+    __syncthreads();  // nst complete, every read of y_eval above done
+    for (int j = tid; j < n; j += kBfgsStepThreads) {
+      const T yj = p.y_eval[prob * n + j];  // y <- y_eval
+      p.y[prob * n + j] = yj;
+      gst[j] = vg[j];
+      p.y_eval[prob * n + j] = yj - alpha * nst[j];  // gauss_newton.py:126-127
+    }
+  } else {
+    terminate = false;
+    for (int j = tid; j < n; j += kBfgsStepThreads) p.y_eval[prob * n + j] = p.y[prob * n + j] - alpha * nst[j];
+  }
+  if (p.root_norm) terminate = terminate && (p.root_norm[prob] < atol);  // _ToRoot.terminate (_root_find.py:64-73)
+  result = RES_OK;
+  if (!y_old_finite) result = RES_NONFINITE;  // _iterate.py:216
+  ++steps;
+  if (tid == 0) {
+    if (accept) {
+      sc[0] = fe;
+      sc[4] = sc[4] + T(1);
+    }
+    sc[1] = alpha;
+    sc[2] = T(0);
+    sc[3] = terminate ? T(1) : T(0);
+    p.num_steps[prob] = steps;
+    p.result[prob] = result;
+    if (p.active_count && !terminate && result == RES_OK && steps < p.max_steps) atomicAdd(p.active_count, 1);
+  }
+}
+
+template <typename T> __global__ void bfgs_step_init_kernel(int64_t batch, int n, int64_t stride, const T* y0, T* y, T* y_eval, T* state,
+                                                            int32_t* num_steps, int32_t* result) {
+  const int64_t prob = blockIdx.x;
+  if (prob >= batch) return;
+  T* st = state + prob * stride;
+  for (int64_t e = threadIdx.x; e < stride; e += blockDim.x) {
+    const int64_t i = e / n, j = e - i * n;
+    st[e] = (e < (int64_t)n * n && i == j) ? T(1) : T(0);  // H^-1 = I (quasi_newton.py:41-75), f = 0, g = 0, newton = 0
+  }
+  __syncthreads();
+  bool fin = true;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const T v = y0[prob * n + j];
+    y[prob * n + j] = v;
+    y_eval[prob * n + j] = v;
+    fin = fin && t_finite(v);
+  }
+  const int allfin = __syncthreads_and(fin ? 1 : 0);
+  if (threadIdx.x == 0) {
+    T* sc = st + (int64_t)n * n + 2 * n;
+    sc[1] = T(1);  // alpha = step_init (backtracking.py:51-53)
+    sc[2] = T(1);  // first_step
+    num_steps[prob] = 0;
+    result[prob] = allfin ? RES_OK : RES_NONFINITE;
+  }
+}
+
+template <typename T> __global__ void step_finish_kernel(int64_t batch, int64_t stride, int64_t term_off, const T* state, int32_t* result) {
+  const int64_t prob = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= batch) return;
+  const bool terminate = state[prob * stride + term_off] != T(0);
+  if (result[prob] == RES_OK && !terminate) result[prob] = RES_NL_MAX_STEPS;  // _iterate.py:253-257
+}
+
+template <typename T>
+static int root_step_typed(int64_t batch, int n, const void* f, const void* J, const void* lower, const void* upper, void* y, void* state,
+                           const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
+  RootStepParams<T> p;
+  p.f_eval = static_cast<const T*>(f);
+  p.J_eval = static_cast<const T*>(J);
+  p.lower = static_cast<const T*>(lower);
+  p.upper = static_cast<const T*>(upper);
+  p.y = static_cast<T*>(y);
+  p.state = static_cast<T*>(state);
+  p.num_steps = num_steps;
+  p.result = result;
+  p.active_count = active;
+  p.batch = batch;
+  p.n = n;
+  p.rtol = (T)o->rtol;
+  p.atol = (T)o->atol;
+  p.kappa = (T)o->kappa;
+  p.norm = o->norm;
+  p.max_steps = o->max_steps;
+  p.cauchy = o->cauchy_termination;
+  if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
+  const unsigned grid = (unsigned)((batch + kRootStepWarps - 1) / kRootStepWarps);
+  if (n <= 8) root_step_kernel<T, 8><<<grid, kRootStepWarps * 32, 0, st>>>(p);
+  else if (n <= 16) root_step_kernel<T, 16><<<grid, kRootStepWarps * 32, 0, st>>>(p);
+  else root_step_kernel<T, 32><<<grid, kRootStepWarps * 32, 0, st>>>(p);
+  return check_cuda(cudaGetLastError(), "root_step_kernel launch");
+}
+
+template <typename T>
+static int bfgs_step_typed(int64_t batch, int n, const void* f, const void* g, const void* root_norm, void* y, void* y_eval, void* state,
+                           const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
+  BfgsStepParams<T> p;
+  p.f_eval = static_cast<const T*>(f);
+  p.g_eval = static_cast<const T*>(g);
+  p.root_norm = static_cast<const T*>(root_norm);
+  p.y = static_cast<T*>(y);
+  p.y_eval = static_cast<T*>(y_eval);
+  p.state = static_cast<T*>(state);
+  p.state_stride = bfgs_state_stride(n);
+  p.num_steps = num_steps;
+  p.result = result;
+  p.active_count = active;
+  p.batch = batch;
+  p.n = n;
+  p.rtol = (T)o->rtol;
+  p.atol = (T)o->atol;
+  p.norm = o->norm;
+  p.max_steps = o->max_steps;
+  if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
+  bfgs_step_kernel<T><<<(unsigned)batch, kBfgsStepThreads, 4 * (size_t)n * sizeof(T), st>>>(p);
+  return check_cuda(cudaGetLastError(), "bfgs_step_kernel launch");
+}
+
+}  // namespace b200opt
+
+using namespace b200opt;
+
+static int gstep_check(const char* who, int dtype, int64_t batch, int n, int n_max) {
+  if (dtype != B200OPT_F32 && dtype != B200OPT_F64) {
+    set_error("%s: unknown dtype %d", who, dtype);
+    return B200OPT_EINVAL;
+  }
+  if (batch < 0 || batch > 2147483647LL || n < 1 || n > n_max) {
+    set_error("%s: need 0 <= batch < 2^31 and 1 <= n <= %d (n=%d)", who, n_max, n);
+    return B200OPT_EINVAL;
+  }
+  return 0;
+}
+static int opts_check(const char* who, const b200opt_options_t* o) {
+  if (!o || o->norm < 0 || o->norm > 2 || o->max_steps < 0) {
+    set_error("%s: bad options", who);
+    return B200OPT_EINVAL;
+  }
+  return 0;
+}
+
+constexpr int kBfgsStepNMax = 1024;  // 4 n elements of shared memory per CTA, n^2 elements of state per problem
+
+extern "C" {
+
+int64_t b200opt_root_step_state_size(int32_t dtype, int32_t n) {
+  if (gstep_check("root_step_state_size", dtype, 0, n, 32)) return -1;
+  return (int64_t)kRootStateElems * (dtype == B200OPT_F32 ? 4 : 8);
+}
+
+int32_t b200opt_root_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* state, int32_t* num_steps,
+                               int32_t* result, void* stream) {
+  if (int e = gstep_check("root_step_init", dtype, batch, n, 32)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200OPT_F64)
+    root_step_init_kernel<double><<<(unsigned)batch, 32, 0, st>>>(batch, n, static_cast<const double*>(y0), static_cast<double*>(y),
+                                                                  static_cast<double*>(state), num_steps, result);
+  else
+    root_step_init_kernel<float><<<(unsigned)batch, 32, 0, st>>>(batch, n, static_cast<const float*>(y0), static_cast<float*>(y),
+                                                                 static_cast<float*>(state), num_steps, result);
+  return check_cuda(cudaGetLastError(), "root_step_init launch");
+}
+
+int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* J_eval, const void* lower,
+                          const void* upper, void* y, void* state, const b200opt_options_t* opts, int32_t* num_steps,
+                          int32_t* result, int32_t* active_count, void* stream) {
+  if (int e = gstep_check("root_step", dtype, batch, n, 32)) return e;
+  if (int e = opts_check("root_step", opts)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200OPT_F64)
+    return root_step_typed<double>(batch, n, f_eval, J_eval, lower, upper, y, state, opts, num_steps, result, active_count, st);
+  return root_step_typed<float>(batch, n, f_eval, J_eval, lower, upper, y, state, opts, num_steps, result, active_count, st);
+}
+
+int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result, void* stream) {
+  if (int e = gstep_check("root_step_finish", dtype, batch, n, 32)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((batch + 127) / 128);
+  if (dtype == B200OPT_F64)
+    step_finish_kernel<double><<<grid, 128, 0, st>>>(batch, kRootStateElems, 2, static_cast<const double*>(state), result);
+  else
+    step_finish_kernel<float><<<grid, 128, 0, st>>>(batch, kRootStateElems, 2, static_cast<const float*>(state), result);
+  return check_cuda(cudaGetLastError(), "root_step_finish launch");
+}
+
+int64_t b200opt_bfgs_step_state_size(int32_t dtype, int32_t n) {
+  if (gstep_check("bfgs_step_state_size", dtype, 0, n, kBfgsStepNMax)) return -1;
+  return bfgs_state_stride(n) * (dtype == B200OPT_F32 ? 4 : 8);
+}
+
+int32_t b200opt_bfgs_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* y_eval, void* state,
+                               int32_t* num_steps, int32_t* result, void* stream) {
+  if (int e = gstep_check("bfgs_step_init", dtype, batch, n, kBfgsStepNMax)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t stride = bfgs_state_stride(n);
+  if (dtype == B200OPT_F64)
+    bfgs_step_init_kernel<double><<<(unsigned)batch, 128, 0, st>>>(batch, n, stride, static_cast<const double*>(y0), static_cast<double*>(y),
+                                                                   static_cast<double*>(y_eval), static_cast<double*>(state), num_steps, result);
+  else
+    bfgs_step_init_kernel<float><<<(unsigned)batch, 128, 0, st>>>(batch, n, stride, static_cast<const float*>(y0), static_cast<float*>(y),
+                                                                  static_cast<float*>(y_eval), static_cast<float*>(state), num_steps, result);
+  return check_cuda(cudaGetLastError(), "bfgs_step_init launch");
+}
+
+int32_t b200opt_bfgs_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* g_eval, const void* root_norm,
+                          void* y, void* y_eval, void* state, const b200opt_options_t* opts, int32_t* num_steps, int32_t* result,
+                          int32_t* active_count, void* stream) {
+  if (int e = gstep_check("bfgs_step", dtype, batch, n, kBfgsStepNMax)) return e;
+  if (int e = opts_check("bfgs_step", opts)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200OPT_F64)
+    return bfgs_step_typed<double>(batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
+  return bfgs_step_typed<float>(batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
+}
+
+int32_t b200opt_bfgs_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result, void* stream) {
+  if (int e = gstep_check("bfgs_step_finish", dtype, batch, n, kBfgsStepNMax)) return e;
+  if (batch == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((batch + 127) / 128);
+  const int64_t stride = bfgs_state_stride(n), term_off = (int64_t)n * n + 2 * n + 3;
+  if (dtype == B200OPT_F64)
+    step_finish_kernel<double><<<grid, 128, 0, st>>>(batch, stride, term_off, static_cast<const double*>(state), result);
+  else
+    step_finish_kernel<float><<<grid, 128, 0, st>>>(batch, stride, term_off, static_cast<const float*>(state), result);
+  return check_cuda(cudaGetLastError(), "bfgs_step_finish launch");
+}
+
+}  // extern "C"

@@ -104,3 +104,134 @@ def test_generic_matches_registered_family_and_oracle():
         safe = r["margin"] > 1e3
         assert np.array_equal(to_np(g.stats["num_steps"])[safe], r["num_steps"][safe])
         assert np.allclose(to_np(g.value)[safe], r["value"][safe], rtol=1e-9, atol=0)
+
+
+# ======================================================================================= generic Newton / Chord / BFGS
+def _res_name(sol):
+    return optx.RESULTS.name(int(sol.result))
+
+
+# tests/test_root_find.py:32-55 of the reference: Newton and Chord on the fixed-point zoo, |f(root)| < 1e-5;
+# iteration counts and result codes against the oracle (LU with partial pivoting on both sides)
+@pytest.mark.parametrize("chord", (False, True), ids=("newton", "chord"))
+@pytest.mark.parametrize("name,fn,y0,args", F.FIXED_POINT, ids=[p[0] for p in F.FIXED_POINT])
+def test_root_find_zoo_generic(name, fn, y0, args, chord):
+    solver = (optx.Chord if chord else optx.Newton)(1e-8, 1e-8)
+    sol = optx.fixed_point(fn, solver, torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000, throw=False)
+    out = fn(sol.value, _dev(args)) - sol.value
+    assert np.allclose(to_np(out), 0.0, atol=1e-5, rtol=1e-5)
+    ref = S.newton_chord(F.batched_lsq(F.as_root(fn)), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000, chord=chord)
+    assert _res_name(sol) == S.RESULT_NAMES[ref["result"][0]]
+    assert int(sol.stats["num_steps"]) == int(ref["num_steps"][0])
+    assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-9, atol=1e-12)
+
+
+# tests/test_root_find.py:160-193: clipping to bounds selects the root
+@pytest.mark.parametrize("chord,tol", ((False, 1e-4), (True, 1e-2)), ids=("newton", "chord"))
+def test_newton_bounded_generic(chord, tol):
+    solver = (optx.Chord if chord else optx.Newton)(1e-5, 1e-5)
+    inf = float("inf")
+    y0 = torch.tensor([0.1, 1.1, 0.1, 0.1, -1.1], dtype=torch.float64, device=DEV)
+    sol = optx.root_find(F.newton_bounded, solver, y0, None, options=dict(lower=torch.tensor([-inf, 0.0, -inf, -inf, -inf])), throw=False)
+    assert np.allclose(to_np(sol.value), [0.0, 1.0, 0.0, 0.0, -1.0], rtol=tol, atol=tol)
+    y0 = torch.tensor([0.1, -1.1, 0.1, 0.1, -1.1], dtype=torch.float64, device=DEV)
+    sol = optx.root_find(F.newton_bounded, solver, y0, None, options=dict(upper=torch.tensor([inf, 0.0, inf, inf, inf])), throw=False)
+    assert np.allclose(to_np(sol.value), [0.0, -1.0, 0.0, 0.0, -1.0], rtol=tol, atol=tol)
+
+
+# tests/test_root_find.py:238-245: non-Cauchy (Hairer-Wanner) termination on f(y) = y returns successful
+@pytest.mark.parametrize("solver_cls", (optx.Newton, optx.Chord))
+def test_newton_chord_small_diff_generic(solver_cls):
+    sol = optx.root_find(lambda y, _: y, solver_cls(1e-5, 1e-5, cauchy_termination=False), torch.zeros(1, dtype=torch.float64, device=DEV))
+    assert _res_name(sol) == "successful"
+
+
+def test_newton_generic_batched_matches_registered_family():
+    """The implicit-Euler root finds of BASELINE configs[2] through the generic step kernel == the persistent kernel."""
+    w = synthetic.implicit_euler_batch(256)
+    A, Bm, yp, dt, y0 = (torch.as_tensor(w[k], device=DEV) for k in ("A", "B", "y_prev", "dt", "y0"))
+
+    def fn(y, a):
+        A_, B_, yp_, dt_ = a
+        return y - yp_ - dt_ * (A_ @ y + y * (B_ @ y))
+
+    gen = optx.root_find(fn, optx.Newton(1e-8, 1e-8), y0, (A, Bm, yp, dt), args_in_dims=(None, None, 0, 0), throw=False)
+    per = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-8, 1e-8), y0, (A, Bm, yp, dt), throw=False)
+    assert torch.equal(gen.stats["num_steps"], per.stats["num_steps"])
+    assert torch.equal(gen.result, per.result)
+    assert torch.allclose(gen.value, per.value, rtol=1e-11, atol=1e-13)
+
+
+# tests/test_minimise.py:30-62: BFGS on the minimisation zoo, f(argmin) ~ min at 1e-4, max_steps = 10_000; vs the oracle
+@pytest.mark.parametrize("name,fn,minimum,y0,args", F.MINIMISATION, ids=[p[0] for p in F.MINIMISATION])
+def test_bfgs_zoo_generic(name, fn, minimum, y0, args):
+    sol = optx.minimise(fn, optx.BFGS(1e-8, 1e-8), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000, throw=False)
+    fmin = float(fn(sol.value, _dev(args)))
+    assert np.allclose(fmin, minimum, atol=1e-4, rtol=1e-4)
+    ref = S.bfgs(F.batched_min(fn), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000)
+    assert _res_name(sol) == S.RESULT_NAMES[ref["result"][0]]
+    assert abs(int(sol.stats["num_steps"]) - int(ref["num_steps"][0])) <= max(2, int(0.1 * ref["num_steps"][0]))
+    assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-5, atol=1e-6)
+
+
+# tests/test_compat.py:19-24,41-45: Beale optimum [3, 0.5]; two steps are not enough
+def test_bfgs_beale_generic():
+    y0 = torch.tensor([2.0, 0.0], dtype=torch.float64, device=DEV)
+    sol = optx.minimise(F.beale, optx.BFGS(1e-8, 1e-8), y0, (1.5, 2.25, 2.625), max_steps=10_000)
+    assert np.allclose(to_np(sol.value), [3.0, 0.5], rtol=1e-5, atol=1e-5)
+    sol = optx.minimise(F.beale, optx.BFGS(1e-8, 1e-8), y0, (1.5, 2.25, 2.625), max_steps=2, throw=False)
+    assert _res_name(sol) == "nonlinear_max_steps_reached" and int(sol.stats["num_steps"]) == 2
+    with pytest.raises(RuntimeError):
+        optx.minimise(F.beale, optx.BFGS(1e-8, 1e-8), y0, (1.5, 2.25, 2.625), max_steps=2, throw=True)
+
+
+def test_bfgs_generic_prefix_parity_with_oracle():
+    """Step-by-step: with max_steps = k the step kernel and the oracle hold the same iterate and inverse Hessian."""
+    name, fn, minimum, y0, args = F.MINIMISATION[1]  # himmelblau
+    for k in (1, 2, 3, 5, 8):
+        sol = optx.minimise(fn, optx.BFGS(1e-8, 1e-8), torch.as_tensor(y0, device=DEV), args, max_steps=k, throw=False, return_hessian_inv=True)
+        ref = S.bfgs(F.batched_min(fn), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=k)
+        assert int(sol.stats["num_steps"]) == int(ref["num_steps"][0])
+        assert int(sol.stats["num_accepted_steps"][0]) == int(ref["num_accepted"][0])
+        assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-12, atol=0)
+        assert np.allclose(to_np(sol.state["hessian_inv"][0]), ref["hessian_inv"][0], rtol=1e-10, atol=1e-14)
+
+
+def test_bfgs_generic_matches_persistent_kernel():
+    """Chained Rosenbrock n = 64 (BASELINE configs[3]) through the generic step kernel == the persistent kernel."""
+    w = synthetic.rosenbrock_batch(8)
+    y0 = torch.as_tensor(w["y0"], device=DEV)
+
+    def fn(y, _):
+        return (100.0 * (y[1:] - y[:-1] ** 2) ** 2 + (1.0 - y[:-1]) ** 2).sum()
+
+    gen = optx.minimise(fn, optx.BFGS(1e-8, 1e-8), y0, None, max_steps=40, throw=False, return_hessian_inv=True)
+    per = optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), y0, None, max_steps=40, throw=False, return_hessian_inv=True)
+    assert torch.equal(gen.stats["num_accepted_steps"], per.stats["num_accepted_steps"])
+    assert torch.allclose(gen.value, per.value, rtol=1e-9, atol=1e-12)
+    assert torch.allclose(gen.state["hessian_inv"], per.state["hessian_inv"], rtol=1e-7, atol=1e-10)
+
+
+# tests/test_root_find.py:196-213: root_find through a minimiser (BFGS on norm(fn)) and the no-root case
+def test_root_via_min_generic():
+    y0 = torch.tensor([0.5, -0.3, 0.7], dtype=torch.float64, device=DEV)
+    sol = optx.root_find(F.root_via_min, optx.BFGS(1e-8, 1e-8), y0, None, throw=False)
+    assert np.allclose(to_np(sol.value), [-0.1, 0.5, 0.0], rtol=1e-5, atol=1e-5)
+    bad = optx.root_find(F.bad_root_via_min, optx.BFGS(1e-8, 1e-8), y0, None, throw=False)
+    assert _res_name(bad) == "nonlinear_max_steps_reached"
+    with pytest.raises(RuntimeError):
+        optx.root_find(F.bad_root_via_min, optx.BFGS(1e-8, 1e-8), y0, None, throw=True)
+
+
+# tests/test_least_squares.py:27-53 with a minimiser as the solver (_least_squares.py:102-114)
+def test_least_squares_via_bfgs_generic():
+    name, fn, minimum, y0, args = F.LEAST_SQUARES[1]
+    sol = optx.least_squares(fn, optx.BFGS(1e-8, 1e-8), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000, throw=False)
+    r = fn(sol.value, _dev(args))
+    assert np.allclose(float((r * r).sum()), minimum, atol=1e-4, rtol=1e-4)
+
+
+def test_generic_nonfinite_newton_bfgs():
+    nan = torch.tensor([float("nan")], dtype=torch.float64, device=DEV)
+    assert _res_name(optx.root_find(lambda y, _: y**2, optx.Newton(0.1, 0.1), nan, throw=False)) == "nonfinite"
+    assert _res_name(optx.minimise(lambda y, _: (y**2).sum(), optx.BFGS(0.1, 0.1), nan, throw=False)) == "nonfinite"
