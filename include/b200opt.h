@@ -195,13 +195,19 @@ int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const 
  * 79-99) for every still-running problem; n <= 1024.  f_eval [batch] = fn(y_eval), g_eval [batch][n] = its gradient.
  * root_norm: optional [batch], norm of the root function at the pre-step y: adds the `norm(f) < atol` condition of
  * root_find-through-a-minimiser (_root_find.py:64-73).  The carry (H^-1 n x n, gradient, direction, f, step size,
- * flags) lives in `state` (b200opt_bfgs_step_state_size bytes per problem), initialised by _init. */
+ * flags) lives in `state` (b200opt_bfgs_step_state_size bytes per problem), initialised by _init.
+ * update: B200OPT_UPDATE_BFGS or B200OPT_UPDATE_DFP (quasi_newton.py:487-573).  use_inverse != 0: the carry is the
+ * inverse Hessian approximation and the direction is a mat-vec; use_inverse == 0: the carry is the Hessian
+ * approximation and the direction comes from a Cholesky solve (n <= 64), non-finite solution => `singular`. */
+#define B200OPT_UPDATE_BFGS 0
+#define B200OPT_UPDATE_DFP 1
 int64_t b200opt_bfgs_step_state_size(int32_t dtype, int32_t n);
 int32_t b200opt_bfgs_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* y_eval,
                                void* state, int32_t* num_steps, int32_t* result, void* stream);
-int32_t b200opt_bfgs_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* g_eval,
-                          const void* root_norm, void* y, void* y_eval, void* state, const b200opt_options_t* opts,
-                          int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream);
+int32_t b200opt_bfgs_step(int32_t update, int32_t use_inverse, int32_t dtype, int64_t batch, int32_t n,
+                          const void* f_eval, const void* g_eval, const void* root_norm, void* y, void* y_eval,
+                          void* state, const b200opt_options_t* opts, int32_t* num_steps, int32_t* result,
+                          int32_t* active_count, void* stream);
 int32_t b200opt_bfgs_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result,
                                  void* stream);
 

@@ -25,6 +25,7 @@ from ._models import KIND_LSQ, KIND_MIN, KIND_ROOT, RegisteredModel
 from ._solution import RESULTS, Solution
 from ._solvers import (
     BFGS,
+    DFP,
     AbstractLeastSquaresSolver,
     AbstractMinimiser,
     AbstractRootFinder,
@@ -166,8 +167,8 @@ def _check_defaults(solver):
         raise NotImplementedError("the CUDA LM kernel implements ClassicalTrustRegion with the reference defaults")
     if isinstance(solver, GaussNewton) and search != LearningRate(1.0):
         raise NotImplementedError("the CUDA GN kernel implements LearningRate(1.0)")
-    if isinstance(solver, BFGS) and search != BacktrackingArmijo():
-        raise NotImplementedError("the CUDA BFGS kernel implements BacktrackingArmijo with the reference defaults")
+    if isinstance(solver, (BFGS, DFP)) and search != BacktrackingArmijo():
+        raise NotImplementedError("the CUDA quasi-Newton kernels implement BacktrackingArmijo with the reference defaults")
 
 
 # ------------------------------------------------------------------------------------------ least squares
@@ -363,11 +364,9 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
              args_in_dims=None):
     """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
     _check_common(fn, options, has_aux, adjoint)
-    if not isinstance(solver, BFGS):
+    if not isinstance(solver, (BFGS, DFP)):
         raise TypeError(f"minimise: unsupported solver {type(solver).__name__}")
     _check_defaults(solver)
-    if max_steps is None:
-        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
     if not isinstance(fn, RegisteredModel):
         from ._generic import minimise_generic
 
@@ -375,6 +374,11 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
                                 return_hessian_inv=return_hessian_inv)
     if fn.kind != KIND_MIN:
         raise TypeError(f"model {fn.name} is not a minimisation family")
+    if isinstance(solver, DFP) or not solver.use_inverse:
+        raise NotImplementedError("registered minimisation families run BFGS(use_inverse=True) in the persistent kernel; "
+                                  "DFP / use_inverse=False take a Python callable (generic step kernel)")
+    if max_steps is None:
+        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
     lib = _lib.load()
     y0, buf, single = _prepare_y0(y0)
     B, n = y0.shape

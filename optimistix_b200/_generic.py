@@ -263,15 +263,21 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
     res = t.empty((B,), dtype=t.int32, device=dev)
     active = t.zeros((1,), dtype=t.int32, device=dev)
     stream = t.cuda.current_stream(dev).cuda_stream
-    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps)
+    unbounded = max_steps is None  # compat.minimize without maxiter (compat/_impl.py:103): run until every problem stops
+    max_steps_k = (2**31 - 1) if unbounded else max_steps
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps_k)
+    update = _lib.UPDATE_DFP if getattr(solver, "_update", "bfgs") == "dfp" else _lib.UPDATE_BFGS
+    use_inverse = 1 if getattr(solver, "use_inverse", True) else 0
+    if not use_inverse and n > 64:
+        raise NotImplementedError("use_inverse=False factorises the Hessian approximation in shared memory: n <= 64")
     _lib.check(lib.b200opt_bfgs_step_init(dtype_code, B, n, Y0.data_ptr(), y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
                                           steps.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_init")
     launches = 0
-    for _ in range(max_steps):
+    while launches < max_steps_k:
         g, f = gv(y_eval)
         g, f = g.contiguous(), f.contiguous()
         rn = rootv(y).to(Y0.dtype).contiguous() if rootv is not None else None
-        _lib.check(lib.b200opt_bfgs_step(dtype_code, B, n, f.data_ptr(), g.data_ptr(), rn.data_ptr() if rn is not None else None,
+        _lib.check(lib.b200opt_bfgs_step(update, use_inverse, dtype_code, B, n, f.data_ptr(), g.data_ptr(), rn.data_ptr() if rn is not None else None,
                                          y.data_ptr(), y_eval.data_ptr(), state.data_ptr(), C.byref(opts), steps.data_ptr(),
                                          res.data_ptr(), active.data_ptr(), stream), "b200opt_bfgs_step")
         launches += 1
@@ -282,7 +288,7 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
         _throw_if_failed(res)
     stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches,
              "num_accepted_steps": state[:, n * n + 2 * n + 4].to(t.int32)}
-    st = {"f": state[:, n * n + 2 * n]}
+    st = {"f": state[:, n * n + 2 * n], "grad": state[:, n * n : n * n + n]}
     if return_hessian_inv:
-        st["hessian_inv"] = state[:, : n * n].reshape(B, n, n)
+        st["hessian_inv" if use_inverse else "hessian"] = state[:, : n * n].reshape(B, n, n)
     return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=st)

@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200opt.h")
 F32, F64 = 0, 1
 NORM_IDS = {"max": 0, "two": 1, "rms": 2}
 SOLVER_LM, SOLVER_GN, SOLVER_NEWTON, SOLVER_CHORD, SOLVER_BFGS = 0, 1, 2, 3, 4
+UPDATE_BFGS, UPDATE_DFP = 0, 1
 
 
 class Options(C.Structure):
@@ -75,7 +76,7 @@ _SIGNATURES = {
     "b200opt_root_step_finish": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_bfgs_step_state_size": (_i64, [_i32, _i32]),
     "b200opt_bfgs_step_init": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b200opt_bfgs_step": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_bfgs_step": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_bfgs_step_finish": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_gram_workspace_size": (_i64, [_i32]),
     "b200opt_gn_gram": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

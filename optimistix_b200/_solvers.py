@@ -143,6 +143,10 @@ class AbstractBFGS(AbstractQuasiNewton):
     pass
 
 
+class AbstractDFP(AbstractQuasiNewton):
+    pass
+
+
 def _check_verbose(verbose):
     if verbose not in (False, None):
         raise NotImplementedError("verbose=... printing is not available from inside the persistent CUDA kernel")
@@ -185,10 +189,26 @@ class Chord(_AbstractNewtonChord):
 
 
 class BFGS(AbstractBFGS):
+    """quasi_newton.py:443-458.  use_inverse=True (default): registered families run in the persistent kernel (H^-1 in
+    registers); Python callables and use_inverse=False (Hessian approximation + Cholesky solve) run in the generic
+    per-iteration step kernel."""
+    _update = "bfgs"
+
     def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, use_inverse: bool = True, verbose=False):
         _check_verbose(verbose)
-        if not use_inverse:
-            raise NotImplementedError("BFGS(use_inverse=False) is a 'next' row (SURVEY 8f.4); the CUDA path keeps H^-1")
+        self.rtol, self.atol, self.norm, self.use_inverse = rtol, atol, norm, use_inverse
+        self.descent = NewtonDescent(linear_solver=Cholesky())
+        self.search = BacktrackingArmijo()
+        self.verbose = verbose
+
+
+class DFP(AbstractDFP):
+    """Davidon-Fletcher-Powell (quasi_newton.py:576-633): same search and descent as BFGS, the DFP update
+    (:516-547).  Runs in the generic per-iteration step kernel."""
+    _update = "dfp"
+
+    def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, use_inverse: bool = True, verbose=False):
+        _check_verbose(verbose)
         self.rtol, self.atol, self.norm, self.use_inverse = rtol, atol, norm, use_inverse
         self.descent = NewtonDescent(linear_solver=Cholesky())
         self.search = BacktrackingArmijo()

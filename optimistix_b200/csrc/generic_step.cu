@@ -142,8 +142,16 @@ template <typename T> __global__ void root_step_init_kernel(int64_t batch, int n
 }
 
 // =============================================================================================== BFGS step
-// state per problem (elements of T): [H^-1 (n*n) | g (n) | newton (n) | f | alpha | first | terminate | num_accepted | pad..]
-__host__ __device__ inline int64_t bfgs_state_stride(int n) { return ((int64_t)n * n + 2 * n + 5 + 3) / 4 * 4; }
+// state per problem (elements of T):
+//   [M (n*n: H^-1, or H when use_inverse=False) | g (n) | newton (n) | f | alpha | first | terminate | num_accepted | descent result | pad..]
+// Update variants (quasi_newton.py:342-415 BFGS, :487-573 DFP), with s = y_eval - y, q = grad_new - grad, inner = q.s:
+//   form A:  M += ((inner + v.Mv) / inner^2) u u^T - (Mv u^T + u Mv^T) / inner     BFGS inverse (u=s, v=q), DFP direct (u=q, v=s)
+//   form B:  M += u u^T / inner - Mv Mv^T / (v.Mv)                                 DFP inverse (u=s, v=q), BFGS direct (u=q, v=s)
+// Direct variants (use_inverse=False) get the direction from a Cholesky solve M newton = grad (NewtonDescent with
+// lx.Cholesky(), quasi_newton.py:455; n <= 64, factorised in shared memory); a non-finite solution is `singular`.
+constexpr int B200OPT_QN_FORM_B = 1, B200OPT_QN_SWAP = 2, B200OPT_QN_DIRECT = 4;
+constexpr int kBfgsDirectNMax = 64;
+__host__ __device__ inline int64_t bfgs_state_stride(int n) { return ((int64_t)n * n + 2 * n + 6 + 3) / 4 * 4; }
 
 template <typename T> struct BfgsStepParams {
   const T* f_eval;       // [batch]     fn(y_eval)
@@ -159,7 +167,7 @@ template <typename T> struct BfgsStepParams {
   int64_t batch;
   int n;
   T rtol, atol;
-  int norm, max_steps;
+  int norm, max_steps, mode;
 };
 
 constexpr int kBfgsStepThreads = 128;
@@ -194,7 +202,11 @@ template <typename T> __global__ void __launch_bounds__(kBfgsStepThreads) bfgs_s
   T* vd = reinterpret_cast<T*>(smem_raw);  // s = y_eval - y
   T* vq = vd + n;                          // q = grad_new - grad
   T* vg = vq + n;                          // grad_new
-  T* vhq = vg + n;                         // H^-1 q
+  T* vhq = vg + n;                         // M v
+  T* chol = vhq + n;                       // direct variants: n x (n + 1) copy of the Hessian approximation
+  const bool form_b = (p.mode & B200OPT_QN_FORM_B) != 0, direct = (p.mode & B200OPT_QN_DIRECT) != 0;
+  const T* vu = (p.mode & B200OPT_QN_SWAP) ? vq : vd;
+  const T* vv = (p.mode & B200OPT_QN_SWAP) ? vd : vq;
   const int64_t prob = blockIdx.x;
   T* st = p.state + prob * p.state_stride;
   T* H = st;
@@ -205,6 +217,7 @@ template <typename T> __global__ void __launch_bounds__(kBfgsStepThreads) bfgs_s
   int steps = p.num_steps[prob];
   bool terminate = sc[3] != T(0);
   if (terminate || result != RES_OK || steps >= p.max_steps) return;  // block-uniform
+  int descent_result = (int)sc[5];
   const T rtol = p.rtol, atol = p.atol;
   const T f = sc[0];
   T alpha = sc[1];
@@ -235,34 +248,84 @@ template <typename T> __global__ void __launch_bounds__(kBfgsStepThreads) bfgs_s
     const bool update = inner > Num<T>::eps();  // :360
     T c1 = T(0), c2 = T(0);
     if (update) {
-      // pass 1: inv_mvp = H q (one warp per row, coalesced)
+      // pass 1: mvp = M v (one warp per row, coalesced)
       for (int i = warp; i < n; i += NW) {
         T acc = T(0);
-        for (int j = lane; j < n; j += 32) acc += H[(int64_t)i * n + j] * vq[j];
+        for (int j = lane; j < n; j += 32) acc += H[(int64_t)i * n + j] * vv[j];
         acc = warp_sum(acc);
         if (lane == 0) vhq[i] = acc;
       }
       __syncthreads();
       T part = T(0);
-      for (int j = tid; j < n; j += kBfgsStepThreads) part += vq[j] * vhq[j];
+      for (int j = tid; j < n; j += kBfgsStepThreads) part += vv[j] * vhq[j];
       const T mvp_inner = block_sum(part, red);
-      c1 = (inner + mvp_inner) / (inner * inner);  // term1 coefficient (:379)
-      c2 = T(1) / inner;                           // term2 coefficient (:380)
+      if (form_b) {
+        c1 = T(1) / inner;      // u u^T / inner
+        c2 = T(1) / mvp_inner;  // Mv Mv^T / (v.Mv)
+      } else {
+        c1 = (inner + mvp_inner) / (inner * inner);  // term1 coefficient (:379)
+        c2 = T(1) / inner;                           // term2 coefficient (:380)
+      }
     }
-    // pass 2: H' = H + c1 s s^T - c2 (Hq s^T + s Hq^T), fused with newton = H' grad_new (gauss_newton.py:60-61)
+    // pass 2: the rank-2 update, fused (inverse variants) with newton = M' grad_new (gauss_newton.py:60-61)
     for (int i = warp; i < n; i += NW) {
-      const T s_i = vd[i], hq_i = update ? vhq[i] : T(0);
+      const T u_i = vu[i], mv_i = update ? vhq[i] : T(0);
       T acc = T(0);
       for (int j = lane; j < n; j += 32) {
         T h = H[(int64_t)i * n + j];
         if (update) {
-          h = h + c1 * (s_i * vd[j]) - c2 * (hq_i * vd[j] + s_i * vhq[j]);
+          h = form_b ? h + c1 * (u_i * vu[j]) - c2 * (mv_i * vhq[j]) : h + c1 * (u_i * vu[j]) - c2 * (mv_i * vu[j] + u_i * vhq[j]);
           H[(int64_t)i * n + j] = h;
         }
+        if (direct) chol[i * (n + 1) + j] = h;
         acc += h * vg[j];
       }
       acc = warp_sum(acc);
-      if (lane == 0) nst[i] = acc;
+      if (lane == 0 && !direct) nst[i] = acc;
+    }
+    if (direct) {
+      // newton = M'^-1 grad_new by Cholesky (lower factor in place; a non-positive pivot gives NaN -> `singular`)
+      __syncthreads();
+      for (int k = 0; k < n; ++k) {
+        const T dk = t_sqrt(chol[k * (n + 1) + k]);
+        __syncthreads();
+        for (int i = k + tid; i < n; i += kBfgsStepThreads) chol[i * (n + 1) + k] = (i == k) ? dk : chol[i * (n + 1) + k] / dk;
+        __syncthreads();
+        const int rem = n - k - 1;
+        for (int e = tid; e < rem * rem; e += kBfgsStepThreads) {
+          const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+          if (j <= i) chol[i * (n + 1) + j] -= chol[i * (n + 1) + k] * chol[j * (n + 1) + k];
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {  // substitutions: one warp, lane-strided rows, serial in k
+        for (int i = lane; i < n; i += 32) vhq[i] = vg[i];
+        __syncwarp();
+        for (int k = 0; k < n; ++k) {
+          const T zk = vhq[k] / chol[k * (n + 1) + k];
+          __syncwarp();
+          if (lane == 0) vhq[k] = zk;
+          for (int i = k + 1 + lane; i < n; i += 32) vhq[i] -= chol[i * (n + 1) + k] * zk;
+          __syncwarp();
+        }
+        for (int k = n - 1; k >= 0; --k) {
+          const T xk = vhq[k] / chol[k * (n + 1) + k];
+          __syncwarp();
+          if (lane == 0) vhq[k] = xk;
+          for (int i = lane; i < k; i += 32) vhq[i] -= chol[k * (n + 1) + i] * xk;
+          __syncwarp();
+        }
+        bool fin_sol = true;
+        for (int i = lane; i < n; i += 32) {
+          nst[i] = vhq[i];
+          fin_sol = fin_sol && t_finite(vhq[i]);
+        }
+        fin_sol = __all_sync(kFull, fin_sol);
+        if (lane == 0) red[0] = fin_sol ? T(0) : T(1);
+      }
+      __syncthreads();
+      descent_result = (red[0] != T(0)) ? RES_SINGULAR : RES_OK;  // newton_step: RESULTS.promote(out.result)
+      __syncthreads();
     }
     // ---- termination (quasi_newton.py:244-249): cauchy_termination on y and on the scalar f, never on the first step
     NormAcc<T> yn(p.norm);
@@ -284,13 +347,14 @@ template <typename T> __global__ void __launch_bounds__(kBfgsStepThreads) bfgs_s
     for (int j = tid; j < n; j += kBfgsStepThreads) p.y_eval[prob * n + j] = p.y[prob * n + j] - alpha * nst[j];
   }
   if (p.root_norm) terminate = terminate && (p.root_norm[prob] < atol);  // _ToRoot.terminate (_root_find.py:64-73)
-  result = RES_OK;
+  result = descent_result;  // quasi_newton.py:280-283: the descent's result (the search always succeeds)
   if (!y_old_finite) result = RES_NONFINITE;  // _iterate.py:216
   ++steps;
   if (tid == 0) {
     if (accept) {
       sc[0] = fe;
       sc[4] = sc[4] + T(1);
+      sc[5] = (T)descent_result;
     }
     sc[1] = alpha;
     sc[2] = T(0);
@@ -365,8 +429,8 @@ static int root_step_typed(int64_t batch, int n, const void* f, const void* J, c
 }
 
 template <typename T>
-static int bfgs_step_typed(int64_t batch, int n, const void* f, const void* g, const void* root_norm, void* y, void* y_eval, void* state,
-                           const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
+static int bfgs_step_typed(int mode, int64_t batch, int n, const void* f, const void* g, const void* root_norm, void* y, void* y_eval,
+                           void* state, const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
   BfgsStepParams<T> p;
   p.f_eval = static_cast<const T*>(f);
   p.g_eval = static_cast<const T*>(g);
@@ -384,8 +448,10 @@ static int bfgs_step_typed(int64_t batch, int n, const void* f, const void* g, c
   p.atol = (T)o->atol;
   p.norm = o->norm;
   p.max_steps = o->max_steps;
+  p.mode = mode;
   if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
-  bfgs_step_kernel<T><<<(unsigned)batch, kBfgsStepThreads, 4 * (size_t)n * sizeof(T), st>>>(p);
+  const size_t smem = (4 * (size_t)n + ((mode & B200OPT_QN_DIRECT) ? (size_t)n * (n + 1) : 0)) * sizeof(T);
+  bfgs_step_kernel<T><<<(unsigned)batch, kBfgsStepThreads, smem, st>>>(p);
   return check_cuda(cudaGetLastError(), "bfgs_step_kernel launch");
 }
 
@@ -479,16 +545,24 @@ int32_t b200opt_bfgs_step_init(int32_t dtype, int64_t batch, int32_t n, const vo
   return check_cuda(cudaGetLastError(), "bfgs_step_init launch");
 }
 
-int32_t b200opt_bfgs_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* g_eval, const void* root_norm,
-                          void* y, void* y_eval, void* state, const b200opt_options_t* opts, int32_t* num_steps, int32_t* result,
-                          int32_t* active_count, void* stream) {
-  if (int e = gstep_check("bfgs_step", dtype, batch, n, kBfgsStepNMax)) return e;
+int32_t b200opt_bfgs_step(int32_t update, int32_t use_inverse, int32_t dtype, int64_t batch, int32_t n, const void* f_eval,
+                          const void* g_eval, const void* root_norm, void* y, void* y_eval, void* state,
+                          const b200opt_options_t* opts, int32_t* num_steps, int32_t* result, int32_t* active_count, void* stream) {
+  if (int e = gstep_check("bfgs_step", dtype, batch, n, use_inverse ? kBfgsStepNMax : kBfgsDirectNMax)) return e;
   if (int e = opts_check("bfgs_step", opts)) return e;
+  if (update != B200OPT_UPDATE_BFGS && update != B200OPT_UPDATE_DFP) {
+    set_error("bfgs_step: unknown quasi-Newton update %d", update);
+    return B200OPT_EINVAL;
+  }
   if (batch == 0) return 0;
+  // BFGS inverse: form A (u=s, v=q); DFP inverse: form B (u=s, v=q); BFGS direct: form B swapped; DFP direct: form A swapped
+  int mode = 0;
+  if ((update == B200OPT_UPDATE_DFP) == (use_inverse != 0)) mode |= B200OPT_QN_FORM_B;
+  if (!use_inverse) mode |= B200OPT_QN_SWAP | B200OPT_QN_DIRECT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200OPT_F64)
-    return bfgs_step_typed<double>(batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
-  return bfgs_step_typed<float>(batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
+    return bfgs_step_typed<double>(mode, batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
+  return bfgs_step_typed<float>(mode, batch, n, f_eval, g_eval, root_norm, y, y_eval, state, opts, num_steps, result, active_count, st);
 }
 
 int32_t b200opt_bfgs_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result, void* stream) {

@@ -356,9 +356,32 @@ def newton_chord(
     return dict(value=y, num_steps=num_steps, result=result)
 
 
+def _solve_cholesky(H, g):
+    """lx.linear_solve(H, g, lx.Cholesky(), throw=False): lower factor, two triangular solves; a non-positive pivot
+    gives NaN (jnp.linalg.cholesky semantics) and a non-finite solution is reported as `singular`."""
+    B, n, _ = H.shape
+    x = np.full((B, n), np.nan, H.dtype)
+    for b in range(B):
+        try:
+            L = np.linalg.cholesky(H[b])
+        except np.linalg.LinAlgError:
+            continue
+        z = np.zeros(n, H.dtype)
+        for i in range(n):
+            z[i] = (g[b, i] - L[i, :i] @ z[:i]) / L[i, i]
+        xb = np.zeros(n, H.dtype)
+        for i in range(n - 1, -1, -1):
+            xb[i] = (z[i] - L[i + 1 :, i] @ xb[i + 1 :]) / L[i, i]
+        x[b] = xb
+    res = np.where(np.isfinite(x).all(axis=1), OK, SINGULAR)
+    return x, res
+
+
 # ------------------------------------------------------------------ BFGS
-def bfgs(model, y0, args=None, *, rtol, atol, norm="max", max_steps=256, near_zero_residual=None):
-    """BFGS with use_inverse=True and BacktrackingArmijo.
+def bfgs(model, y0, args=None, *, rtol, atol, norm="max", max_steps=256, near_zero_residual=None, update="bfgs", use_inverse=True):
+    """BFGS / DFP (``update``) with BacktrackingArmijo, on the inverse Hessian (``use_inverse=True``, the default) or on
+    the Hessian approximation itself with a Cholesky solve for the direction (quasi_newton.py:387-399, :487-573;
+    NewtonDescent(linear_solver=lx.Cholesky()) :455, gauss_newton.py:64-78: non-finite solution => singular).
 
     Restates quasi_newton.py:176-202 (init), :204-300 (step), :334-340 (init_hessian), :342-415
     (update_hessian, inverse branch :371-385); backtracking.py:29-31,51-53,79-99; NewtonDescent
@@ -386,6 +409,7 @@ def bfgs(model, y0, args=None, *, rtol, atol, norm="max", max_steps=256, near_ze
     froot = None
     if near_zero_residual is not None:
         froot = np.full(B, np.inf, dt)
+    dres = np.full(B, OK)
 
     with np.errstate(all="ignore"):
         for _ in range(max_steps):
@@ -405,13 +429,23 @@ def bfgs(model, y0, args=None, *, rtol, atol, norm="max", max_steps=256, near_ze
             q = g_e - g
             inner = np.einsum("bn,bn->b", q, d)
             upd = inner > eps  # :360
-            Hq = np.einsum("bij,bj->bi", Hinv, q)
-            mvp_inner = np.einsum("bn,bn->b", q, Hq)
-            term1 = ((inner + mvp_inner)[:, None, None] * (d[:, :, None] * d[:, None, :])) / (inner**2)[:, None, None]
-            term2 = (Hq[:, :, None] * d[:, None, :] + d[:, :, None] * Hq[:, None, :]) / inner[:, None, None]
+            # the four updates are two formulas with the roles of s = d and q exchanged (:371-399, :516-547)
+            u, v = (d, q) if use_inverse else (q, d)
+            Hq = np.einsum("bij,bj->bi", Hinv, v)
+            mvp_inner = np.einsum("bn,bn->b", v, Hq)
+            if (update == "bfgs") == bool(use_inverse):
+                term1 = ((inner + mvp_inner)[:, None, None] * (u[:, :, None] * u[:, None, :])) / (inner**2)[:, None, None]
+                term2 = (Hq[:, :, None] * u[:, None, :] + u[:, :, None] * Hq[:, None, :]) / inner[:, None, None]
+            else:
+                term1 = (u[:, :, None] * u[:, None, :]) / inner[:, None, None]
+                term2 = (Hq[:, :, None] * Hq[:, None, :]) / mvp_inner[:, None, None]
             H_upd = Hinv + term1 - term2  # :375-382
             H_acc = _freeze(upd, H_upd, Hinv)
-            newton_acc = np.einsum("bij,bj->bi", H_acc, g_e)  # gauss_newton.py:60-61
+            if use_inverse:
+                newton_acc = np.einsum("bij,bj->bi", H_acc, g_e)  # gauss_newton.py:60-61
+                dres_acc = np.full(B, OK)
+            else:
+                newton_acc, dres_acc = _solve_cholesky(H_acc, g_e)  # gauss_newton.py:64-78
             term_acc = cauchy_termination(rtol, atol, nrm, y_eval, d, f_e[:, None], df[:, None])  # :244-246
             term_acc = term_acc & ~first  # :247-249
             n_terminate = np.where(accept, term_acc, False)
@@ -420,8 +454,9 @@ def bfgs(model, y0, args=None, *, rtol, atol, norm="max", max_steps=256, near_ze
             g_new = _freeze(accept, g_e, g)
             H_new = _freeze(accept, H_acc, Hinv)
             newton_new = _freeze(accept, newton_acc, newton)
+            dres = np.where(accept, dres_acc, dres)
             y_eval_new = y_new - n_alpha[:, None] * newton_new  # gauss_newton.py:126-127, quasi_newton.py:281-282
-            n_result = np.full(B, OK)
+            n_result = dres.copy()  # quasi_newton.py:280-283
             if froot is not None:
                 # _ToRoot.step stores the solver's returned aux, which is prev_aux = the residual at the
                 # carry's pre-step y (quasi_newton.py:285: where(first_step, aux, state.aux); on the first

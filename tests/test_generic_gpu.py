@@ -235,3 +235,50 @@ def test_generic_nonfinite_newton_bfgs():
     nan = torch.tensor([float("nan")], dtype=torch.float64, device=DEV)
     assert _res_name(optx.root_find(lambda y, _: y**2, optx.Newton(0.1, 0.1), nan, throw=False)) == "nonfinite"
     assert _res_name(optx.minimise(lambda y, _: (y**2).sum(), optx.BFGS(0.1, 0.1), nan, throw=False)) == "nonfinite"
+
+
+# ---- quasi-Newton variants (quasi_newton.py:387-399 BFGS on the Hessian, :487-573 DFP) vs the oracle
+@pytest.mark.parametrize("cls,update", ((optx.BFGS, "bfgs"), (optx.DFP, "dfp")))
+@pytest.mark.parametrize("use_inverse", (True, False))
+@pytest.mark.parametrize("idx", (0, 1, 2))  # bowl (n=20), himmelblau, matyas
+def test_quasi_newton_variants_generic(cls, update, use_inverse, idx):
+    name, fn, minimum, y0, args = F.MINIMISATION[idx]
+    sol = optx.minimise(fn, cls(1e-8, 1e-8, use_inverse=use_inverse), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000,
+                        throw=False)
+    ref = S.bfgs(F.batched_min(fn), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000, update=update, use_inverse=use_inverse)
+    assert _res_name(sol) == S.RESULT_NAMES[ref["result"][0]]
+    if S.RESULT_NAMES[ref["result"][0]] == "successful":
+        fmin = float(fn(sol.value, _dev(args)))
+        assert np.allclose(fmin, minimum, atol=1e-4, rtol=1e-4)
+        assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-5, atol=1e-6)
+    # the first steps are the same state machine
+    for k in (1, 2, 3, 4):
+        g = optx.minimise(fn, cls(1e-8, 1e-8, use_inverse=use_inverse), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=k, throw=False)
+        r = S.bfgs(F.batched_min(fn), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=k, update=update, use_inverse=use_inverse)
+        assert int(g.stats["num_steps"]) == int(r["num_steps"][0])
+        assert np.allclose(to_np(g.value), r["value"][0], rtol=1e-9, atol=1e-11)  # matyas: iterates cancel to ~1e-13
+
+
+# tests/test_compat.py:19-24,27-45 of the reference: the jax.scipy.optimize.minimize drop-in
+def test_compat_minimize():
+    def beale(x, c1, c2, c3):
+        a, b = x[0], x[1]
+        return (c1 - a + a * b) ** 2 + (c2 - a + a * b**2) ** 2 + (c3 - a + a * b**3) ** 2
+
+    x0 = torch.tensor([2.0, 0.0], dtype=torch.float64, device=DEV)
+    res = optx.compat.minimize(beale, x0, (1.5, 2.25, 2.625), method="bfgs")
+    assert bool(res.success) and int(res.status) == 0
+    assert np.allclose(to_np(res.x), [3.0, 0.5], rtol=1e-4, atol=1e-4)
+    assert np.allclose(float(res.fun), 0.0, atol=1e-8)
+    assert res.hess_inv.shape == (2, 2) and res.jac.shape == (2,)
+    assert int(res.nit) <= int(res.nfev)
+    res2 = optx.compat.minimize(beale, x0, (1.5, 2.25, 2.625), method="BFGS", options=dict(maxiter=2))
+    assert not bool(res2.success) and int(res2.status) == 1 and int(res2.nfev) == 2
+    with pytest.raises(ValueError):
+        optx.compat.minimize(beale, x0, (1.5, 2.25, 2.625), method="l-bfgs")
+    with pytest.raises(TypeError):
+        optx.compat.minimize(beale, x0, [1.5, 2.25, 2.625], method="bfgs")
+    with pytest.raises(ValueError):
+        optx.compat.minimize(beale, x0, (1.5, 2.25, 2.625), method="bfgs", options=dict(gtol=1.0))
+    with pytest.raises(ValueError):
+        optx.compat.minimize(beale, x0[None], (1.5, 2.25, 2.625), method="bfgs")

@@ -166,3 +166,15 @@ def test_batched_equals_unbatched():
         one = S.levenberg_marquardt(models.exp_decay, w["y0"][i : i + 1], dict(t=w["t"], d=w["d"][i : i + 1]), rtol=1e-8, atol=1e-8)
         assert one["num_steps"][0] == full["num_steps"][i]
         assert np.array_equal(one["value"][0], full["value"][i])
+
+
+# ---- helpers.py:250-254 of the reference: BFGS(use_inverse=False), DFP(use_inverse=True/False) in the minimiser list of
+# test_minimise.py:30-62 (f(argmin) ~ min at 1e-4)
+@pytest.mark.parametrize("update,use_inverse", (("bfgs", False), ("dfp", True), ("dfp", False)))
+@pytest.mark.parametrize("name,fn,minimum,y0,args", F.MINIMISATION[:3], ids=[p[0] for p in F.MINIMISATION[:3]])
+def test_quasi_newton_variants_zoo(name, fn, minimum, y0, args, update, use_inverse):
+    model = F.batched_min(fn)
+    out = S.bfgs(model, y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000, update=update, use_inverse=use_inverse)
+    fmin, _ = model(out["value"], args)
+    assert S.RESULT_NAMES[out["result"][0]] == "successful"
+    assert np.allclose(fmin, minimum, atol=1e-4, rtol=1e-4)
