@@ -190,6 +190,13 @@ int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f
 int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result,
                                  void* stream);
 
+/* ---- batched dense solve A x = b (n <= 32), LU with partial pivoting, one warp per system ----------------------
+ * The linear solve of ImplicitAdjoint (optimistix/_ad.py:83-118: tangents / cotangents of a solution are
+ * -(d rewrite / d y)^-1 d rewrite / d args).  A [batch][n][n] row-major, b and x [batch][n]; status (optional)
+ * [batch]: successful, or singular when the solution is not finite. */
+int32_t b200opt_lu_solve(int32_t dtype, int64_t batch, int32_t n, const void* A, const void* b, void* x, int32_t* status,
+                         void* stream);
+
 /* ---- generic per-iteration step, minimisation (BFGS, inverse Hessian, backtracking Armijo) -------------------
  * One call = one AbstractQuasiNewton.step (optimistix/_solver/quasi_newton.py:204-300, :342-415; backtracking.py:
  * 79-99) for every still-running problem; n <= 1024.  f_eval [batch] = fn(y_eval), g_eval [batch][n] = its gradient.

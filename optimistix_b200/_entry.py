@@ -182,7 +182,7 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
             raise NotImplementedError("least_squares through a minimiser takes a Python callable (generic path)")
         _check_common(fn, options, has_aux, adjoint)
         return minimise(lambda y, a: 0.5 * (fn(y, a).reshape(-1) ** 2).sum(), solver, y0, args, options, max_steps=max_steps,
-                        throw=throw, args_in_dims=args_in_dims)
+                        adjoint=adjoint, throw=throw, args_in_dims=args_in_dims, _implicit=("lstsq", fn))
     if not isinstance(solver, (LevenbergMarquardt, GaussNewton)):
         raise TypeError(f"least_squares: unsupported solver {type(solver).__name__}")
     _check_common(fn, options, has_aux, adjoint)
@@ -193,7 +193,7 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
         from ._generic import least_squares_generic
 
         return least_squares_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, root_near_zero=_root_near_zero,
-                                     options=options, args_in_dims=args_in_dims)
+                                     options=options, args_in_dims=args_in_dims, adjoint=adjoint)
     if fn.kind != KIND_LSQ:
         raise TypeError(f"model {fn.name} is not a least-squares family")
     if fn.name == "linear_rows":
@@ -248,8 +248,8 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
         raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
     if isinstance(solver, AbstractLeastSquaresSolver):
         # _root_find.py:200-225: least-squares solver wrapped in _LstsqToRoot (extra `norm(f) < atol` test)
-        return least_squares(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, _root_near_zero=True, chunk=chunk,
-                             args_in_dims=args_in_dims)
+        return least_squares(fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw, _root_near_zero=True,
+                             chunk=chunk, args_in_dims=args_in_dims)
     if isinstance(solver, AbstractMinimiser):
         # _root_find.py:39-41,45-80,176-199: minimise norm(fn), terminate only once norm(fn) < atol as well
         if isinstance(fn, RegisteredModel):
@@ -259,13 +259,14 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
 
         norm = solver.norm
         return minimise_generic(lambda y, a: norm(fn(y, a).reshape(-1)), solver, y0, args, max_steps=max_steps,
-                                throw=throw, args_in_dims=args_in_dims, root_fn=fn)
+                                throw=throw, args_in_dims=args_in_dims, root_fn=fn, adjoint=adjoint)
     if not isinstance(solver, (Newton, Chord)):
         raise TypeError(f"root_find: unsupported solver {type(solver).__name__}")
     if not isinstance(fn, RegisteredModel):
         from ._generic import root_find_generic
 
-        return root_find_generic(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims)
+        return root_find_generic(fn, solver, y0, args, options, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims,
+                                 adjoint=adjoint)
     if fn.kind != KIND_ROOT:
         raise TypeError(f"model {fn.name} is not a root-finding family")
     lib = _lib.load()
@@ -354,14 +355,14 @@ def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_s
             raise ValueError("The input and output of `fixed_point_fn` must have the same structure")
         return out - y
 
-    return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, throw=throw,
+    return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, adjoint=adjoint, throw=throw,
                      args_in_dims=args_in_dims)
 
 
 # ------------------------------------------------------------------------------------------ minimise
 def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False,
-             args_in_dims=None):
+             args_in_dims=None, _implicit=None):
     """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
     _check_common(fn, options, has_aux, adjoint)
     if not isinstance(solver, (BFGS, DFP)):
@@ -371,7 +372,7 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
         from ._generic import minimise_generic
 
         return minimise_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims,
-                                return_hessian_inv=return_hessian_inv)
+                                return_hessian_inv=return_hessian_inv, adjoint=adjoint, implicit=_implicit)
     if fn.kind != KIND_MIN:
         raise TypeError(f"model {fn.name} is not a minimisation family")
     if isinstance(solver, DFP) or not solver.use_inverse:

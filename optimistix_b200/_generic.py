@@ -18,6 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from ._adjoint import attach_if_needed
 from ._solution import RESULTS, Solution
 
 
@@ -54,7 +55,8 @@ def _batched_r_and_J(fn, args, args_in_dims, jac_mode, single):
     return lambda Y: vm(Y, args)
 
 
-def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_zero=False, options=None, args_in_dims=None):
+def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_zero=False, options=None, args_in_dims=None,
+                          adjoint=None, implicit=None):
     """LM / GN for an arbitrary residual function (device tensors only: the Jacobian is evaluated by torch on the GPU)."""
     from ._solvers import LevenbergMarquardt
 
@@ -76,7 +78,7 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
         raise NotImplementedError("generic least-squares step kernel supports n <= 16 parameters (register-resident Gram)")
     dtype_code = _lib.F32 if y0.dtype == t.float32 else _lib.F64
     jac_mode = (options or {}).get("jac", "fwd")
-    rj = _batched_r_and_J(fn, args, args_in_dims, jac_mode, single)
+    rj = _batched_r_and_J(fn, _detached(args), args_in_dims, jac_mode, single)
     r, J = rj(Y0)
     m = int(r.shape[1])
     es = 4 if dtype_code == _lib.F32 else 8
@@ -115,6 +117,8 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
             raise RuntimeError(f"{bad.size} of {rh.size} solves failed; first failure (problem {int(bad[0])}): "
                                f"{RESULTS.name(code)}: {RESULTS[code]}")
     stats = {"num_steps": steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    kind, ifn = implicit or ("root" if root_near_zero else "lstsq", fn)
+    y = attach_if_needed(adjoint, kind, ifn, y, args, args_in_dims)
     value, result = y, res
     if single:
         value, result = y[0], res[0]
@@ -149,6 +153,15 @@ def _throw_if_failed(res):
                            f"{RESULTS.name(code)}: {RESULTS[code]}")
 
 
+def _detached(args):
+    """args with every tensor leaf detached: the forward iteration is never recorded by autograd (ImplicitAdjoint
+    differentiates the optimality condition at the solution instead, _adjoint.py)."""
+    t = _torch()
+    from torch.utils._pytree import tree_map
+
+    return tree_map(lambda x: x.detach() if isinstance(x, t.Tensor) else x, args)
+
+
 def _vmapped(f, args, args_in_dims):
     """vmap f(y, args) over the batch axis of y (and of the leaves of args selected by args_in_dims)."""
     t = _torch()
@@ -159,7 +172,7 @@ def _vmapped(f, args, args_in_dims):
     return lambda Y: vm(Y, args)
 
 
-def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_in_dims=None):
+def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_in_dims=None, adjoint=None):
     """Newton / Chord for an arbitrary `fn(y, args) -> [n]`: torch evaluates f and the n x n Jacobian (the role of
     jax.linearize / jacfwd at newton_chord.py:116-119; Chord: once, at y0, :80-87), `b200opt_root_step` does the LU
     solve with partial pivoting, the update, clipping, termination and result codes."""
@@ -179,8 +192,9 @@ def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_i
             raise ValueError("root_find: fn must map [n] -> [n]")
         return out
 
-    f_only = _vmapped(one, args, args_in_dims)
-    f_and_J = _vmapped(lambda y, a: tuple(reversed(t.func.jacfwd(lambda z: (one(z, a), one(z, a)), has_aux=True)(y))), args,
+    args_fwd = _detached(args)
+    f_only = _vmapped(one, args_fwd, args_in_dims)
+    f_and_J = _vmapped(lambda y, a: tuple(reversed(t.func.jacfwd(lambda z: (one(z, a), one(z, a)), has_aux=True)(y))), args_fwd,
                        args_in_dims)
     lower = upper = None
     if options:
@@ -226,10 +240,12 @@ def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_i
     if throw:
         _throw_if_failed(res)
     stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    y = attach_if_needed(adjoint, "root", fn, y, args, args_in_dims)
     return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=state)
 
 
-def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=None, root_fn=None, return_hessian_inv=False):
+def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=None, root_fn=None, return_hessian_inv=False,
+                     adjoint=None, implicit=None):
     """BFGS (inverse Hessian, backtracking Armijo) for an arbitrary scalar `fn(y, args)`: torch evaluates f and its
     gradient (jax.linearize + linear_transpose at quasi_newton.py:214-227), `b200opt_bfgs_step` does the rest.
 
@@ -247,11 +263,12 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
             raise ValueError("minimise function must output a single scalar.")  # _minimise.py:97-104
         return out.reshape(())
 
-    gv = _vmapped(lambda y, a: t.func.grad_and_value(lambda z: one(z, a))(y), args, args_in_dims)
+    args_fwd = _detached(args)
+    gv = _vmapped(lambda y, a: t.func.grad_and_value(lambda z: one(z, a))(y), args_fwd, args_in_dims)
     rootv = None
     if root_fn is not None:
         norm = solver.norm
-        rootv = _vmapped(lambda y, a: norm(root_fn(y, a).reshape(-1)), args, args_in_dims)
+        rootv = _vmapped(lambda y, a: norm(root_fn(y, a).reshape(-1)), args_fwd, args_in_dims)
     es = 4 if dtype_code == _lib.F32 else 8
     nbytes = lib.b200opt_bfgs_step_state_size(dtype_code, n)
     if nbytes <= 0:
@@ -291,4 +308,6 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
     st = {"f": state[:, n * n + 2 * n], "grad": state[:, n * n : n * n + n]}
     if return_hessian_inv:
         st["hessian_inv" if use_inverse else "hessian"] = state[:, : n * n].reshape(B, n, n)
+    kind, ifn = implicit or (("root", root_fn) if root_fn is not None else ("min", fn))
+    y = attach_if_needed(adjoint, kind, ifn, y, args, args_in_dims)
     return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=st)

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "b200opt_root_step_init": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_root_step": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_root_step_finish": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp]),
+    "b200opt_lu_solve": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_bfgs_step_state_size": (_i64, [_i32, _i32]),
     "b200opt_bfgs_step_init": (_i32, [_i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_bfgs_step": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

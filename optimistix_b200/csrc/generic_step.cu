@@ -141,6 +141,31 @@ template <typename T> __global__ void root_step_init_kernel(int64_t batch, int n
   }
 }
 
+// =============================================================================================== batched LU solve
+// A x = b for `batch` independent n x n systems (n <= 32): the linear solve of ImplicitAdjoint (optimistix/_ad.py:83-118,
+// lx.AutoLinearSolver(well_posed=None) on a square operator = LU with partial pivoting).  One warp per system, the same
+// row-per-lane factorisation as the Newton kernels; status = singular when the solution is not finite.
+template <typename T, int N>
+__global__ void __launch_bounds__(kRootStepWarps * 32) lu_solve_kernel(const T* A, const T* b, T* x, int32_t* status, int64_t batch, int n) {
+  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N];
+  __shared__ unsigned char piv_all[kRootStepWarps][N];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t prob = (int64_t)blockIdx.x * kRootStepWarps + wib;
+  if (prob >= batch) return;
+  const bool act = lane < n;
+  T a[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = (act && j < n) ? A[(prob * n + lane) * (int64_t)n + j] : ((j == lane) ? T(1) : T(0));
+  const T rhs = act ? b[prob * n + lane] : T(0);
+  int mycol;
+  T rinv;
+  warp_lu_factor<T, N>(a, mycol, rinv, rowbuf_all[wib], piv_all[wib], lane);
+  const T sol = warp_lu_solve<T, N>(a, mycol, rinv, rhs, piv_all[wib], lane);
+  const bool ok = __all_sync(kFull, !act || t_finite(sol));
+  if (act) x[prob * n + lane] = sol;
+  if (lane == 0 && status) status[prob] = ok ? RES_OK : RES_SINGULAR;
+}
+
 // =============================================================================================== BFGS step
 // state per problem (elements of T):
 //   [M (n*n: H^-1, or H when use_inverse=False) | g (n) | newton (n) | f | alpha | first | terminate | num_accepted | descent result | pad..]
@@ -523,6 +548,30 @@ int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const 
   else
     step_finish_kernel<float><<<grid, 128, 0, st>>>(batch, kRootStateElems, 2, static_cast<const float*>(state), result);
   return check_cuda(cudaGetLastError(), "root_step_finish launch");
+}
+
+int32_t b200opt_lu_solve(int32_t dtype, int64_t batch, int32_t n, const void* A, const void* b, void* x, int32_t* status, void* stream) {
+  if (int e = gstep_check("lu_solve", dtype, batch, n, 32)) return e;
+  if (batch == 0) return 0;
+  if (!A || !b || !x) {
+    set_error("lu_solve: NULL buffer");
+    return B200OPT_EINVAL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((batch + kRootStepWarps - 1) / kRootStepWarps);
+  const int threads = kRootStepWarps * 32;
+#define B200OPT_LU_LAUNCH(T, N) lu_solve_kernel<T, N><<<grid, threads, 0, st>>>(static_cast<const T*>(A), static_cast<const T*>(b), static_cast<T*>(x), status, batch, n)
+  if (dtype == B200OPT_F64) {
+    if (n <= 8) B200OPT_LU_LAUNCH(double, 8);
+    else if (n <= 16) B200OPT_LU_LAUNCH(double, 16);
+    else B200OPT_LU_LAUNCH(double, 32);
+  } else {
+    if (n <= 8) B200OPT_LU_LAUNCH(float, 8);
+    else if (n <= 16) B200OPT_LU_LAUNCH(float, 16);
+    else B200OPT_LU_LAUNCH(float, 32);
+  }
+#undef B200OPT_LU_LAUNCH
+  return check_cuda(cudaGetLastError(), "lu_solve_kernel launch");
 }
 
 int64_t b200opt_bfgs_step_state_size(int32_t dtype, int32_t n) {
