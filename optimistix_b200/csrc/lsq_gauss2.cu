@@ -1,4 +1,62 @@
+#include <stdlib.h>
+
+#include "lsq_kernel_p2.cuh"
 #include "lsq_launch.cuh"
 namespace b200opt {
-int lsq_launch_gauss2(const LsqArgs& a) { return lsq_launch_model<Gauss2>(a); }
+
+// packed-fp32 fast path (lsq_kernel_p2.cuh); everything it does not cover goes to the scalar kernel
+template <class PModel, bool TRUST> static int lsq_launch_p2(const LsqParams<float>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel_p2<PModel, TRUST>;
+  const size_t per_warp = WarpReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)(3 + PModel::NAUX) * p.m_pad;
+  const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
+  if (smem > 227 * 1024) return -1;  // caller falls back
+  static thread_local size_t smem_set = 0, occ_smem = ~size_t(0);
+  static thread_local int blocks_per_sm = 1;
+  if (smem > smem_set) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
+    smem_set = smem;
+  }
+  if (occ_smem != smem) {
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy")) return B200OPT_ECUDA;
+    blocks_per_sm = occ > 0 ? occ : 1;
+    occ_smem = smem;
+  }
+  const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
+  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
+  const int grid = (int)(need < cap ? need : cap);
+  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
+}
+
+int lsq_launch_gauss2(const LsqArgs& a) {
+  static const bool scalar_only = getenv("B200OPT_LSQ_SCALAR") != nullptr;  // A/B switch for profiling
+  const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
+  if (!scalar_only && a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
+      !a.opts->root_near_zero) {
+    LsqParams<float> p;
+    p.y0 = static_cast<const float*>(a.y0);
+    p.shared = static_cast<const float*>(a.shared);
+    p.prob = static_cast<const float*>(a.prob);
+    p.prob_stride = a.prob_stride;
+    p.y_out = static_cast<float*>(a.y_out);
+    p.num_steps = a.num_steps;
+    p.result = a.result;
+    p.step_size_out = static_cast<float*>(a.step_size_out);
+    p.num_accepted = a.num_accepted;
+    p.batch = a.batch;
+    p.m = a.m;
+    p.m_pad = a.m;
+    p.rtol = (float)a.opts->rtol;
+    p.atol = (float)a.opts->atol;
+    p.norm = a.opts->norm;
+    p.max_steps = a.opts->max_steps;
+    p.root_near_zero = 0;
+    p.vec_ok = 1;
+    const int rc = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT ? lsq_launch_p2<Gauss2P2, true>(p, a.stream)
+                                                                  : lsq_launch_p2<Gauss2P2, false>(p, a.stream);
+    if (rc >= 0) return rc;
+  }
+  return lsq_launch_model<Gauss2>(a);
+}
 }  // namespace b200opt

@@ -1,0 +1,256 @@
+// Packed-fp32 variant of the batched LM / GN kernel (lsq_kernel.cuh) for sm_100a.
+//
+// Blackwell issues fp32 FMA / MUL / ADD on register PAIRS (FFMA2 / FMUL2 / FADD2: two lanes of arithmetic per issue slot,
+// `__ffma2_rn` & co.).  The scalar kernel is bound by issue slots, not by the FMA pipe (profiles/README.md: 1505
+// instructions per problem-iteration, pipe 45% busy), so this variant evaluates TWO ROWS of the problem per instruction:
+// lane l owns the row pairs (64 k + 2 l, 64 k + 2 l + 1), which are adjacent in memory, so every shared-memory access
+// is one conflict-free 64-bit access, and the residual, the Jacobian row and the 44 Gram / gradient partial sums are
+// all carried as (even row, odd row) pairs.  The state machine, the replicated 8 x 8 algebra and the results are those
+// of lsq_kernel.cuh; only the order of the floating-point additions inside the row sums differs.
+//
+// exp(-z^2/2) = 2^(t K), K = -log2(e)/2, is evaluated as ex2.approx(hi) * (1 + ln2 * lo) with hi + lo = t K split exactly
+// by one extra FMA (error <= 2 ulp; the hardware ex2 alone would lose |hi| ulp to the rounding of its argument).
+//
+// Used when: fp32, max_norm, no root-finding extra condition, m a multiple of 64, 16-byte aligned rows.
+#pragma once
+#include "lsq_kernel.cuh"
+
+namespace b200opt {
+
+__device__ __forceinline__ float2 p2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(-0.5 * t) for a pair of non-negative t
+__device__ __forceinline__ float2 exp_mhalf2(float2 t) {
+  const float K = -0.72134752044448170368f;  // -log2(e) / 2
+  const float2 hi = mul2(t, p2(K));
+  const float2 nhi = mul2(t, p2(-K));           // == -hi exactly
+  const float2 lo = fma2(t, p2(K), nhi);        // t K - hi, exact
+  const float2 e0 = make_float2(ex2_approx(hi.x), ex2_approx(hi.y));
+  return fma2(mul2(e0, lo), p2(0.69314718055994530942f), e0);
+}
+
+// model family id 1 (two Gaussians + linear baseline), two rows at a time.  Same parameter layout as Gauss2<float>.
+struct Gauss2P2 {
+  static constexpr int N = 8;
+  static constexpr int NAUX = 2;
+  struct Consts {
+    float2 i1, c1, i2, c2;    // z = x * i + c,  c = -mu * i
+    float2 a1, a2, b0, b1;    // amplitudes and baseline (residual)
+    float2 ai1, ai2;          // A * i (Jacobian)
+  };
+  __device__ static __forceinline__ Consts prepare(const float (&y)[N]) {
+    const float i1 = 1.0f / y[2], i2 = 1.0f / y[5];
+    Consts c;
+    c.i1 = p2(i1), c.c1 = p2(-y[1] * i1), c.i2 = p2(i2), c.c2 = p2(-y[4] * i2);
+    c.a1 = p2(y[0]), c.a2 = p2(y[3]), c.b0 = p2(y[6]), c.b1 = p2(y[7]);
+    c.ai1 = p2(y[0] * i1), c.ai2 = p2(y[3] * i2);
+    return c;
+  }
+  __device__ static __forceinline__ float2 residual(const Consts& c, float2 x, float2 d, float2 (&aux)[NAUX]) {
+    const float2 z1 = fma2(x, c.i1, c.c1), z2 = fma2(x, c.i2, c.c2);
+    const float2 e1 = exp_mhalf2(mul2(z1, z1)), e2 = exp_mhalf2(mul2(z2, z2));
+    aux[0] = e1;
+    aux[1] = e2;
+    const float2 base = fma2(c.b1, x, add2(c.b0, make_float2(-d.x, -d.y)));
+    return fma2(c.a1, e1, fma2(c.a2, e2, base));
+  }
+  __device__ static __forceinline__ void jac(const Consts& c, float2 x, const float2 (&aux)[NAUX], float2 (&j)[N]) {
+    const float2 z1 = fma2(x, c.i1, c.c1), z2 = fma2(x, c.i2, c.c2);
+    j[0] = aux[0];
+    j[1] = mul2(mul2(aux[0], z1), c.ai1);
+    j[2] = mul2(j[1], z1);
+    j[3] = aux[1];
+    j[4] = mul2(mul2(aux[1], z2), c.ai2);
+    j[5] = mul2(j[4], z2);
+    j[6] = p2(1.0f);
+    j[7] = x;
+  }
+};
+
+#ifndef LSQ_P2_MINBLOCKS
+#define LSQ_P2_MINBLOCKS 3
+#endif
+template <class PModel, bool TRUST>
+__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_solve_kernel_p2(const LsqParams<float> p) {
+  using T = float;
+  constexpr int N = PModel::N;
+  constexpr int NG = Tri<N>::size;
+  constexpr int NAUX = PModel::NAUX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int m = p.m, mp = p.m_pad;  // m % 64 == 0, m_pad == m
+  constexpr int SCR = WarpReduceLayout<T, NG + N>::elems;
+  T* xs = reinterpret_cast<T*>(smem_raw);
+  T* wbase = xs + mp + (size_t)wib * (SCR + (size_t)(3 + NAUX) * mp);
+  T* scratch = wbase;
+  T* ds = wbase + SCR;
+  T* racc = ds + mp;
+  T* rtry = racc + mp;
+  T* auxs = rtry + mp;
+  const int64_t warp0 = (int64_t)blockIdx.x * kLsqWarpsPerBlock + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kLsqWarpsPerBlock;
+  const T rtol = p.rtol, atol = p.atol;
+  const int npairs = m >> 6;  // row pairs per lane
+
+  for (int i = threadIdx.x; i < mp; i += blockDim.x) xs[i] = p.shared[i];
+  __syncthreads();
+  const float2* xs2 = reinterpret_cast<const float2*>(xs);
+  const float2* ds2 = reinterpret_cast<const float2*>(ds);
+
+  for (int64_t prob = warp0; prob < p.batch; prob += nwarps) {
+    T y[N], ye[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);
+    const T* drow = p.prob + prob * p.prob_stride;
+    for (int i = lane; i < m / 4; i += 32) reinterpret_cast<float4*>(ds)[i] = __ldg(reinterpret_cast<const float4*>(drow) + i);
+    for (int i = lane; i < mp; i += 32) racc[i] = T(0);
+    __syncwarp();
+
+    T G[NG], g[N];
+#pragma unroll
+    for (int a = 0; a < NG; ++a) G[a] = T(0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) g[j] = T(0);
+    T rr = T(0);
+    T delta = T(1);
+    bool first = true, terminate = false;
+    bool yfin = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) yfin = yfin && t_finite(y[j]);
+    int result = yfin ? RES_OK : RES_NONFINITE;
+    int steps = 0, naccept = 0;
+
+    while (!terminate && result == RES_OK && steps < p.max_steps) {
+      bool y_old_finite = true;
+#pragma unroll
+      for (int j = 0; j < N; ++j) y_old_finite = y_old_finite && t_finite(y[j]);
+
+      // ---- residual at the trial point, two rows per instruction (gauss_newton.py:253)
+      const typename PModel::Consts pc = PModel::prepare(ye);
+      float2 part = make_float2(0.f, 0.f);
+      float2* rtry2 = reinterpret_cast<float2*>(rtry);
+      float2* auxs2 = reinterpret_cast<float2*>(auxs);
+#pragma unroll 2
+      for (int k = 0; k < npairs; ++k) {
+        const int idx = k * 32 + lane;
+        float2 aux[NAUX];
+        const float2 r = PModel::residual(pc, xs2[idx], ds2[idx], aux);
+        rtry2[idx] = r;
+#pragma unroll
+        for (int q = 0; q < NAUX; ++q) auxs2[q * (mp >> 1) + idx] = aux[q];
+        part = fma2(r, r, part);
+      }
+      const T rre = warp_sum(part.x + part.y);
+
+      T d[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) d[j] = ye[j] - y[j];
+
+      // ---- search (trust_region.py:86-104 / learning_rate.py:24-35)
+      bool accept = true;
+      if (TRUST) {
+        T lin = T(0), quad = T(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          T gd = T(0);
+#pragma unroll
+          for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
+          quad += d[i] * gd;
+          lin += d[i] * g[i];
+        }
+        const T pred = lin + T(0.5) * quad;
+        const T df = T(0.5) * rre - T(0.5) * rr;
+        accept = (df <= T(0.01) * pred) || first;
+        const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
+        delta *= accept ? (good ? T(3.5) : T(1)) : T(0.25);
+      } else {
+        delta = T(1);
+      }
+
+      if (accept) {
+        bool yconv = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) yconv = yconv && (t_abs(d[j]) < atol + rtol * t_abs(ye[j]));
+        ++naccept;
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[j] = ye[j];
+        rr = rre;
+        // Gram / gradient partials as (even row, odd row) pairs
+        float2 acc2[NG + N];
+#pragma unroll
+        for (int a = 0; a < NG + N; ++a) acc2[a] = make_float2(0.f, 0.f);
+        bool fconv = true;
+        const float2* racc2 = reinterpret_cast<const float2*>(racc);
+#pragma unroll 2
+        for (int k = 0; k < npairs; ++k) {
+          const int idx = k * 32 + lane;
+          float2 aux[NAUX], j[N];
+#pragma unroll
+          for (int q = 0; q < NAUX; ++q) aux[q] = auxs2[q * (mp >> 1) + idx];
+          const float2 re = rtry2[idx], ro = racc2[idx];
+          PModel::jac(pc, xs2[idx], aux, j);
+#pragma unroll
+          for (int a = 0; a < N; ++a) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b) acc2[Tri<N>::at(a, b)] = fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
+            acc2[NG + a] = fma2(j[a], re, acc2[NG + a]);
+          }
+          fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
+        }
+        T acc[NG + N];
+#pragma unroll
+        for (int a = 0; a < NG + N; ++a) acc[a] = acc2[a].x + acc2[a].y;
+        warp_allreduce_array<T, NG + N>(acc, scratch, lane);
+#pragma unroll
+        for (int a = 0; a < NG; ++a) G[a] = acc[a];
+#pragma unroll
+        for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
+        fconv = __all_sync(kFull, fconv);
+        terminate = yconv && fconv;
+        T* t = racc;
+        racc = rtry;
+        rtry = t;
+      } else {
+        terminate = false;
+      }
+
+      // ---- descent (levenberg_marquardt.py:55-57,66-75,132 / gauss_newton.py:64-78,126-127)
+      T lam = T(0);
+      if (TRUST) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
+      T pstep[N];
+      spd_solve<T, N>(G, lam, g, pstep);
+      bool pfin = true;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        pfin = pfin && t_finite(pstep[j]);
+        ye[j] = y[j] - pstep[j];
+      }
+      result = pfin ? RES_OK : RES_SINGULAR;
+      if (!y_old_finite) result = RES_NONFINITE;
+      first = false;
+      ++steps;
+    }
+    if (result == RES_OK && !terminate) result = RES_NL_MAX_STEPS;
+
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (lane == j) p.y_out[prob * N + j] = y[j];
+    if (lane == 0) {
+      p.num_steps[prob] = steps;
+      p.result[prob] = result;
+      if (p.step_size_out) p.step_size_out[prob] = delta;
+      if (p.num_accepted) p.num_accepted[prob] = naccept;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b200opt
