@@ -75,8 +75,18 @@ struct Gauss2P2 {
 };
 
 #ifndef LSQ_P2_MINBLOCKS
-#define LSQ_P2_MINBLOCKS 3
+#define LSQ_P2_MINBLOCKS 4
 #endif
+#ifndef LSQ_P2_UNROLL_R
+#define LSQ_P2_UNROLL_R 4
+#endif
+#ifndef LSQ_P2_UNROLL_J
+#define LSQ_P2_UNROLL_J 4
+#endif
+#ifndef LSQ_P2_SPLIT
+#define LSQ_P2_SPLIT 5  // 0: one sweep with all 44 pair accumulators (88 registers)
+#endif
+constexpr int kUnrollR = LSQ_P2_UNROLL_R, kUnrollJ = LSQ_P2_UNROLL_J;  // (macros are not expanded inside #pragma)
 template <class PModel, bool TRUST>
 __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_solve_kernel_p2(const LsqParams<float> p) {
   using T = float;
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
       float2 part = make_float2(0.f, 0.f);
       float2* rtry2 = reinterpret_cast<float2*>(rtry);
       float2* auxs2 = reinterpret_cast<float2*>(auxs);
-#pragma unroll 2
+#pragma unroll kUnrollR
       for (int k = 0; k < npairs; ++k) {
         const int idx = k * 32 + lane;
         float2 aux[NAUX];
@@ -183,31 +193,49 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 #pragma unroll
         for (int j = 0; j < N; ++j) y[j] = ye[j];
         rr = rre;
-        // Gram / gradient partials as (even row, odd row) pairs
-        float2 acc2[NG + N];
-#pragma unroll
-        for (int a = 0; a < NG + N; ++a) acc2[a] = make_float2(0.f, 0.f);
+        // Gram / gradient partials as (even row, odd row) pairs.  The 44 pair accumulators would cost 88 registers, so
+        // the rows are swept twice, each sweep carrying about half of them (parameters [0, SPLIT) then [SPLIT, N)): the
+        // Jacobian row is recomputed (a handful of packed multiplies), occupancy goes from 12 to 16+ warps per SM.
+        T acc[NG + N];
         bool fconv = true;
         const float2* racc2 = reinterpret_cast<const float2*>(racc);
-#pragma unroll 2
-        for (int k = 0; k < npairs; ++k) {
-          const int idx = k * 32 + lane;
-          float2 aux[NAUX], j[N];
+        constexpr int SPLIT = LSQ_P2_SPLIT;
 #pragma unroll
-          for (int q = 0; q < NAUX; ++q) aux[q] = auxs2[q * (mp >> 1) + idx];
-          const float2 re = rtry2[idx], ro = racc2[idx];
-          PModel::jac(pc, xs2[idx], aux, j);
+        for (int half = 0; half < (SPLIT > 0 ? 2 : 1); ++half) {
+          const int a_lo = (half == 0) ? 0 : SPLIT, a_hi = (half == 0 && SPLIT > 0) ? SPLIT : N;
+          float2 acc2[NG + N];
+#pragma unroll
+          for (int a = 0; a < NG + N; ++a) acc2[a] = make_float2(0.f, 0.f);
+#pragma unroll kUnrollJ
+          for (int k = 0; k < npairs; ++k) {
+            const int idx = k * 32 + lane;
+            float2 aux[NAUX], j[N];
+#pragma unroll
+            for (int q = 0; q < NAUX; ++q) aux[q] = auxs2[q * (mp >> 1) + idx];
+            const float2 re = rtry2[idx];
+            PModel::jac(pc, xs2[idx], aux, j);
+#pragma unroll
+            for (int a = 0; a < N; ++a) {
+              if (a >= a_lo && a < a_hi) {
+#pragma unroll
+                for (int b = 0; b <= a; ++b) acc2[Tri<N>::at(a, b)] = fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
+                acc2[NG + a] = fma2(j[a], re, acc2[NG + a]);
+              }
+            }
+            if (half == 0) {
+              const float2 ro = racc2[idx];
+              fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
+            }
+          }
 #pragma unroll
           for (int a = 0; a < N; ++a) {
+            if (a >= a_lo && a < a_hi) {
 #pragma unroll
-            for (int b = 0; b <= a; ++b) acc2[Tri<N>::at(a, b)] = fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
-            acc2[NG + a] = fma2(j[a], re, acc2[NG + a]);
+              for (int b = 0; b <= a; ++b) acc[Tri<N>::at(a, b)] = acc2[Tri<N>::at(a, b)].x + acc2[Tri<N>::at(a, b)].y;
+              acc[NG + a] = acc2[NG + a].x + acc2[NG + a].y;
+            }
           }
-          fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
         }
-        T acc[NG + N];
-#pragma unroll
-        for (int a = 0; a < NG + N; ++a) acc[a] = acc2[a].x + acc2[a].y;
         warp_allreduce_array<T, NG + N>(acc, scratch, lane);
 #pragma unroll
         for (int a = 0; a < NG; ++a) G[a] = acc[a];
