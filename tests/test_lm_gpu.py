@@ -220,3 +220,50 @@ def test_lm_prefix_state_parity(family):
         checked += int(safe.sum())
         print(f"[prefix {family}] k={k}: {int(safe.sum())} margin-safe problems identical; max rel iterate diff {rel.max():.3g}")
     assert checked > 4000
+
+
+def test_gauss2_packed_fp32_path_matches_scalar_path():
+    """The packed-fp32 (FFMA2, two rows per instruction) kernel and the scalar kernel are the same state machine: run the
+    same fits through both (a row pitch that is not a multiple of 4 floats sends the C entry point to the scalar kernel)."""
+    import ctypes as C
+
+    from optimistix_b200 import _lib
+
+    lib = _lib.load()
+    B, n, m = 4096, 8, 256
+    w = synthetic.gauss2_batch(B, seed=11)
+    y0, x = _cuda(w["y0"]), _cuda(w["x"])
+    d = _cuda(w["d"])
+    pitch = m + 1
+    d_pad = torch.zeros((B, pitch), dtype=torch.float32, device=DEV)
+    d_pad[:, :m] = d
+    opts = _lib.make_options(1e-4, 1e-4, "max", 256)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(data, stride, max_steps=256):
+        o = _lib.make_options(1e-4, 1e-4, "max", max_steps)
+        y = torch.empty_like(y0)
+        steps = torch.empty(B, dtype=torch.int32, device=DEV)
+        res = torch.empty(B, dtype=torch.int32, device=DEV)
+        delta = torch.empty(B, dtype=torch.float32, device=DEV)
+        nacc = torch.empty(B, dtype=torch.int32, device=DEV)
+        _lib.check(lib.b200opt_least_squares(_lib.SOLVER_LM, optx.models.gauss2.model_id, _lib.F32, B, n, m, y0.data_ptr(), x.data_ptr(),
+                                             data.data_ptr(), stride, C.byref(o), y.data_ptr(), steps.data_ptr(), res.data_ptr(),
+                                             delta.data_ptr(), nacc.data_ptr(), st), "least_squares")
+        torch.cuda.synchronize()
+        return y, steps, res, delta, nacc
+
+    del opts
+    # the first iterations: same accept/reject decisions, same radius, iterates equal to fp32 rounding of the row sums
+    for k in (1, 2, 3):
+        yp, sp, rp, dp, ap = run(d, m, k)
+        ys, ss, rs, dss, as_ = run(d_pad, pitch, k)
+        same = (ap == as_) & (dp == dss)
+        assert float(same.float().mean()) >= 0.995
+        assert torch.allclose(yp[same], ys[same], rtol=2e-4, atol=2e-5)
+    yp, sp, rp, dp, ap = run(d, m)
+    ys, ss, rs, dss, as_ = run(d_pad, pitch)
+    assert float((rp == rs).float().mean()) >= 0.999
+    scaled = ((yp - ys).abs() / (1e-4 + 1e-4 * ys.abs())).amax(1)
+    assert float((scaled <= 1.0).float().mean()) >= 0.99
+    assert abs(float(sp.float().mean()) - float(ss.float().mean())) <= 0.02 * float(ss.float().mean())
