@@ -64,8 +64,28 @@ __device__ __forceinline__ int warp_argmax_abs(float v, bool valid) {
 //   a[k]       = multiplier l_ik for k < mycol, U entries for k >= mycol;  rinv = 1 / U[mycol][mycol]
 //   piv[k]     (shared, per warp) = lane that was the pivot of step k
 // `rowbuf` is a per-warp shared line of N elements, 16-byte aligned.
+#ifndef ROOT_FAST_RCP
+#define ROOT_FAST_RCP 1
+#endif
+#ifndef ROOT_STS64
+#define ROOT_STS64 1
+#endif
 __device__ __forceinline__ float t_rcp(float x) { return __frcp_rn(x); }
+#if ROOT_FAST_RCP
+// 1 / pivot: hardware seed (rcp.approx.ftz.f64, relative error 2^-23) + two Newton steps -> ~1 ulp in 5 instructions
+// (the correctly rounded __drcp_rn costs 13 and sits on the critical path of every elimination step).  A zero pivot
+// gives NaN instead of inf; both end as a non-finite solution = `singular`.
+__device__ __forceinline__ double t_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+#else
 __device__ __forceinline__ double t_rcp(double x) { return __drcp_rn(x); }
+#endif
 
 template <typename T, int N>
 __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T* rowbuf, unsigned char* piv, int lane) {
@@ -80,13 +100,23 @@ __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T
     const int k0 = (k / V) * V;  // 128-bit aligned start of the part of the pivot row still in use
     const int p = warp_argmax_abs(a[k], !done);
     if (lane == p) {
+#if ROOT_STS64
+      // element-wise stores: every double already sits in an aligned register pair, a 128-bit store would first have
+      // to move two of them into an aligned quad
+      if (sizeof(T) == 8) {
 #pragma unroll
-      for (int j = k0; j < N; j += V) {
-        Vec v;
-        T* vv = reinterpret_cast<T*>(&v);
+        for (int j = k; j < N; ++j) rowbuf[j] = a[j];
+      } else
+#endif
+      {
 #pragma unroll
-        for (int q = 0; q < V; ++q) vv[q] = a[j + q];
-        *reinterpret_cast<Vec*>(rowbuf + j) = v;
+        for (int j = k0; j < N; j += V) {
+          Vec v;
+          T* vv = reinterpret_cast<T*>(&v);
+#pragma unroll
+          for (int q = 0; q < V; ++q) vv[q] = a[j + q];
+          *reinterpret_cast<Vec*>(rowbuf + j) = v;
+        }
       }
       piv[k] = (unsigned char)p;
     }
@@ -189,8 +219,11 @@ template <class Model, typename T> constexpr size_t root_smem_bytes() {
   return sizeof(T) * Model::kSharedElems + kRootWarpsPerBlock * (sizeof(T) * 2 * Model::N + 32);
 }
 
+#ifndef ROOT_MINBLOCKS
+#define ROOT_MINBLOCKS 4
+#endif
 template <class Model, typename T>
-__global__ void __launch_bounds__(kRootWarpsPerBlock * 32, 3) root_solve_kernel(const RootParams<T> p) {
+__global__ void __launch_bounds__(kRootWarpsPerBlock * 32, ROOT_MINBLOCKS) root_solve_kernel(const RootParams<T> p) {
   constexpr int N = Model::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
