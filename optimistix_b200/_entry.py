@@ -76,14 +76,13 @@ class _Buf:
         t = _torch()
         if self.device:
             return t.empty(shape, dtype=dtype or self.tdtype, device=like.device)
-        # plain pageable outputs: the C host pipeline bounces D2H through its own cached page-locked buffers
-        return np.empty(shape, dtype=dtype or self.ndtype)
+        return _host_empty(shape, dtype or self.ndtype)
 
     def empty_i32(self, shape, like):
         t = _torch()
         if self.device:
             return t.empty(shape, dtype=t.int32, device=like.device)
-        return np.empty(shape, dtype=np.int32)
+        return _host_empty(shape, np.int32)
 
     @staticmethod
     def ptr(x):
@@ -92,6 +91,20 @@ class _Buf:
         if _is_torch(x):
             return x.data_ptr()
         return x.ctypes.data
+
+
+def _host_empty(shape, dtype):
+    """Host output / staging array.  Page-locked through torch's caching host allocator when a CUDA device is present:
+    the D2H copies of the C host pipeline then land directly in it (no bounce buffer, no first-touch page faults on a
+    fresh pageable array - those cost more than the solve itself for the small-problem workloads)."""
+    t = _torch()
+    if t.cuda.is_available():
+        try:
+            tdt = {np.dtype(np.float32): t.float32, np.dtype(np.float64): t.float64, np.dtype(np.int32): t.int32}[np.dtype(dtype)]
+            return t.empty(shape, dtype=tdt, pin_memory=True).numpy()
+        except Exception:  # noqa: BLE001 - out of lockable memory: a pageable array works too (the pipeline bounces)
+            pass
+    return np.empty(shape, dtype=dtype)
 
 
 def _prepare_y0(y0):
@@ -331,10 +344,13 @@ def _pack_root_args(fn, a, buf, dev, B, n, single):
         prob[:, n] = dt
         prob[:, n + 1] = 0
     else:
+        t = _torch()
         shared = np.concatenate([A.reshape(-1), Bm.reshape(-1)])
-        prob = np.zeros((B, stride), dtype=buf.ndtype)
-        prob[:, :n] = y_prev
-        prob[:, n] = dt
+        prob = _host_empty((B, stride), buf.ndtype)
+        pt = t.from_numpy(prob)  # torch's copy kernels are multi-threaded; numpy slice assignment is not
+        pt[:, :n].copy_(t.from_numpy(y_prev))
+        pt[:, n].copy_(t.from_numpy(dt))
+        pt[:, n + 1].zero_()
     return shared, prob, stride
 
 
