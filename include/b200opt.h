@@ -237,6 +237,13 @@ int32_t b200opt_gn_gram_linear(const float* J, const float* y, const float* d, c
  * the same buffer that was given to b200opt_gn_gram. */
 int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float* p_out, int32_t* status_out, void* workspace,
                          void* stream);
+/* Multi-rank form: `parts` holds the ALL-GATHERED row-shard partials, nparts blocks of part_stride >= n*n + n + 2 floats,
+ * each [G | g | r^T r | f-statistic (IEEE bits of a non-negative float, as written by b200opt_gn_gram_linear)].  The
+ * kernel sums them in rank order in fp64 (bit-identical on every rank) before factorising, so one all-gather replaces
+ * the sum all-reduce of the Gram and the max all-reduce of the termination statistic.  summary_out (optional, [2]):
+ * total r^T r and the maximum f-statistic.  nparts == 1 needs no f-statistic slot unless summary_out is given. */
+int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda,
+                               float* p_out, int32_t* status_out, float* summary_out, void* workspace, void* stream);
 /* r = J y - d for the "linear_rows" family (one coalesced pass over the row shard). If r_old is not NULL the
  * f-space half of cauchy_termination (optimistix/_misc.py:306-309) is fused in: *fmax_bits (device, caller-zeroed)
  * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */

@@ -5,8 +5,10 @@ Each rank holds a contiguous shard of the rows of J (and of d); every rank holds
     G,g,rr = J^T J, J^T r, r^T r                } tile feeds the tcgen05 tensor cores (fp32 accumulate in TMEM) and the
                                                   CUDA-core residual / J^T r / f-test statistic at the same time
                                                   (unfused pair: b200opt_linear_residual + b200opt_gn_gram)
-    all-reduce [G | g | rr] (sum) and the f-test statistic (max) over the ranks   -- the ONLY exchange: n^2+n+2 floats
-    p      = G^-1 g                             b200opt_gn_solve (fp64 Cholesky, identical on every rank)
+    all-gather [G | g | rr | f-test statistic] over the ranks      -- the ONLY exchange: n^2+n+2 floats per rank
+    p      = G^-1 g                             b200opt_gn_solve_parts: sums the gathered partials in rank order in fp64
+                                                  (sum of G, g, rr; max of the statistic), then fp64 Cholesky; every rank
+                                                  computes bit-identical values, so no second collective is needed
     y, y_eval = y_eval, y_eval - p
 which is AbstractGaussNewton.step with search = LearningRate(1.0) (always accept) and descent = NewtonDescent
 (optimistix/_solver/gauss_newton.py:243-334, :64-78, learning_rate.py:24-35) under the driver of
@@ -23,6 +25,7 @@ from . import _lib
 from ._solution import RESULTS, Solution
 
 N = 256
+OUT_FLOATS = N * N + N + 2  # [G | g | rr | f-stat bits]: one rank's contribution to the normal equations
 
 
 class CudaOps:
@@ -67,6 +70,13 @@ class CudaOps:
                                              self._stream()), "b200opt_gn_solve")
         self.launches += 1
 
+    def solve_parts(self, parts, nparts, stride, lam, p, status, summary):
+        """parts: the all-gathered [G | g | rr | f-stat] blocks of every rank (or this rank's own block, nparts = 1)."""
+        _lib.check(self.lib.b200opt_gn_solve_parts(parts.data_ptr(), int(nparts), int(stride), N, float(lam), p.data_ptr(),
+                                                   status.data_ptr(), summary.data_ptr(), self.ws.data_ptr(), self._stream()),
+                   "b200opt_gn_solve_parts")
+        self.launches += 1
+
 
 def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None, fused=True):
     """Solve min_y |J y - d|^2 with this rank's row shard (J [m_local, 256] fp32, d [m_local]); returns a Solution.
@@ -96,10 +106,13 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     y_eval = y.clone()
     r_old = torch.zeros(m_local, dtype=torch.float32, device=dev)  # gauss_newton.py:229-230: zero-filled f_info
     r_new = torch.empty_like(r_old)
-    out = torch.empty(N * N + N + 1, dtype=torch.float32, device=dev)
+    out = torch.empty(OUT_FLOATS, dtype=torch.float32, device=dev)  # [G | g | rr | f-stat]: what one rank contributes
+    fmax = out[N * N + N + 1:].view(torch.int32)  # IEEE bits of a non-negative float: integer max == float max
+    world = dist.get_world_size(group) if distributed else 1
+    gathered = torch.empty(world * OUT_FLOATS, dtype=torch.float32, device=dev) if distributed else out
+    summary = torch.zeros(2, dtype=torch.float32, device=dev)  # total r^T r, max f-stat
     p = torch.empty(N, dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    fmax = torch.zeros(1, dtype=torch.int32, device=dev)  # IEEE bits of a non-negative float: integer max == float max
     result = RESULTS.successful if bool(torch.isfinite(y).all()) else RESULTS.nonfinite  # _iterate.py:216-219
     terminate = False
     steps = 0
@@ -111,14 +124,12 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
             ops.residual(J, y_eval, d, r_new, r_old, rtol, atol, fmax)  # gauss_newton.py:253 + f-space half of :280-288
             ops.gram(J, r_new, out)
         if distributed:
-            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(fmax, op=dist.ReduceOp.MAX, group=group)
+            dist.all_gather_into_tensor(gathered, out, group=group)  # the only exchange of the iteration
+        ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)  # NewtonDescent.query: newton = G^-1 g
         y_diff = y_eval - y
         y_conv = bool(((y_diff.abs() / (atol + rtol * y_eval.abs())).max() < 1).item())  # _misc.py:306-308
-        f_stat = fmax.view(torch.float32)
-        f_conv = bool((f_stat < 1).item())  # NaN compares false, like jnp.max
+        f_conv = bool((summary[1] < 1).item())  # NaN compares false, like jnp.max
         terminate = y_conv and f_conv  # LearningRate always accepts (learning_rate.py:24-35)
-        ops.solve(out, 0.0, p, status)  # NewtonDescent.query: newton = G^-1 g
         y = y_eval
         y_eval = y - p  # gauss_newton.py:126-127 with step_size 1
         r_old, r_new = r_new, r_old
@@ -130,6 +141,6 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
         result = RESULTS.nonlinear_max_steps_reached  # _iterate.py:253-257
     if throw and result != RESULTS.successful:
         raise RuntimeError(f"{RESULTS.name(result)}: {RESULTS[result]}")
-    stats = {"num_steps": steps, "max_steps": max_steps, "loss": 0.5 * float(out[N * N + N].item()),
+    stats = {"num_steps": steps, "max_steps": max_steps, "loss": 0.5 * float(summary[0].item()),
              "gpu_launches": getattr(ops, "launches", None)}
     return Solution(value=y, result=result, aux=None, stats=stats, state={"gram": out, "residual": r_old})

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "b200opt_gn_gram": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_gram_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_solve": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp, _vp]),
+    "b200opt_gn_solve_parts": (_i32, [_vp, _i32, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_linear_residual": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, C.c_float, C.c_float, _vp, _vp]),
 }
 

@@ -22,8 +22,11 @@ constexpr int SOLVE_PW = 32;                 // panel width
 constexpr int SOLVE_LD = SOLVE_PW + 1;       // row pitch of the panel buffers (odd: conflict-free row and column access)
 constexpr size_t SOLVE_SMEM = (size_t)(256 * SOLVE_LD + 3 * 256 + 3 * SOLVE_PW + 8) * sizeof(double);
 
-__global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out, int n, double lambda, double* A, float* p_out,
-                                                           int32_t* status) {
+// `parts` row-shard partials [G | g | rr | f-statistic bits] (stride `part_stride` floats) are summed here, in rank order
+// and in fp64, so that after ONE all-gather every rank holds bit-identical normal equations (and the max of the
+// f-space termination statistic) without a second collective.
+__global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out, int nparts, int64_t part_stride, int n, double lambda,
+                                                           double* A, float* p_out, int32_t* status, float* summary) {
   extern __shared__ double sm[];
   double* Lp = sm;                          // [256][SOLVE_LD] finished panel of the factor (rows c0..n-1 used)
   double* z = Lp + 256 * SOLVE_LD;          // [256] right-hand side -> L^-1 g
@@ -35,9 +38,27 @@ __global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out
   // lower triangle of G + lambda I in fp64
   for (int e = tid; e < n * n; e += nt) {
     const int i = e / n, j = e - i * n;
-    if (j <= i) A[e] = (double)gram_out[e] + (i == j ? lambda : 0.0);
+    if (j <= i) {
+      double acc = 0.0;
+      for (int q = 0; q < nparts; ++q) acc += (double)gram_out[q * part_stride + e];
+      A[e] = acc + (i == j ? lambda : 0.0);
+    }
   }
-  for (int i = tid; i < n; i += nt) z[i] = (double)gram_out[n * n + i];
+  for (int i = tid; i < n; i += nt) {
+    double acc = 0.0;
+    for (int q = 0; q < nparts; ++q) acc += (double)gram_out[q * part_stride + n * n + i];
+    z[i] = acc;
+  }
+  if (summary && tid == 0) {
+    double rr = 0.0;
+    float fs = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      rr += (double)gram_out[q * part_stride + n * n + n];
+      fs = nan_max(fs, gram_out[q * part_stride + n * n + n + 1]);
+    }
+    summary[0] = (float)rr;
+    summary[1] = fs;
+  }
   __syncthreads();
 
   const int npanels = (n + SOLVE_PW - 1) / SOLVE_PW;
@@ -227,8 +248,14 @@ extern "C" {
 
 int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float* p_out, int32_t* status_out, void* workspace,
                          void* stream) {
-  if (n < 1 || n > 256 || !gram_out || !p_out || !workspace) {
-    set_error("gn_solve: need 1 <= n <= 256 and non-NULL buffers");
+  return b200opt_gn_solve_parts(gram_out, 1, 0, n, lambda, p_out, status_out, nullptr, workspace, stream);
+}
+
+int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda, float* p_out,
+                               int32_t* status_out, float* summary_out, void* workspace, void* stream) {
+  const float* gram_out = parts;
+  if (n < 1 || n > 256 || !gram_out || !p_out || !workspace || nparts < 1 || (nparts > 1 && part_stride < (int64_t)n * n + n + 2)) {
+    set_error("gn_solve: need 1 <= n <= 256, nparts >= 1, part_stride >= n*n + n + 2 and non-NULL buffers");
     return B200OPT_EINVAL;
   }
   // the fp64 scratch sits after the per-CTA partials of b200opt_gn_gram in the same workspace
@@ -240,7 +267,8 @@ int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float*
       return B200OPT_ECUDA;
     attr_set = true;
   }
-  gn_solve_kernel<<<1, 1024, SOLVE_SMEM, static_cast<cudaStream_t>(stream)>>>(gram_out, n, lambda, A, p_out, status_out);
+  gn_solve_kernel<<<1, 1024, SOLVE_SMEM, static_cast<cudaStream_t>(stream)>>>(gram_out, nparts, part_stride, n, lambda, A, p_out, status_out,
+                                                                              summary_out);
   return check_cuda(cudaGetLastError(), "gn_solve_kernel launch");
 }
 

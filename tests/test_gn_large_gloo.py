@@ -23,7 +23,7 @@ class NumpyOps:
         r = J @ y - d
         stat = ((r - r_old).abs() / (atol + rtol * r.abs())).max() if r_old is not None else torch.zeros(())
         r_out.copy_(r)
-        fmax.view(torch.float32)[0] = stat
+        fmax.view(torch.float32)[0] = stat  # `fmax` is a view of the last slot of this rank's block
 
     def gram(self, J, r, out):
         Jd = J.double()
@@ -31,11 +31,15 @@ class NumpyOps:
         out[N * N : N * N + N] = (Jd.T @ r.double()).float()
         out[N * N + N] = float(r.double() @ r.double())
 
-    def solve(self, out, lam, p, status):
-        G = out[: N * N].view(N, N).double() + lam * torch.eye(N, dtype=torch.float64)
-        x = torch.linalg.solve(G, out[N * N : N * N + N].double())
+    def solve_parts(self, parts, nparts, stride, lam, p, status, summary):
+        blocks = parts.view(nparts, stride).double()
+        tot = blocks.sum(0)  # rank order, fp64 (what b200opt_gn_solve_parts does)
+        G = tot[: N * N].view(N, N) + lam * torch.eye(N, dtype=torch.float64)
+        x = torch.linalg.solve(G, tot[N * N : N * N + N])
         p.copy_(x.float())
         status[0] = 0 if bool(torch.isfinite(x).all()) else 2
+        summary[0] = float(tot[N * N + N])
+        summary[1] = parts.view(nparts, stride)[:, N * N + N + 1].max()
 
 
 def _free_port():

@@ -160,3 +160,38 @@ def test_gn_solve_and_residual_kernels():
     out2 = torch.zeros_like(out)
     _lib.check(lib.b200opt_gn_solve(out2.data_ptr(), N, 0.0, p.data_ptr(), status.data_ptr(), ws.data_ptr(), st), "gn_solve")
     assert int(status.item()) == optx.RESULTS.singular
+
+
+def test_gn_solve_parts_sums_gathered_partials():
+    """b200opt_gn_solve_parts: the all-gathered row-shard partials are summed in rank order (fp64) before the Cholesky."""
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator().manual_seed(5)
+    stride = N * N + N + 2
+    parts = torch.zeros(3, stride, dtype=torch.float32)
+    G_tot = torch.zeros(N, N, dtype=torch.float64)
+    for q in range(3):
+        A = torch.randn(N, N, dtype=torch.float64, generator=gen)
+        Gq = (A @ A.T + N * torch.eye(N, dtype=torch.float64)).float()
+        parts[q, : N * N] = Gq.reshape(-1)
+        parts[q, N * N : N * N + N] = torch.randn(N, generator=gen)
+        parts[q, N * N + N] = float(q + 1)
+        parts[q, N * N + N + 1] = [0.25, 3.5, 0.75][q]
+        G_tot += Gq.double()
+    g_tot = parts[:, N * N : N * N + N].double().sum(0)
+    parts = parts.to(DEV)
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    p = torch.empty(N, dtype=torch.float32, device=DEV)
+    status = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    summary = torch.zeros(2, dtype=torch.float32, device=DEV)
+    _lib.check(lib.b200opt_gn_solve_parts(parts.data_ptr(), 3, stride, N, 0.0, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
+                                          ws.data_ptr(), st), "gn_solve_parts")
+    p_ref = torch.linalg.solve(G_tot, g_tot)
+    assert int(status.item()) == 0
+    assert torch.allclose(p.cpu().double(), p_ref, rtol=1e-5, atol=1e-7)
+    assert summary.cpu().tolist() == [6.0, 3.5]
+    # NaN statistic on one rank propagates (jnp.max semantics)
+    parts[1, N * N + N + 1] = float("nan")
+    _lib.check(lib.b200opt_gn_solve_parts(parts.data_ptr(), 3, stride, N, 0.0, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
+                                          ws.data_ptr(), st), "gn_solve_parts")
+    assert torch.isnan(summary[1])
