@@ -69,8 +69,11 @@ template <typename T> struct Rosenbrock {
 
 template <typename T> __device__ __forceinline__ T warp_dot2(T a0, T a1, T b0, T b1) { return warp_sum(a0 * b0 + a1 * b1); }
 
+#ifndef BFGS_MINBLOCKS
+#define BFGS_MINBLOCKS 4
+#endif
 template <class Model, typename T>
-__global__ void __launch_bounds__(kBfgsThreads, 3) bfgs_solve_kernel(const MinParams<T> p) {
+__global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kernel(const MinParams<T> p) {
   constexpr int N = kBfgsN;
   __shared__ __align__(16) T vq[4][N], vs[4][N], vg[4][N];  // per-warp private copies: q, s, new gradient
   __shared__ __align__(16) T xhq[2][N], xnt[2][N];          // cross-warp exchange, double buffered
