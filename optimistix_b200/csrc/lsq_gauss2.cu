@@ -5,8 +5,8 @@
 namespace b200opt {
 
 // packed-fp32 fast path (lsq_kernel_p2.cuh); everything it does not cover goes to the scalar kernel
-template <class PModel, bool TRUST> static int lsq_launch_p2(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2<PModel, TRUST>;
+template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const LsqParams<float>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel_p2<PModel, TRUST, NPAIRS>;
   const size_t per_warp = WarpReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)(3 + PModel::NAUX) * p.m_pad;
   const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
   if (smem > 227 * 1024) return -1;  // caller falls back
@@ -53,8 +53,10 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.max_steps = a.opts->max_steps;
     p.root_near_zero = 0;
     p.vec_ok = 1;
-    const int rc = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT ? lsq_launch_p2<Gauss2P2, true>(p, a.stream)
-                                                                  : lsq_launch_p2<Gauss2P2, false>(p, a.stream);
+    const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
+    int rc;
+    if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
+    else rc = lm ? lsq_launch_p2<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 0>(p, a.stream);
     if (rc >= 0) return rc;
   }
   return lsq_launch_model<Gauss2>(a);

@@ -87,7 +87,9 @@ struct Gauss2P2 {
 #define LSQ_P2_SPLIT 5  // 0: one sweep with all 44 pair accumulators (88 registers)
 #endif
 constexpr int kUnrollR = LSQ_P2_UNROLL_R, kUnrollJ = LSQ_P2_UNROLL_J;  // (macros are not expanded inside #pragma)
-template <class PModel, bool TRUST>
+// NPAIRS > 0: the number of row pairs per lane (m / 64) is a compile-time constant: both row sweeps are fully unrolled and
+// the accumulators are initialised by the first pair instead of being zeroed.  NPAIRS == 0: any m % 64 == 0.
+template <class PModel, bool TRUST, int NPAIRS>
 __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_solve_kernel_p2(const LsqParams<float> p) {
   using T = float;
   constexpr int N = PModel::N;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
   const int64_t warp0 = (int64_t)blockIdx.x * kLsqWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kLsqWarpsPerBlock;
   const T rtol = p.rtol, atol = p.atol;
-  const int npairs = m >> 6;  // row pairs per lane
+  const int npairs = NPAIRS > 0 ? NPAIRS : (m >> 6);  // row pairs per lane
 
   for (int i = threadIdx.x; i < mp; i += blockDim.x) xs[i] = p.shared[i];
   __syncthreads();
@@ -148,8 +150,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
       float2 part = make_float2(0.f, 0.f);
       float2* rtry2 = reinterpret_cast<float2*>(rtry);
       float2* auxs2 = reinterpret_cast<float2*>(auxs);
-#pragma unroll kUnrollR
-      for (int k = 0; k < npairs; ++k) {
+      auto res_pair = [&](int k) {
         const int idx = k * 32 + lane;
         float2 aux[NAUX];
         const float2 r = PModel::residual(pc, xs2[idx], ds2[idx], aux);
@@ -157,6 +158,13 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 #pragma unroll
         for (int q = 0; q < NAUX; ++q) auxs2[q * (mp >> 1) + idx] = aux[q];
         part = fma2(r, r, part);
+      };
+      if (NPAIRS > 0) {
+#pragma unroll
+        for (int k = 0; k < (NPAIRS > 0 ? NPAIRS : 1); ++k) res_pair(k);
+      } else {
+#pragma unroll kUnrollR
+        for (int k = 0; k < npairs; ++k) res_pair(k);
       }
       const T rre = warp_sum(part.x + part.y);
 
@@ -204,10 +212,11 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
         for (int half = 0; half < (SPLIT > 0 ? 2 : 1); ++half) {
           const int a_lo = (half == 0) ? 0 : SPLIT, a_hi = (half == 0 && SPLIT > 0) ? SPLIT : N;
           float2 acc2[NG + N];
+          if (NPAIRS == 0) {
 #pragma unroll
-          for (int a = 0; a < NG + N; ++a) acc2[a] = make_float2(0.f, 0.f);
-#pragma unroll kUnrollJ
-          for (int k = 0; k < npairs; ++k) {
+            for (int a = 0; a < NG + N; ++a) acc2[a] = make_float2(0.f, 0.f);
+          }
+          auto jac_pair = [&](int k, bool init) {
             const int idx = k * 32 + lane;
             float2 aux[NAUX], j[N];
 #pragma unroll
@@ -218,14 +227,22 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
             for (int a = 0; a < N; ++a) {
               if (a >= a_lo && a < a_hi) {
 #pragma unroll
-                for (int b = 0; b <= a; ++b) acc2[Tri<N>::at(a, b)] = fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
-                acc2[NG + a] = fma2(j[a], re, acc2[NG + a]);
+                for (int b = 0; b <= a; ++b)
+                  acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
+                acc2[NG + a] = init ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
               }
             }
             if (half == 0) {
               const float2 ro = racc2[idx];
               fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
             }
+          };
+          if (NPAIRS > 0) {
+#pragma unroll
+            for (int k = 0; k < (NPAIRS > 0 ? NPAIRS : 1); ++k) jac_pair(k, k == 0);
+          } else {
+#pragma unroll kUnrollJ
+            for (int k = 0; k < npairs; ++k) jac_pair(k, false);
           }
 #pragma unroll
           for (int a = 0; a < N; ++a) {
