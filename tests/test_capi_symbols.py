@@ -51,3 +51,32 @@ def test_bad_arguments_fail_loudly(lib):
     assert code == -1 and b"dtype" in lib.b200opt_last_error()
     # batch == 0 is a valid no-op (empty input) and touches no pointer
     assert lib.b200opt_least_squares(0, 0, 1, 0, 3, 64, None, None, None, 64, C.byref(o), None, None, None, None, None, None) == 0
+
+
+def test_xla_shim_uses_only_declared_entry_points_with_matching_arity():
+    """integration/b200opt_xla.cc (the jax.ffi binding a maintainer would build; not compilable here) must call only functions the
+    header declares, with the declared number of arguments."""
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "integration", "b200opt_xla.cc")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+
+    def arity(text, name):
+        i = text.index(name + "(") + len(name) + 1
+        depth, n, seen = 1, 0, False
+        while depth:
+            c = text[i]
+            depth += c == "("
+            depth -= c == ")"
+            if depth == 1 and c == ",":
+                n += 1
+            seen = seen or not c.isspace()
+            i += 1
+        return n + 1 if seen and text[text.index(name + "(") + len(name) + 1 : i - 1].strip() not in ("", "void") else 0
+
+    used = sorted(set(re.findall(r"\b(b200opt_[a-z0-9_]+)\s*\(", shim)))
+    assert {"b200opt_least_squares", "b200opt_lsq_step", "b200opt_root_step", "b200opt_bfgs_step", "b200opt_lu_solve"} <= set(used)
+    for name in used:
+        assert name in _declared(), name
+        assert arity(shim, name) == arity(hdr, name), (name, arity(shim, name), arity(hdr, name))
