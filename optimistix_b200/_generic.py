@@ -77,6 +77,8 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
     if n > 16:
         raise NotImplementedError("generic least-squares step kernel supports n <= 16 parameters (register-resident Gram)")
     dtype_code = _lib.F32 if y0.dtype == t.float32 else _lib.F64
+    if B == 0:
+        return _empty_solution(Y0, max_steps)
     jac_mode = (options or {}).get("jac", "fwd")
     rj = _batched_r_and_J(fn, _detached(args), args_in_dims, jac_mode, single)
     r, J = rj(Y0)
@@ -144,6 +146,13 @@ def _prep_y0(y0):
     return Y0, single, (_lib.F32 if y0.dtype == t.float32 else _lib.F64)
 
 
+def _empty_solution(Y0, max_steps):
+    """A batch of zero problems: nothing to launch (and torch.func.vmap refuses an empty batch axis)."""
+    t = _torch()
+    z = t.zeros((0,), dtype=t.int32, device=Y0.device)
+    return Solution(value=Y0.clone(), result=z, aux=None, stats={"num_steps": z.clone(), "max_steps": max_steps}, state=None)
+
+
 def _throw_if_failed(res):
     rh = res.cpu().numpy()
     bad = np.flatnonzero(rh != RESULTS.successful)
@@ -185,6 +194,8 @@ def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_i
     if n > 32:
         raise NotImplementedError("generic Newton/Chord step kernel supports n <= 32 unknowns (row-per-lane LU)")
     dev = Y0.device
+    if B == 0:
+        return _empty_solution(Y0, max_steps)
 
     def one(y, a):
         out = fn(y, a).reshape(-1)
@@ -256,6 +267,8 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
     Y0, single, dtype_code = _prep_y0(y0)
     B, n = Y0.shape
     dev = Y0.device
+    if B == 0:
+        return _empty_solution(Y0, max_steps)
 
     def one(y, a):
         out = fn(y, a)

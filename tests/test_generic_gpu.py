@@ -282,3 +282,45 @@ def test_compat_minimize():
         optx.compat.minimize(beale, x0, (1.5, 2.25, 2.625), method="bfgs", options=dict(gtol=1.0))
     with pytest.raises(ValueError):
         optx.compat.minimize(beale, x0[None], (1.5, 2.25, 2.625), method="bfgs")
+
+
+# ---- shapes and dtypes of the generic paths: batches with per-problem args, fp32, one unknown, empty batch
+def test_generic_batched_per_problem_args_and_fp32():
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B = 37
+    a = 1.0 + torch.rand(B, generator=g, device=DEV, dtype=torch.float64)
+    # root: y^3 = a (n = 1), minimise: (y0 - a)^2 + 2 (y1 + a)^2 (n = 2), batched over a
+    sol = optx.root_find(lambda y, a_: y**3 - a_, optx.Newton(1e-10, 1e-10), torch.ones(B, 1, dtype=torch.float64, device=DEV), a,
+                         args_in_dims=0)
+    assert torch.allclose(sol.value[:, 0], a ** (1 / 3), rtol=1e-9)
+    assert sol.stats["num_steps"].shape == (B,) and bool((sol.result == 0).all())
+    sol = optx.minimise(lambda y, a_: (y[0] - a_) ** 2 + 2 * (y[1] + a_) ** 2, optx.BFGS(1e-9, 1e-9),
+                        torch.zeros(B, 2, dtype=torch.float64, device=DEV), a, args_in_dims=0)
+    assert torch.allclose(sol.value, torch.stack([a, -a], 1), rtol=1e-6, atol=1e-8)
+    # fp32 end to end
+    a32 = a.float()
+    sol = optx.root_find(lambda y, a_: y**3 - a_, optx.Newton(1e-5, 1e-5), torch.ones(B, 1, dtype=torch.float32, device=DEV), a32,
+                         args_in_dims=0)
+    assert sol.value.dtype == torch.float32 and torch.allclose(sol.value[:, 0], a32 ** (1 / 3), rtol=1e-4)
+    sol = optx.minimise(lambda y, a_: (y[0] - a_) ** 2 + 2 * (y[1] + a_) ** 2, optx.DFP(1e-4, 1e-4, use_inverse=False),
+                        torch.zeros(B, 2, dtype=torch.float32, device=DEV), a32, args_in_dims=0)
+    assert sol.value.dtype == torch.float32 and torch.allclose(sol.value, torch.stack([a32, -a32], 1), rtol=1e-3, atol=1e-4)
+
+
+def test_generic_empty_batch():
+    e = torch.zeros(0, 3, dtype=torch.float64, device=DEV)
+    for sol in (optx.root_find(lambda y, _: y - 1.0, optx.Newton(1e-8, 1e-8), e),
+                optx.minimise(lambda y, _: (y * y).sum(), optx.BFGS(1e-8, 1e-8), e),
+                optx.least_squares(lambda y, _: y - 1.0, optx.LevenbergMarquardt(1e-8, 1e-8), e)):
+        assert sol.value.shape == (0, 3) and sol.result.shape == (0,) and sol.stats["num_steps"].shape == (0,)
+
+
+def test_generic_limits_are_reported():
+    with pytest.raises(NotImplementedError):
+        optx.root_find(lambda y, _: y, optx.Newton(1e-8, 1e-8), torch.zeros(33, dtype=torch.float64, device=DEV))
+    with pytest.raises(NotImplementedError):
+        optx.minimise(lambda y, _: (y * y).sum(), optx.BFGS(1e-8, 1e-8, use_inverse=False), torch.zeros(65, dtype=torch.float64, device=DEV))
+    with pytest.raises(ValueError):
+        optx.minimise(lambda y, _: y, optx.BFGS(1e-8, 1e-8), torch.zeros(2, dtype=torch.float64, device=DEV))  # not a scalar
+    sol = optx.minimise(lambda y, _: ((y - 2.0) ** 2).sum(), optx.BFGS(1e-8, 1e-8), torch.zeros(200, dtype=torch.float64, device=DEV))
+    assert torch.allclose(sol.value, torch.full((200,), 2.0, dtype=torch.float64, device=DEV), atol=1e-6)  # n > 64: H^-1 in HBM
