@@ -155,6 +155,20 @@ def _finish(buf, single, throw, value, num_steps, result, max_steps, extra_stats
     return Solution(value=value, result=result, aux=None, stats=stats, state=state)
 
 
+def _attach_registered(adjoint, kind, model, a, y_out, buf):
+    """ImplicitAdjoint for a registered family: the persistent kernel produced y_out; its gradient w.r.t. the tensors in
+    `args` follows from the family's torch evaluator (`RegisteredModel.torch_fn`) by the implicit function theorem
+    (_adjoint.py).  Device tensors only; y0 never carries a gradient (the solution does not depend on it, _ad.py)."""
+    if not buf.device or model.torch_fn is None:
+        return y_out
+    from ._adjoint import attach_if_needed, needs_grad
+
+    if not needs_grad(a):
+        return y_out
+    in_dims = {k: (None if i < model.n_shared else 0) for i, k in enumerate(model.arg_names)}
+    return attach_if_needed(adjoint, kind, lambda y, ad: model.torch_fn(y, ad), y_out, a, in_dims)
+
+
 def _stream_ptr(buf, like):
     if not buf.device:
         return None
@@ -249,6 +263,7 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
                                               buf.ptr(shared), m, buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out),
                                               buf.ptr(steps), buf.ptr(res), int(chunk))
     _lib.check(code, "b200opt_least_squares")
+    y_out = _attach_registered(adjoint, "root" if _root_near_zero else "lstsq", fn, a, y_out, buf)
     return _finish(buf, single, throw, y_out, steps, res, max_steps, extra)
 
 
@@ -313,6 +328,7 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
                                           int(shared.shape[0]), buf.ptr(prob), stride, C.byref(opts), buf.ptr(y_out),
                                           buf.ptr(steps), buf.ptr(res), int(chunk))
     _lib.check(code, "b200opt_root_find")
+    y_out = _attach_registered(adjoint, "root", fn, a, y_out, buf)
     return _finish(buf, single, throw, y_out, steps, res, max_steps)
 
 

@@ -111,3 +111,43 @@ def test_recursive_checkpoint_adjoint_is_refused():
     a = torch.tensor([2.0], requires_grad=True, **f64)
     with pytest.raises(NotImplementedError):
         optx.root_find(lambda y, a_: y * y - a_, optx.Newton(1e-10, 1e-10), torch.ones(1, **f64), a, adjoint=optx.RecursiveCheckpointAdjoint())
+
+
+def test_registered_family_gradient_matches_generic_path():
+    """exp_decay through the persistent kernel: d(decay rate)/d(data) by ImplicitAdjoint == the generic path's gradient."""
+    from optimistix_b200 import synthetic
+
+    w = synthetic.exp_decay_batch(32)
+    t = torch.as_tensor(w["t"], device=DEV)
+    y0 = torch.as_tensor(w["y0"], device=DEV)
+    d1 = torch.as_tensor(w["d"], device=DEV).clone().requires_grad_(True)
+    d2 = d1.detach().clone().requires_grad_(True)
+    reg = optx.least_squares(optx.models.exp_decay, optx.LevenbergMarquardt(1e-12, 1e-12), y0, (t, d1), throw=False)
+    (reg.value[:, 1] * torch.arange(32, **f64)).sum().backward()
+
+    def fn(y, a):
+        tt, dd = a
+        return y[0] * torch.exp(-y[1] * tt) + y[2] - dd
+
+    gen = optx.least_squares(fn, optx.LevenbergMarquardt(1e-12, 1e-12), y0, (t, d2), args_in_dims=(None, 0), throw=False)
+    (gen.value[:, 1] * torch.arange(32, **f64)).sum().backward()
+    assert torch.allclose(reg.value, gen.value, rtol=1e-8, atol=1e-10)
+    assert torch.allclose(d1.grad, d2.grad, rtol=1e-6, atol=1e-9)
+    assert float(d1.grad.abs().sum()) > 0
+
+
+def test_registered_root_family_gradient_vs_finite_differences():
+    """implicit_euler (BASELINE configs[2] family): d y_new / d dt through the persistent Newton kernel."""
+    from optimistix_b200 import synthetic
+
+    w = synthetic.implicit_euler_batch(8)
+    A, Bm, yp, y0 = (torch.as_tensor(w[k], device=DEV) for k in ("A", "B", "y_prev", "y0"))
+    dt = torch.as_tensor(w["dt"], device=DEV).clone().requires_grad_(True)
+    sol = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-12, 1e-12), y0, (A, Bm, yp, dt), throw=False)
+    sol.value.sum().backward()
+    h = 1e-7
+    with torch.no_grad():
+        up = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-12, 1e-12), y0, (A, Bm, yp, dt + h), throw=False).value
+        dn = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-12, 1e-12), y0, (A, Bm, yp, dt - h), throw=False).value
+    fd = ((up - dn) / (2 * h)).sum(1)
+    assert torch.allclose(dt.grad, fd, rtol=1e-4, atol=1e-6)
