@@ -39,7 +39,7 @@ template <typename T> struct RootStepParams {
 constexpr int kRootStepWarps = 4;
 
 template <typename T, int N> __global__ void __launch_bounds__(kRootStepWarps * 32) root_step_kernel(const RootStepParams<T> p) {
-  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N];
+  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N + 4];
   __shared__ unsigned char piv_all[kRootStepWarps][N];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t prob = (int64_t)blockIdx.x * kRootStepWarps + wib;
@@ -147,7 +147,7 @@ template <typename T> __global__ void root_step_init_kernel(int64_t batch, int n
 // row-per-lane factorisation as the Newton kernels; status = singular when the solution is not finite.
 template <typename T, int N>
 __global__ void __launch_bounds__(kRootStepWarps * 32) lu_solve_kernel(const T* A, const T* b, T* x, int32_t* status, int64_t batch, int n) {
-  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N];
+  __shared__ __align__(16) T rowbuf_all[kRootStepWarps][N + 4];
   __shared__ unsigned char piv_all[kRootStepWarps][N];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t prob = (int64_t)blockIdx.x * kRootStepWarps + wib;

@@ -18,6 +18,16 @@
 #include "common.cuh"
 #include "models.cuh"
 
+// Tuning switches (A/B-measured on B200, 256 Ki implicit-Euler root finds; defaults are the fastest):
+//   ROOT_ARGMAX_BRANCH  second REDUX only when several candidates share the high word     6.65 ms vs 6.55 ms (off)
+//   ROOT_EARLY_RCP      start every candidate's reciprocal before the pivot is known       6.73 ms vs 6.55 ms (off)
+#ifndef ROOT_ARGMAX_BRANCH
+#define ROOT_ARGMAX_BRANCH 0
+#endif
+#ifndef ROOT_EARLY_RCP
+#define ROOT_EARLY_RCP 0
+#endif
+
 namespace b200opt {
 
 template <typename T> struct RootParams {
@@ -47,10 +57,20 @@ __device__ __forceinline__ int warp_argmax_abs(double v, bool valid) {
   const unsigned hi = valid ? (unsigned)__double2hiint(a) + 1u : 0u;  // non-negative doubles order like integers
   const unsigned m1 = __reduce_max_sync(kFull, hi);
   const bool c1 = valid && hi == m1;
+#if ROOT_ARGMAX_BRANCH
+  unsigned b = __ballot_sync(kFull, c1);
+  if (b & (b - 1)) {  // several candidates share the high word (rare): the low words decide (warp-uniform branch)
+    const unsigned lo = c1 ? (unsigned)__double2loint(a) : 0u;
+    const unsigned m2 = __reduce_max_sync(kFull, lo);
+    b = __ballot_sync(kFull, c1 && lo == m2);
+  }
+  return __ffs(b) - 1;
+#else
   const unsigned lo = c1 ? (unsigned)__double2loint(a) : 0u;
   const unsigned m2 = __reduce_max_sync(kFull, lo);
   const unsigned b = __ballot_sync(kFull, c1 && lo == m2);
   return __ffs(b) - 1;
+#endif
 }
 __device__ __forceinline__ int warp_argmax_abs(float v, bool valid) {
   const unsigned key = valid ? __float_as_uint(fabsf(v)) + 1u : 0u;
@@ -63,7 +83,7 @@ __device__ __forceinline__ int warp_argmax_abs(float v, bool valid) {
 //   mycol      = the elimination step at which this lane's row was the pivot row (its U row starts there)
 //   a[k]       = multiplier l_ik for k < mycol, U entries for k >= mycol;  rinv = 1 / U[mycol][mycol]
 //   piv[k]     (shared, per warp) = lane that was the pivot of step k
-// `rowbuf` is a per-warp shared line of N elements, 16-byte aligned.
+// `rowbuf` is a per-warp shared line of N + 4 elements, 16-byte aligned (slot N carries 1 / pivot).
 #ifndef ROOT_FAST_RCP
 #define ROOT_FAST_RCP 1
 #endif
@@ -98,8 +118,16 @@ __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const int k0 = (k / V) * V;  // 128-bit aligned start of the part of the pivot row still in use
+    // every candidate's reciprocal is started before the pivot is known (getf2 scales the column by 1/pivot): the
+    // 5-instruction dependent chain overlaps the arg-max reduction instead of following the pivot-row broadcast
+#if ROOT_EARLY_RCP
+    const T rc = t_rcp(a[k]);
+#endif
     const int p = warp_argmax_abs(a[k], !done);
     if (lane == p) {
+#if ROOT_EARLY_RCP
+      rowbuf[N] = rc;
+#endif
 #if ROOT_STS64
       // element-wise stores: every double already sits in an aligned register pair, a 128-bit store would first have
       // to move two of them into an aligned quad
@@ -122,8 +150,11 @@ __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T
     }
     __syncwarp();
     // pivot row: broadcast reads (every lane reads the same 16 bytes: one wavefront per 128-bit load)
-    const Vec v0 = *reinterpret_cast<const Vec*>(rowbuf + k0);
-    const T r = t_rcp(reinterpret_cast<const T*>(&v0)[k - k0]);  // getf2 scales the column by 1/pivot
+#if ROOT_EARLY_RCP
+    const T r = rowbuf[N];
+#else
+    const T r = t_rcp(rowbuf[k]);
+#endif
     const bool elim = !done && lane != p;
     if (lane == p) {
       done = true;
@@ -215,8 +246,8 @@ template <typename T> struct ImplicitEuler {
 };
 
 template <class Model, typename T> constexpr size_t root_smem_bytes() {
-  // shared model data + per warp: y[N] + rowbuf[N] (16B aligned) + piv[N]
-  return sizeof(T) * Model::kSharedElems + kRootWarpsPerBlock * (sizeof(T) * 2 * Model::N + 32);
+  // shared model data + per warp: y[N] + rowbuf[N + 4] (16B aligned) + piv[N]
+  return sizeof(T) * Model::kSharedElems + kRootWarpsPerBlock * (sizeof(T) * (2 * Model::N + 4) + 32);
 }
 
 #ifndef ROOT_MINBLOCKS
@@ -228,10 +259,10 @@ __global__ void __launch_bounds__(kRootWarpsPerBlock * 32, ROOT_MINBLOCKS) root_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  unsigned char* wbase = smem_raw + sizeof(T) * Model::kSharedElems + wib * (sizeof(T) * 2 * N + 32);
+  unsigned char* wbase = smem_raw + sizeof(T) * Model::kSharedElems + wib * (sizeof(T) * (2 * N + 4) + 32);
   T* ys = reinterpret_cast<T*>(wbase);
   T* rowbuf = ys + N;
-  unsigned char* piv = reinterpret_cast<unsigned char*>(rowbuf + N);
+  unsigned char* piv = reinterpret_cast<unsigned char*>(rowbuf + N + 4);
   Model::stage_shared(p.shared, sh, threadIdx.x, blockDim.x);
   __syncthreads();
 
