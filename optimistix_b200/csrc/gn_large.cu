@@ -260,7 +260,7 @@ int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_
   }
   // the fp64 scratch sits after the per-CTA partials of b200opt_gn_gram in the same workspace
   double* A = reinterpret_cast<double*>(static_cast<char*>(workspace) + (size_t)256 * (256 * 256 + 256 + 4) * 4);
-  static bool attr_set = false;
+  static thread_local bool attr_set = false;  // per host thread: the entry points are re-entrant
   if (!attr_set) {
     if (check_cuda(cudaFuncSetAttribute(gn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM),
                    "cudaFuncSetAttribute(gn_solve_kernel)"))

@@ -9,17 +9,23 @@
 // Kernel design (persistent, one CTA per SM, 320 threads):
 //   * J [m][256] fp32 row-major is streamed ONCE from HBM by TMA in tiles of 64 rows x 256 columns (64 KiB), as 8
 //     boxes of 32 columns (128 bytes = the swizzle span; CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), 3-stage mbarrier ring
-//     (192 KiB of shared memory).
+//     (192 KiB of shared memory).  Tile rows / stages are compile-time (GRAM_KROWS / GRAM_STAGES; 32 x 6 and 32 x 7
+//     measured slower: the per-tile synchronisation of the CUDA-core warps costs more than the shallower ring).
 //   * the same shared-memory tile is BOTH MMA operands: A = J_tile^T (M = parameter index) and B = J_tile
 //     (N = parameter index), both "MN-major" (the parameter index is the contiguous one), K = rows, kind::tf32
 //     (K = 8 rows per instruction), fp32 accumulation in TMEM.  Symmetry: only the blocks
 //     (rows 0-127 x cols 0-255) and (rows 128-255 x cols 128-255) are computed - 384 of 512 TMEM columns, 0.75 of
 //     the MMA work.  The accumulators stay in TMEM across ALL tiles of the CTA; there is one epilogue per CTA.
-//   * g and rr come from CUDA cores: 8 warps read the tile from shared memory (one 128-byte line per warp per row,
-//     conflict free under the swizzle) while the tensor core works on it.
+//   * g = J^T r, rr = r^T r and - in the fused mode of b200opt_gn_gram_linear - the residual r = J y - d itself come
+//     from the CUDA cores: 8 warps make ONE pass over the tile while the tensor core works on it.  A lane keeps 32
+//     columns of one row in registers (conflict-free 128-bit reads under the swizzle), forms its share of the row's
+//     dot product with y, gets the row's residual by a 3-step butterfly over the 8 lanes of the row and accumulates
+//     J[row][c] * r[row] into its 32 column partials.  Shared memory is the contended resource (the tensor core streams
+//     its operands from it as well: 20 KB of operand reads per 8 KB of tile), which is why the tile is read only once.
 //   * per-CTA partials go to a workspace; a second small kernel adds them in a fixed order (deterministic) and
 //     mirrors the triangle.
-// Roofline: HBM-bound by construction (68.7 GB of J per pass at configs[4]); tensor pipe ~55% busy at the HBM rate.
+// Roofline: HBM-bound by construction (68.7 GB of J per pass at configs[4]); tensor pipe ~55-68% busy at the HBM rate.
+// Measured (profiles/README.md): fused pass 85% of the measured HBM copy rate, unfused Gram 96%.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
