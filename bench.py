@@ -261,6 +261,26 @@ def bench_gram(args, rank, world, local_rank):
         t_step += ev[0].elapsed_time(ev[3])
     barrier()
     clocks = sampler.stop()
+    # size-independent property at the full size (outside the timed region): Gauss-Newton from y = 0 must recover the
+    # parameters the data were generated from (d = J y_true + 0.01 N(0,1)) to the noise level, on every rank identically
+    y.zero_()
+    r_old.zero_()
+    gn_steps = 0
+    for gn_steps in range(1, 13):
+        step()
+        y_conv = bool(((p.abs() / (1e-4 + 1e-4 * y.abs())).max() < 1).item()) if gn_steps > 1 else False  # Cauchy test on y ...
+        f_conv = float(summary[1].item()) < 1.0  # ... and on the residuals (_misc.py:291-310), as gauss_newton_large does
+        if y_conv and f_conv:
+            break
+        y.sub_(p)
+        r, r_old = r_old, r
+    # the least-squares estimate scatters around y_true with std sigma / (sqrt(m) * column scale): report the largest
+    # z-score over the 256 parameters (about 3 for a correct solve; a 1e-4 relative numerical error would read >> 10)
+    rel = ((y - y_true).abs() * scale * (float(m_local * world) ** 0.5) / 0.01).max()
+    if world > 1:
+        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    checks = {"gn_steps_to_convergence": gn_steps, "max_zscore_vs_generating_parameters": float(rel.item()),
+              "loss": 0.5 * float(summary[0].item()), "linear_solve_status": int(status.item())}
     if world > 1:
         t = torch.tensor([t_step, t_gram, t_res], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,7 +313,7 @@ def bench_gram(args, rank, world, local_rank):
                            "peak_tflops_tf32_assumed": tf32_peak, "frac": (gram_tflops / tf32_peak) if tf32_peak else None,
                            "note": "tf32 peak assumed = measured bf16 peak / 2 (no tf32 measurement in MEASURED_PEAKS.json)"},
                 "breakdown_ms": {"residual_pass": ms_res, "gram": ms_gram, "allgather+solve": ms - ms_res - ms_gram},
-                "gpu_launches": (3 if fused else 4) * K, "clocks": clocks, "cpu_baseline": None, "e2e": None}
+                "gpu_launches": (3 if fused else 4) * K, "clocks": clocks, "checks": checks, "cpu_baseline": None, "e2e": None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
