@@ -33,7 +33,14 @@
 #ifndef B200OPT_H_
 #define B200OPT_H_
 
+#ifdef __CUDACC_RTC__ /* NVRTC (run-time compiled model families) has no host headers */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -106,6 +113,7 @@ typedef struct b200opt_model_info {
   const char* problem_layout; /* what each row of `problem_args` holds */
 } b200opt_model_info_t;
 
+#ifndef __CUDACC_RTC__ /* host entry points: not visible to run-time compiled device code */
 int32_t b200opt_version(void);
 const char* b200opt_last_error(void);
 const char* b200opt_result_name(int32_t result_code);
@@ -113,6 +121,22 @@ int32_t b200opt_model_count(void);
 int32_t b200opt_model_info_get(int32_t model_id, b200opt_model_info_t* out);
 int32_t b200opt_model_id(const char* name); /* -1 if unknown */
 void b200opt_default_options(b200opt_options_t* out);
+
+/* ---- run-time registration of a least-squares "curve" family (the user side of the model registry) -----------------
+ * struct_body: CUDA C++ text, the members of
+ *     template <typename T> struct UserModel { static constexpr int N = n; static constexpr int NAUX = naux; <struct_body> };
+ * which must provide, exactly like the built-in families in optimistix_b200/csrc/models.cuh,
+ *     struct Pre {...};  static __device__ Pre prepare(const T (&y)[N]);
+ *     static __device__ T    residual(const T (&y)[N], const Pre&, const CurveRow<T>& row, T (&aux)[NAUX]);   (row.x abscissa, row.d data)
+ *     static __device__ void jac_row (const T (&y)[N], const Pre&, const CurveRow<T>& row, const T (&aux)[NAUX], T (&j)[N]);
+ * (the role of the reference's `fn(y, args)` and of jax.linearize on it, gauss_newton.py:158-181).  It is compiled with NVRTC
+ * for sm_100a against the library's own kernel headers in `csrc_dir` (optimistix_b200/csrc) and then runs in the same
+ * persistent one-warp-per-problem LM / GN kernel as the built-in families (fp32 and fp64).  Needs a CUDA device.
+ * Returns the new model id (>= B200OPT_JIT_MODEL_BASE) for b200opt_least_squares[_host], or a negative error code;
+ * a compilation error is reported through b200opt_last_error(). */
+#define B200OPT_JIT_MODEL_BASE 1000
+int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux, const char* struct_body,
+                                      const char* csrc_dir);
 
 /* ---- batched nonlinear least squares (LM / GN), one warp per problem, persistent kernel ---------------
  * y0           [batch][n]
@@ -249,6 +273,8 @@ int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_
  * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */
 int32_t b200opt_linear_residual(const float* J, const float* y, const float* d, int64_t m_local, int32_t n, float* r,
                                 const float* r_old, float rtol, float atol, uint32_t* fmax_bits, void* stream);
+
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ F32, F64 = 0, 1
 NORM_IDS = {"max": 0, "two": 1, "rms": 2}
 SOLVER_LM, SOLVER_GN, SOLVER_NEWTON, SOLVER_CHORD, SOLVER_BFGS = 0, 1, 2, 3, 4
 UPDATE_BFGS, UPDATE_DFP = 0, 1
+CSRC_DIR = os.path.join(_HERE, "csrc")
 
 
 class Options(C.Structure):
@@ -59,6 +60,7 @@ _SIGNATURES = {
     "b200opt_model_info_get": (_i32, [_i32, C.POINTER(ModelInfo)]),
     "b200opt_model_id": (_i32, [C.c_char_p]),
     "b200opt_default_options": (None, [C.POINTER(Options)]),
+    "b200opt_register_curve_family": (_i32, [C.c_char_p, _i32, _i32, C.c_char_p, C.c_char_p]),
     "b200opt_least_squares": (_i32, [_i32, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_root_find": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp]),
     "b200opt_minimise": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

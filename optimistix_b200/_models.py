@@ -87,6 +87,29 @@ linear_rows = RegisteredModel("linear_rows", 4, KIND_LSQ, 256, ("J", "d"), 0, No
 _REGISTRY = {m.name: m for m in (exp_decay, gauss2, implicit_euler, rosenbrock, linear_rows)}
 
 
+def register_curve_family(name: str, n: int, source: str, *, naux: int = 1, torch_fn: Callable | None = None,
+                          doc: str = "") -> RegisteredModel:
+    """Register a least-squares "curve" family at run time (the user side of the plugin registry).
+
+    `source` is CUDA C++: the members `struct Pre`, `prepare`, `residual`, `jac_row` of a model struct exactly like the
+    built-in ones in optimistix_b200/csrc/models.cuh (`T` is the scalar type, `N = n`, `NAUX = naux`, `row.x` the abscissa,
+    `row.d` the datum).  `b200opt_register_curve_family` compiles it with NVRTC for sm_100a against the library's own kernel
+    headers; the returned model then runs `least_squares(model, LevenbergMarquardt | GaussNewton, y0, (x, d))` in the same
+    persistent one-warp-per-problem kernel as the built-in families, in fp32 and fp64, on device or host buffers.
+    `torch_fn(y, {"x": ..., "d": ...})` is the optional host-side evaluator (tests, ImplicitAdjoint).  Needs a CUDA device."""
+    from . import _lib
+
+    if name in _REGISTRY:
+        raise ValueError(f"a model family named {name!r} is already registered")
+    lib = _lib.load()
+    model_id = lib.b200opt_register_curve_family(name.encode(), int(n), int(naux), source.encode(), _lib.CSRC_DIR.encode())
+    if model_id < 0:
+        _lib.check(model_id, "b200opt_register_curve_family")
+    m = RegisteredModel(name, int(model_id), KIND_LSQ, int(n), ("x", "d"), 1, torch_fn, doc or "run-time compiled curve family")
+    _REGISTRY[name] = m
+    return m
+
+
 def get(name: str) -> RegisteredModel:
     return _REGISTRY[name]
 

@@ -24,6 +24,11 @@ int check_cuda(cudaError_t e, const char* what) {
   return B200OPT_ECUDA;
 }
 
+int jit_family_count();
+int jit_family_id(const char* name);
+bool jit_family_info(int index, b200opt_model_info_t* out);
+int lsq_launch_jit(const LsqArgs& a, int model_id);
+
 int device_sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -238,8 +243,9 @@ extern "C" {
 int32_t b200opt_version(void) { return B200OPT_VERSION; }
 const char* b200opt_last_error(void) { return g_err; }
 const char* b200opt_result_name(int32_t c) { return (c >= 0 && c < 8) ? kResultNames[c] : "unknown"; }
-int32_t b200opt_model_count(void) { return MODEL_COUNT; }
+int32_t b200opt_model_count(void) { return MODEL_COUNT + jit_family_count(); }
 int32_t b200opt_model_info_get(int32_t id, b200opt_model_info_t* out) {
+  if (out && id >= B200OPT_JIT_MODEL_BASE && jit_family_info(id - B200OPT_JIT_MODEL_BASE, out)) return 0;
   if (id < 0 || id >= MODEL_COUNT || !out) {
     set_error("model_info_get: bad model id %d", id);
     return B200OPT_EINVAL;
@@ -251,7 +257,7 @@ int32_t b200opt_model_id(const char* name) {
   if (!name) return -1;
   for (int i = 0; i < MODEL_COUNT; ++i)
     if (!strcmp(kModels[i].name, name)) return i;
-  return -1;
+  return jit_family_id(name);
 }
 void b200opt_default_options(b200opt_options_t* o) {
   if (!o) return;
@@ -289,6 +295,7 @@ int32_t b200opt_least_squares(int32_t solver, int32_t model_id, int32_t dtype, i
     case MODEL_EXP_DECAY: return lsq_launch_exp_decay(a);
     case MODEL_GAUSS2: return lsq_launch_gauss2(a);
     default:
+      if (model_id >= B200OPT_JIT_MODEL_BASE) return lsq_launch_jit(a, model_id);  // run-time compiled family
       set_error("least_squares: model %d is not a batched least-squares family", model_id);
       return B200OPT_EINVAL;
   }

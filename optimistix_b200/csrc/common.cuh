@@ -1,8 +1,10 @@
 // Shared device helpers for the B200 (sm_100a) Optimistix hot path.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#endif
 
 #include "../../include/b200opt.h"
 
@@ -24,7 +26,11 @@ template <typename T> struct Num;
 template <> struct Num<float> {
   static __host__ __device__ constexpr float eps() { return 1.1920928955078125e-07f; }
   static __host__ __device__ constexpr float max() { return 3.4028234663852886e+38f; }
+#ifdef __CUDACC_RTC__
+  static __device__ float inf() { return __int_as_float(0x7f800000); }
+#else
   static __host__ __device__ constexpr float inf() { return __builtin_huge_valf(); }
+#endif
   static constexpr int precision = 6;  // jnp.finfo(float32).precision
   using Vec = float4;
   static constexpr int kVec = 4;
@@ -32,7 +38,11 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static __host__ __device__ constexpr double eps() { return 2.220446049250313e-16; }
   static __host__ __device__ constexpr double max() { return 1.7976931348623157e+308; }
+#ifdef __CUDACC_RTC__
+  static __device__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+#else
   static __host__ __device__ constexpr double inf() { return __builtin_huge_val(); }
+#endif
   static constexpr int precision = 15;
   using Vec = double2;
   static constexpr int kVec = 2;
@@ -130,8 +140,10 @@ __device__ __forceinline__ void spd_solve(const T (&G)[Tri<N>::size], T lam, con
   }
 }
 
+#ifndef __CUDACC_RTC__
 // thread-local last-error string (host side)
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+#endif
 
 }  // namespace b200opt

@@ -80,3 +80,15 @@ def test_xla_shim_uses_only_declared_entry_points_with_matching_arity():
     for name in used:
         assert name in _declared(), name
         assert arity(shim, name) == arity(hdr, name), (name, arity(shim, name), arity(hdr, name))
+
+
+def test_run_time_family_needs_a_device(lib):
+    """No CPU fallback: registering a run-time family without a CUDA device fails loudly instead of deferring."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a device is present")
+    code = lib.b200opt_register_curve_family(b"nodev", 2, 1, b"struct Pre {};", _lib.CSRC_DIR.encode())
+    assert code < 0 and lib.b200opt_last_error()
