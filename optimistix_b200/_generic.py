@@ -98,18 +98,18 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
     opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=root_near_zero)
     _lib.check(lib.b200opt_lsq_step_init(dtype_code, B, n, m, Y0.data_ptr(), y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
                                          steps.data_ptr(), res.data_ptr(), stream), "b200opt_lsq_step_init")
-    launches = 0
-    for it in range(max_steps):
-        if it > 0:
-            r, J = rj(y_eval)
-        r = r.contiguous()
-        J = J.contiguous()
-        _lib.check(lib.b200opt_lsq_step(solver_id, dtype_code, B, n, m, r.data_ptr(), J.data_ptr(), y.data_ptr(), y_eval.data_ptr(),
-                                        state.data_ptr(), C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), stream),
+    first = {"rJ": (r, J)}
+
+    def body():
+        rr, JJ = first.pop("rJ", None) or rj(y_eval)
+        rr, JJ = rr.contiguous(), JJ.contiguous()
+        st = t.cuda.current_stream(Y0.device).cuda_stream  # the capture stream while a graph is being recorded
+        _lib.check(lib.b200opt_lsq_step(solver_id, dtype_code, B, n, m, rr.data_ptr(), JJ.data_ptr(), y.data_ptr(), y_eval.data_ptr(),
+                                        state.data_ptr(), C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), st),
                    "b200opt_lsq_step")
-        launches += 1
-        if int(active.item()) == 0:  # every lane of the vmapped while_loop has stopped (_iterate.py:230-232)
-            break
+        body.keep = (rr, JJ)  # the eager path must keep its inputs alive until the kernel has run
+
+    launches = _run_iterations(body, body, active, max_steps) if max_steps > 0 else 0
     _lib.check(lib.b200opt_lsq_step_finish(dtype_code, B, n, m, state.data_ptr(), res.data_ptr(), stream), "b200opt_lsq_step_finish")
     if throw:
         rh = res.cpu().numpy()
@@ -144,6 +144,47 @@ def _prep_y0(y0):
         raise ValueError("y0 must have shape [n] (one problem) or [batch, n]")
     Y0 = (y0[None] if single else y0).contiguous()
     return Y0, single, (_lib.F32 if y0.dtype == t.float32 else _lib.F64)
+
+
+def _run_iterations(first_body, body, active, max_steps):
+    """Drive the per-iteration loop: `first_body()` / `body()` evaluate the user's function (and derivatives) at the current
+    point and enqueue ONE step kernel; `active` is the device counter the kernel leaves behind.
+
+    The first iteration runs eagerly (lazy initialisation, attribute setting).  The rest of the loop is launch bound on the
+    host - torch.func dispatches ~30 small kernels per iteration - so one iteration is captured into a CUDA graph and
+    replayed (static shapes, the carry lives in fixed buffers, frozen problems are no-ops inside the step kernel).  If the
+    user's function cannot be captured (it synchronises, allocates outside the pool, ...) the loop falls back to eager
+    launches.  B200OPT_GENERIC_GRAPH=0 disables capture.  Returns the number of step-kernel launches."""
+    import os
+
+    t = _torch()
+    first_body()
+    launches = 1
+    if launches >= max_steps or int(active.item()) == 0:
+        return launches
+    graph = None
+    if os.environ.get("B200OPT_GENERIC_GRAPH", "1") != "0" and max_steps > 3:
+        try:
+            body()  # second eager iteration: the steady-state form of the body (Chord: no Jacobian) warms up too
+            launches += 1
+            if launches >= max_steps or int(active.item()) == 0:
+                return launches
+            g = t.cuda.CUDAGraph()
+            with t.cuda.graph(g):
+                body()
+            graph = g
+        except Exception:  # noqa: BLE001 - not capturable: eager loop below
+            graph = None
+            t.cuda.synchronize()
+    while launches < max_steps:
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+        launches += 1
+        if int(active.item()) == 0:  # every lane of the vmapped while_loop has stopped (_iterate.py:230-232)
+            break
+    return launches
 
 
 def _empty_solution(Y0, max_steps):
@@ -226,27 +267,30 @@ def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_i
     _lib.check(lib.b200opt_root_step_init(dtype_code, B, n, Y0.data_ptr(), y.data_ptr(), state.data_ptr(), steps.data_ptr(),
                                           res.data_ptr(), stream), "b200opt_root_step_init")
     chord = isinstance(solver, Chord)
-    J_fixed = None
-    launches = 0
-    for _ in range(max_steps):
-        if chord:
-            if J_fixed is None:
-                f, J_fixed = f_and_J(y)
-                J_fixed = J_fixed.contiguous()
-            else:
-                f = f_only(y)
-            J = J_fixed
-        else:
-            f, J = f_and_J(y)
-            J = J.contiguous()
-        f = f.contiguous()
+    hold = {}
+
+    def launch(f, J):
+        f, J = f.contiguous(), J.contiguous()
+        st = t.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.b200opt_root_step(dtype_code, B, n, f.data_ptr(), J.data_ptr(), lower.data_ptr() if lower is not None else None,
                                          upper.data_ptr() if upper is not None else None, y.data_ptr(), state.data_ptr(),
-                                         C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), stream),
+                                         C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), st),
                    "b200opt_root_step")
-        launches += 1
-        if int(active.item()) == 0:
-            break
+        hold["fJ"] = (f, J)
+
+    def first_body():
+        f, J = f_and_J(y)
+        if chord:
+            hold["J_fixed"] = J.contiguous()  # newton_chord.py:80-87: linearised once, at y0
+        launch(f, J)
+
+    def body():
+        if chord:
+            launch(f_only(y), hold["J_fixed"])
+        else:
+            launch(*f_and_J(y))
+
+    launches = _run_iterations(first_body, body, active, max_steps) if max_steps > 0 else 0
     _lib.check(lib.b200opt_root_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_root_step_finish")
     if throw:
         _throw_if_failed(res)
@@ -302,17 +346,19 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
         raise NotImplementedError("use_inverse=False factorises the Hessian approximation in shared memory: n <= 64")
     _lib.check(lib.b200opt_bfgs_step_init(dtype_code, B, n, Y0.data_ptr(), y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
                                           steps.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_init")
-    launches = 0
-    while launches < max_steps_k:
+    hold = {}
+
+    def body():
         g, f = gv(y_eval)
         g, f = g.contiguous(), f.contiguous()
         rn = rootv(y).to(Y0.dtype).contiguous() if rootv is not None else None
-        _lib.check(lib.b200opt_bfgs_step(update, use_inverse, dtype_code, B, n, f.data_ptr(), g.data_ptr(), rn.data_ptr() if rn is not None else None,
-                                         y.data_ptr(), y_eval.data_ptr(), state.data_ptr(), C.byref(opts), steps.data_ptr(),
-                                         res.data_ptr(), active.data_ptr(), stream), "b200opt_bfgs_step")
-        launches += 1
-        if int(active.item()) == 0:
-            break
+        st = t.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.b200opt_bfgs_step(update, use_inverse, dtype_code, B, n, f.data_ptr(), g.data_ptr(),
+                                         rn.data_ptr() if rn is not None else None, y.data_ptr(), y_eval.data_ptr(), state.data_ptr(),
+                                         C.byref(opts), steps.data_ptr(), res.data_ptr(), active.data_ptr(), st), "b200opt_bfgs_step")
+        hold["in"] = (g, f, rn)
+
+    launches = _run_iterations(body, body, active, max_steps_k) if max_steps_k > 0 else 0
     _lib.check(lib.b200opt_bfgs_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_finish")
     if throw:
         _throw_if_failed(res)
