@@ -117,7 +117,7 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     terminate = False
     steps = 0
     while not terminate and result == RESULTS.successful and steps < max_steps:
-        y_old_finite = bool(torch.isfinite(y).all())
+        y_fin_t = torch.isfinite(y).all()  # _iterate.py:216,238: finiteness of the carry's y from BEFORE this step
         if fused:
             ops.residual_gram(J, y_eval, d, r_new, r_old, rtol, atol, fmax, out)  # one read of J per iteration
         else:
@@ -127,13 +127,16 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
             dist.all_gather_into_tensor(gathered, out, group=group)  # the only exchange of the iteration
         ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)  # NewtonDescent.query: newton = G^-1 g
         y_diff = y_eval - y
-        y_conv = bool(((y_diff.abs() / (atol + rtol * y_eval.abs())).max() < 1).item())  # _misc.py:306-308
-        f_conv = bool((summary[1] < 1).item())  # NaN compares false, like jnp.max
-        terminate = y_conv and f_conv  # LearningRate always accepts (learning_rate.py:24-35)
+        y_conv_t = (y_diff.abs() / (atol + rtol * y_eval.abs())).max() < 1  # _misc.py:306-308
+        f_conv_t = summary[1] < 1  # NaN compares false, like jnp.max
+        # ONE host read per iteration (the flags of this step and the linear solve's result code)
+        y_old_finite, y_conv, f_conv, result = torch.stack(
+            [y_fin_t.to(torch.int32), y_conv_t.to(torch.int32), f_conv_t.to(torch.int32), status[0]]).tolist()
+        terminate = bool(y_conv) and bool(f_conv)  # LearningRate always accepts (learning_rate.py:24-35)
         y = y_eval
         y_eval = y - p  # gauss_newton.py:126-127 with step_size 1
         r_old, r_new = r_new, r_old
-        result = int(status.item())  # gauss_newton.py:316-318: the linear solve's result
+        # `result` is the linear solve's (gauss_newton.py:316-318)
         if not y_old_finite:
             result = RESULTS.nonfinite
         steps += 1
