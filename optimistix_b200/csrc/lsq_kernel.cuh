@@ -131,8 +131,11 @@ template <class Model, typename T> __host__ __device__ inline size_t lsq_smem_by
   return sizeof(T) * ((size_t)m_pad /* shared abscissa grid */ + kLsqWarpsPerBlock * per_warp);
 }
 
+#ifndef LSQ_MINBLOCKS_F64
+#define LSQ_MINBLOCKS_F64 2
+#endif
 template <class Model, typename T, bool TRUST>
-__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 2)) lsq_solve_kernel(const LsqParams<T> p) {
+__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : LSQ_MINBLOCKS_F64)) lsq_solve_kernel(const LsqParams<T> p) {
   constexpr int N = Model::N;
   constexpr int NG = Tri<N>::size;
   constexpr int NAUX = Model::NAUX;
