@@ -137,6 +137,13 @@ void b200opt_default_options(b200opt_options_t* out);
 #define B200OPT_JIT_MODEL_BASE 1000
 int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux, const char* struct_body,
                                       const char* csrc_dir);
+/* The same for a root-finding family (Newton / Chord persistent kernel, b200opt_root_find[_host]): struct_body provides
+ *     static __device__ void eval_row(const T* sh, const T* ys, const Ctx& c, int lane, T& f, T (&row)[N], bool want_jac);
+ * lane `lane` evaluates F_lane(y) into f and, if want_jac, row `lane` of the Jacobian into row[0..N); sh = the first
+ * shared_elems elements of shared_args (staged in shared memory), ys = the whole iterate y[0..N) (shared memory),
+ * c.prob = this problem's row of problem_args.  n must be a multiple of 4, n <= 32. */
+int32_t b200opt_register_root_family(const char* name, int32_t n, int32_t shared_elems, const char* struct_body,
+                                     const char* csrc_dir);
 
 /* ---- batched nonlinear least squares (LM / GN), one warp per problem, persistent kernel ---------------
  * y0           [batch][n]

@@ -340,7 +340,19 @@ def _bound(buf, b, n, dev):
 
 
 def _pack_root_args(fn, a, buf, dev, B, n, single):
-    """implicit_euler: shared = [A | B] (2 n^2), per problem = [y_prev (n) | dt | pad] with an even stride."""
+    """implicit_euler: shared = [A | B] (2 n^2), per problem = [y_prev (n) | dt | pad] with an even stride.
+    Run-time families (models.register_root_family): args = (shared [S], prob [B, P]) are passed through."""
+    if fn.model_id >= 1000:
+        prob = buf.arr(a["prob"], dev)
+        if single and prob.ndim == 1:
+            prob = prob[None]
+        if prob.ndim != 2 or prob.shape[0] != B:
+            raise ValueError(f"{fn.name}: per-problem args must have shape [{B}, P], got {tuple(prob.shape)}")
+        sh = a["shared"]
+        if sh is None:
+            sh = [0.0]  # the C entry point wants a non-NULL pointer even when the family stages nothing
+        shared = buf.arr(sh, dev).reshape(-1)
+        return shared, prob, int(prob.shape[1])
     if fn.name != "implicit_euler":
         raise NotImplementedError(fn.name)
     A, Bm = buf.arr(a["A"], dev), buf.arr(a["B"], dev)

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b200opt_model_id": (_i32, [C.c_char_p]),
     "b200opt_default_options": (None, [C.POINTER(Options)]),
     "b200opt_register_curve_family": (_i32, [C.c_char_p, _i32, _i32, C.c_char_p, C.c_char_p]),
+    "b200opt_register_root_family": (_i32, [C.c_char_p, _i32, _i32, C.c_char_p, C.c_char_p]),
     "b200opt_least_squares": (_i32, [_i32, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_root_find": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp]),
     "b200opt_minimise": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -110,6 +110,28 @@ def register_curve_family(name: str, n: int, source: str, *, naux: int = 1, torc
     return m
 
 
+def register_root_family(name: str, n: int, source: str, *, shared_elems: int = 0, torch_fn: Callable | None = None,
+                         doc: str = "") -> RegisteredModel:
+    """Register a root-finding family at run time: `source` defines the device function
+    `eval_row(sh, ys, c, lane, f, row, want_jac)` (lane `lane` evaluates F_lane(y) and row `lane` of the Jacobian; `sh` =
+    the `shared_elems` shared arguments staged in shared memory, `ys` = the iterate, `c.prob` = this problem's arguments).
+    The returned model runs `root_find(model, Newton | Chord, y0, (shared, prob))` in the persistent one-warp-per-problem
+    kernel (in-warp LU with partial pivoting); `shared` is a flat array of `shared_elems` values, `prob` is
+    `[batch, anything]`.  n must be a multiple of 4, at most 32.  `torch_fn(y, {"shared": ..., "prob": ...})` is the optional
+    host-side evaluator.  Needs a CUDA device."""
+    from . import _lib
+
+    if name in _REGISTRY:
+        raise ValueError(f"a model family named {name!r} is already registered")
+    lib = _lib.load()
+    model_id = lib.b200opt_register_root_family(name.encode(), int(n), int(shared_elems), source.encode(), _lib.CSRC_DIR.encode())
+    if model_id < 0:
+        _lib.check(model_id, "b200opt_register_root_family")
+    m = RegisteredModel(name, int(model_id), KIND_ROOT, int(n), ("shared", "prob"), 1, torch_fn, doc or "run-time compiled root family")
+    _REGISTRY[name] = m
+    return m
+
+
 def get(name: str) -> RegisteredModel:
     return _REGISTRY[name]
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "lsq_launch.cuh"
+#include "newton_kernel.cuh"
 
 namespace b200opt {
 
@@ -60,9 +61,10 @@ struct Nvrtc {
 
 struct JitFamily {
   const char* name = "";  // strdup'ed once, never freed: b200opt_model_info_get hands the pointer out
-  int n = 0, naux = 0;
+  int kind = B200OPT_KIND_LEAST_SQUARES;
+  int n = 0, naux = 0, shared_elems = 0;
   CUmodule module = nullptr;
-  CUfunction fn[2][2] = {};  // [dtype f32/f64][GN/LM]
+  CUfunction fn[2][2] = {};  // least squares: [dtype f32/f64][GN/LM]; root: [dtype][0]
 };
 
 // Driver API entry points, resolved through the runtime (cudaGetDriverEntryPoint) so that libb200opt.so does not link
@@ -132,8 +134,13 @@ bool jit_family_info(int index, b200opt_model_info_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (index < 0 || index >= (int)g_families.size()) return false;
   const JitFamily& f = g_families[index];
-  *out = b200opt_model_info_t{B200OPT_JIT_MODEL_BASE + index, B200OPT_KIND_LEAST_SQUARES, f.n, f.n, 0, 0, f.name,
-                              "run-time compiled family (b200opt_register_curve_family)", "x[m] abscissa grid", "d[m] data"};
+  if (f.kind == B200OPT_KIND_ROOT)
+    *out = b200opt_model_info_t{B200OPT_JIT_MODEL_BASE + index, B200OPT_KIND_ROOT, f.n, f.n, 0, f.shared_elems, f.name,
+                                "run-time compiled family (b200opt_register_root_family)", "shared[shared_args] staged in shared memory",
+                                "prob[stride] per problem"};
+  else
+    *out = b200opt_model_info_t{B200OPT_JIT_MODEL_BASE + index, B200OPT_KIND_LEAST_SQUARES, f.n, f.n, 0, 0, f.name,
+                                "run-time compiled family (b200opt_register_curve_family)", "x[m] abscissa grid", "d[m] data"};
   return true;
 }
 
@@ -147,6 +154,10 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
       return B200OPT_EINVAL;
     }
     fam = g_families[idx];
+  }
+  if (fam.kind != B200OPT_KIND_LEAST_SQUARES) {
+    set_error("least_squares: model %s is not a least-squares family", fam.name);
+    return B200OPT_EINVAL;
   }
   if (a.n != fam.n) {
     set_error("least_squares: model %s expects n=%d parameters, got n=%d", fam.name, fam.n, a.n);
@@ -199,51 +210,82 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
   return f64 ? launch(double{}) : launch(float{});
 }
 
-}  // namespace b200opt
-
-using namespace b200opt;
-
-extern "C" {
-
-int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux, const char* struct_body, const char* csrc_dir) {
-  if (!name || !struct_body || !csrc_dir || n < 1 || n > 16 || naux < 1 || naux > 8) {
-    set_error("register_curve_family: need a name, a struct body, the csrc directory, 1 <= n <= 16 and 1 <= naux <= 8");
-    return B200OPT_EINVAL;
-  }
-  std::lock_guard<std::mutex> lk(g_mu);
-  for (size_t i = 0; i < g_families.size(); ++i)
-    if (!strcmp(g_families[i].name, name)) {
-      set_error("register_curve_family: a family named %s is already registered", name);
+int root_launch_jit(int model_id, int solver, int dtype, int64_t batch, int n, const void* y0, const void* shared, const void* prob,
+                    int64_t stride, const void* lower, const void* upper, const b200opt_options_t* o, void* y_out, int32_t* num_steps,
+                    int32_t* result, cudaStream_t stream) {
+  JitFamily fam;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int idx = model_id - B200OPT_JIT_MODEL_BASE;
+    if (idx < 0 || idx >= (int)g_families.size() || g_families[idx].kind != B200OPT_KIND_ROOT) {
+      set_error("root_find: model %d is not a registered root-finding family", model_id);
       return B200OPT_EINVAL;
     }
+    fam = g_families[idx];
+  }
+  if (n != fam.n) {
+    set_error("root_find: model %s expects n=%d, got n=%d", fam.name, fam.n, n);
+    return B200OPT_EINVAL;
+  }
+  const bool f64 = dtype == B200OPT_F64;
+  const size_t es = f64 ? 8 : 4;
+  const size_t smem = es * fam.shared_elems + kRootWarpsPerBlock * (es * (2 * fam.n + 4) + 32);  // root_smem_bytes
+  CUfunction fn = fam.fn[f64 ? 1 : 0][0];
+  if (check_cu(g_drv.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem), "cuFuncSetAttribute")) return B200OPT_ECUDA;
+  int occ = 0;
+  if (check_cu(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kRootWarpsPerBlock * 32, smem), "occupancy")) return B200OPT_ECUDA;
+  const int64_t need = (batch + kRootWarpsPerBlock - 1) / kRootWarpsPerBlock;
+  const int64_t cap = (int64_t)device_sm_count() * (occ > 0 ? occ : 1);
+  const unsigned grid = (unsigned)(need < cap ? need : cap);
+  auto launch = [&](auto tag) -> int {
+    using T = decltype(tag);
+    RootParams<T> p;
+    p.y0 = static_cast<const T*>(y0);
+    p.shared = static_cast<const T*>(shared);
+    p.prob = static_cast<const T*>(prob);
+    p.prob_stride = stride;
+    p.lower = static_cast<const T*>(lower);
+    p.upper = static_cast<const T*>(upper);
+    p.y_out = static_cast<T*>(y_out);
+    p.num_steps = num_steps;
+    p.result = result;
+    p.batch = batch;
+    p.n = n;
+    p.rtol = (T)o->rtol;
+    p.atol = (T)o->atol;
+    p.kappa = (T)o->kappa;
+    p.norm = o->norm;
+    p.max_steps = o->max_steps;
+    p.cauchy = o->cauchy_termination;
+    p.chord = solver == B200OPT_SOLVER_CHORD;
+    void* params[] = {&p};
+    return check_cu(g_drv.LaunchKernel(fn, grid, 1, 1, kRootWarpsPerBlock * 32, 1, 1, (unsigned)smem, stream, params, nullptr),
+                    "cuLaunchKernel(run-time root family)");
+  };
+  return f64 ? launch(double{}) : launch(float{});
+}
+
+namespace {
+
+// compile `src`, load it, resolve `nexpr` name expressions into fam.fn (row-major over [2][2]); shared by both kinds
+int compile_and_load(const char* name, const std::string& src, const char* csrc_dir, const char* const* exprs, int nexpr, JitFamily& fam) {
   if (!g_nvrtc.load()) {
-    set_error("register_curve_family: libnvrtc could not be loaded (%s)", dlerror() ? dlerror() : "symbols missing");
+    set_error("register family: libnvrtc could not be loaded (%s)", dlerror() ? dlerror() : "symbols missing");
     return B200OPT_ENOTIMPL;
   }
   // make sure the primary context exists and is current (the rest of the library uses the runtime API)
   if (check_cuda(cudaFree(nullptr), "context")) return B200OPT_ECUDA;
   if (!g_drv.load()) {
-    set_error("register_curve_family: the CUDA driver entry points could not be resolved");
+    set_error("register family: the CUDA driver entry points could not be resolved");
     return B200OPT_ECUDA;
   }
-  char head[512];
-  snprintf(head, sizeof(head),
-           "#include \"lsq_kernel.cuh\"\nnamespace b200opt {\ntemplate <typename T> struct UserModel {\n  static constexpr int N = %d;\n"
-           "  static constexpr int NAUX = %d;\n",
-           n, naux);
-  const std::string src = std::string(head) + struct_body + "\n};\n}  // namespace b200opt\n";
   nvrtcProgram prog = nullptr;
   nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), (std::string(name) + ".cu").c_str(), 0, nullptr, nullptr);
   if (r != NVRTC_SUCCESS) {
-    set_error("register_curve_family: nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    set_error("register family: nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
     return B200OPT_ECUDA;
   }
-  static const char* kExpr[2][2] = {
-      {"b200opt::lsq_solve_kernel<b200opt::UserModel<float>, float, false>", "b200opt::lsq_solve_kernel<b200opt::UserModel<float>, float, true>"},
-      {"b200opt::lsq_solve_kernel<b200opt::UserModel<double>, double, false>",
-       "b200opt::lsq_solve_kernel<b200opt::UserModel<double>, double, true>"}};
-  for (int d = 0; d < 2; ++d)
-    for (int t = 0; t < 2; ++t) g_nvrtc.AddNameExpression(prog, kExpr[d][t]);
+  for (int i = 0; i < nexpr; ++i) g_nvrtc.AddNameExpression(prog, exprs[i]);
   const std::string inc = std::string("-I") + csrc_dir;
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str()};
   r = g_nvrtc.CompileProgram(prog, 4, opts);
@@ -252,7 +294,7 @@ int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux,
     g_nvrtc.GetProgramLogSize(prog, &n_log);
     std::string log(n_log, '\0');
     if (n_log) g_nvrtc.GetProgramLog(prog, &log[0]);
-    set_error("register_curve_family(%s): compilation failed: %.400s", name, log.c_str());
+    set_error("register family (%s): compilation failed: %.400s", name, log.c_str());
     g_nvrtc.DestroyProgram(&prog);
     return B200OPT_EINVAL;
   }
@@ -260,25 +302,95 @@ int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux,
   g_nvrtc.GetCUBINSize(prog, &n_bin);
   std::vector<char> cubin(n_bin);
   g_nvrtc.GetCUBIN(prog, cubin.data());
-  JitFamily fam;
-  fam.name = strdup(name);
-  fam.n = n;
-  fam.naux = naux;
   if (check_cu(g_drv.ModuleLoadData(&fam.module, cubin.data()), "cuModuleLoadData")) {
     g_nvrtc.DestroyProgram(&prog);
     return B200OPT_ECUDA;
   }
-  for (int d = 0; d < 2; ++d)
-    for (int t = 0; t < 2; ++t) {
-      const char* lowered = nullptr;
-      g_nvrtc.GetLoweredName(prog, kExpr[d][t], &lowered);
-      if (!lowered || check_cu(g_drv.ModuleGetFunction(&fam.fn[d][t], fam.module, lowered), "cuModuleGetFunction")) {
-        g_nvrtc.DestroyProgram(&prog);
-        g_drv.ModuleUnload(fam.module);
-        return B200OPT_ECUDA;
-      }
+  for (int i = 0; i < nexpr; ++i) {
+    const char* lowered = nullptr;
+    g_nvrtc.GetLoweredName(prog, exprs[i], &lowered);
+    CUfunction* slot = &fam.fn[0][0] + (nexpr == 4 ? i : 2 * i);
+    if (!lowered || check_cu(g_drv.ModuleGetFunction(slot, fam.module, lowered), "cuModuleGetFunction")) {
+      g_nvrtc.DestroyProgram(&prog);
+      g_drv.ModuleUnload(fam.module);
+      return B200OPT_ECUDA;
     }
+  }
   g_nvrtc.DestroyProgram(&prog);
+  return 0;
+}
+
+bool name_taken(const char* name) {
+  for (size_t i = 0; i < g_families.size(); ++i)
+    if (!strcmp(g_families[i].name, name)) return true;
+  return false;
+}
+
+}  // namespace
+
+}  // namespace b200opt
+
+using namespace b200opt;
+
+extern "C" {
+
+int32_t b200opt_register_root_family(const char* name, int32_t n, int32_t shared_elems, const char* struct_body, const char* csrc_dir) {
+  if (!name || !struct_body || !csrc_dir || n < 4 || n > 32 || (n & 3) || shared_elems < 0 || shared_elems > 24 * 1024) {
+    set_error("register_root_family: need a name, a struct body, the csrc directory, n in {4, 8, ..., 32} and 0 <= shared_elems <= 24576");
+    return B200OPT_EINVAL;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (name_taken(name)) {
+    set_error("register_root_family: a family named %s is already registered", name);
+    return B200OPT_EINVAL;
+  }
+  char head[1024];
+  snprintf(head, sizeof(head),
+           "#include \"newton_kernel.cuh\"\nnamespace b200opt {\ntemplate <typename T> struct UserRoot {\n  static constexpr int N = %d;\n"
+           "  static constexpr int kSharedElems = %d;\n  struct Ctx { const T* prob; };\n"
+           "  __device__ static __forceinline__ void stage_shared(const T* g, T* s, int tid, int nthreads) {\n"
+           "    for (int e = tid; e < kSharedElems; e += nthreads) s[e] = g[e];\n  }\n"
+           "  __device__ static __forceinline__ Ctx load(const T* prob, int) { return Ctx{prob}; }\n",
+           n, shared_elems);
+  const std::string src = std::string(head) + struct_body + "\n};\n}  // namespace b200opt\n";
+  static const char* kExpr[2] = {"b200opt::root_solve_kernel<b200opt::UserRoot<float>, float>",
+                                 "b200opt::root_solve_kernel<b200opt::UserRoot<double>, double>"};
+  JitFamily fam;
+  fam.kind = B200OPT_KIND_ROOT;
+  fam.n = n;
+  fam.shared_elems = shared_elems;
+  if (int e = compile_and_load(name, src, csrc_dir, kExpr, 2, fam)) return e;
+  fam.name = strdup(name);
+  g_families.push_back(fam);
+  return B200OPT_JIT_MODEL_BASE + (int)g_families.size() - 1;
+}
+
+int32_t b200opt_register_curve_family(const char* name, int32_t n, int32_t naux, const char* struct_body, const char* csrc_dir) {
+  if (!name || !struct_body || !csrc_dir || n < 1 || n > 16 || naux < 1 || naux > 8) {
+    set_error("register_curve_family: need a name, a struct body, the csrc directory, 1 <= n <= 16 and 1 <= naux <= 8");
+    return B200OPT_EINVAL;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (name_taken(name)) {
+    set_error("register_curve_family: a family named %s is already registered", name);
+    return B200OPT_EINVAL;
+  }
+  char head[512];
+  snprintf(head, sizeof(head),
+           "#include \"lsq_kernel.cuh\"\nnamespace b200opt {\ntemplate <typename T> struct UserModel {\n  static constexpr int N = %d;\n"
+           "  static constexpr int NAUX = %d;\n",
+           n, naux);
+  const std::string src = std::string(head) + struct_body + "\n};\n}  // namespace b200opt\n";
+  static const char* kExpr[4] = {
+      "b200opt::lsq_solve_kernel<b200opt::UserModel<float>, float, false>", "b200opt::lsq_solve_kernel<b200opt::UserModel<float>, float, true>",
+      "b200opt::lsq_solve_kernel<b200opt::UserModel<double>, double, false>",
+      "b200opt::lsq_solve_kernel<b200opt::UserModel<double>, double, true>"};
+  JitFamily fam;
+  fam.kind = B200OPT_KIND_LEAST_SQUARES;
+  fam.n = n;
+  fam.naux = naux;
+  if (int e = compile_and_load(name, src, csrc_dir, kExpr, 4, fam)) return e;
+  fam.name = strdup(name);
   g_families.push_back(fam);
   return B200OPT_JIT_MODEL_BASE + (int)g_families.size() - 1;
 }

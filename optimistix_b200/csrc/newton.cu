@@ -5,6 +5,9 @@
 
 namespace b200opt {
 int device_sm_count();
+int root_launch_jit(int model_id, int solver, int dtype, int64_t batch, int n, const void* y0, const void* shared, const void* prob,
+                    int64_t stride, const void* lower, const void* upper, const b200opt_options_t* o, void* y_out, int32_t* num_steps,
+                    int32_t* result, cudaStream_t stream);
 
 template <class Model, typename T>
 static int root_launch(int solver, int64_t batch, int n, const void* y0, const void* shared, const void* prob,
@@ -68,13 +71,22 @@ extern "C" int32_t b200opt_root_find(int32_t solver, int32_t model_id, int32_t d
     set_error("root_find: solver %d is not a root finder", solver);
     return B200OPT_EINVAL;
   }
-  if (model_id != MODEL_IMPLICIT_EULER) {
+  if (model_id != MODEL_IMPLICIT_EULER && model_id < B200OPT_JIT_MODEL_BASE) {
     set_error("root_find: model %d is not a root-finding family", model_id);
     return B200OPT_EINVAL;
   }
   if (dtype != B200OPT_F32 && dtype != B200OPT_F64) {
     set_error("root_find: unknown dtype %d", dtype);
     return B200OPT_EINVAL;
+  }
+  if (model_id >= B200OPT_JIT_MODEL_BASE) {  // run-time compiled family (b200opt_register_root_family)
+    if (batch == 0) return 0;
+    if (!y0 || !shared_args || !problem_args || !y_out || !num_steps || !result) {
+      set_error("root_find: NULL buffer");
+      return B200OPT_EINVAL;
+    }
+    return root_launch_jit(model_id, solver, dtype, batch, n, y0, shared_args, problem_args, problem_args_stride, lower, upper, opts, y_out,
+                           num_steps, result, static_cast<cudaStream_t>(stream));
   }
   if (problem_args_stride < n + 1) {
     set_error("root_find: implicit_euler needs problem_args_stride >= n + 1");

@@ -245,7 +245,7 @@ template <typename T> struct ImplicitEuler {
   }
 };
 
-template <class Model, typename T> constexpr size_t root_smem_bytes() {
+template <class Model, typename T> __host__ __device__ constexpr size_t root_smem_bytes() {
   // shared model data + per warp: y[N] + rowbuf[N + 4] (16B aligned) + piv[N]
   return sizeof(T) * Model::kSharedElems + kRootWarpsPerBlock * (sizeof(T) * (2 * Model::N + 4) + 32);
 }
@@ -289,10 +289,10 @@ __global__ void __launch_bounds__(kRootWarpsPerBlock * 32, ROOT_MINBLOCKS) root_
     bool terminate = false;  // init terminate is false in both modes (diff = inf / step = 0)
     int result = __all_sync(kFull, !act || t_finite(y)) ? RES_OK : RES_NONFINITE;
     if (p.chord && result == RES_OK) {  // :80-87 Jacobian linearised and factorised once, at y0
-      ys[lane] = y;
+      if (act) ys[lane] = y;
       __syncwarp();
-      T f;
-      Model::eval_row(sh, ys, ctx, lane, f, a, true);
+      T f = T(0);
+      if (act) Model::eval_row(sh, ys, ctx, lane, f, a, true);  // lanes >= N own no row (families with N < 32)
       __syncwarp();
       warp_lu_factor<T, N>(a, mycol, rinv, rowbuf, piv, lane);
     }
@@ -300,10 +300,10 @@ __global__ void __launch_bounds__(kRootWarpsPerBlock * 32, ROOT_MINBLOCKS) root_
     while (!terminate && result == RES_OK && steps < p.max_steps) {
       const bool y_old_finite = __all_sync(kFull, !act || t_finite(y));
       // ---- step (:103-152)
-      ys[lane] = y;
+      if (act) ys[lane] = y;
       __syncwarp();
-      T fx;
-      Model::eval_row(sh, ys, ctx, lane, fx, a, !p.chord);
+      T fx = T(0);
+      if (act) Model::eval_row(sh, ys, ctx, lane, fx, a, !p.chord);
       __syncwarp();
       if (!p.chord) warp_lu_factor<T, N>(a, mycol, rinv, rowbuf, piv, lane);
       const T sol = warp_lu_solve<T, N>(a, mycol, rinv, fx, piv, lane);

@@ -142,3 +142,74 @@ def test_registration_errors_are_loud():
         optx.models.register_curve_family("lorentz", 4, LORENTZ_SRC)
     with pytest.raises(_lib.B200OptError):
         optx.models.register_curve_family("too_big", 17, LORENTZ_SRC)
+
+
+# ---- run-time ROOT family: F_i(y) = y_i^3 + sum_j S_ij y_j - b_i, S shared (staged in shared memory), b per problem
+CUBIC_SRC = r"""
+  __device__ static __forceinline__ void eval_row(const T* sh, const T* ys, const Ctx& c, int lane, T& f, T (&row)[N], bool want_jac) {
+    const T yi = ys[lane];
+    T acc = yi * yi * yi - c.prob[lane];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const T s = sh[lane * N + j];
+      acc += s * ys[j];
+      if (want_jac) row[j] = s + (j == lane ? T(3) * yi * yi : T(0));
+    }
+    f = acc;
+  }
+"""
+_cubic = None
+
+
+def _cubic_family():
+    global _cubic
+    if _cubic is None:
+        _cubic = optx.models.register_root_family(
+            "cubic8", 8, CUBIC_SRC, shared_elems=64,
+            torch_fn=lambda y, a: y**3 + y @ a["shared"].reshape(8, 8).T - a["prob"])
+    return _cubic
+
+
+def _cubic_numpy(Smat):
+    def model(Y, args):
+        b = args
+        F = Y**3 + Y @ Smat.T - b
+        J = Smat[None, :, :] + 3.0 * Y[:, :, None] ** 2 * np.eye(Y.shape[1])[None]
+        return F.astype(Y.dtype), J.astype(Y.dtype)
+
+    return model
+
+
+@pytest.mark.parametrize("chord", (False, True), ids=("newton", "chord"))
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 1e-5)])
+def test_registered_root_family_vs_oracle(dtype, tol, chord):
+    fam = _cubic_family()
+    rng = np.random.default_rng(7)
+    B = 1000
+    Smat = (np.eye(8) * 3.0 + 0.3 * rng.standard_normal((8, 8))).astype(dtype)
+    b = rng.uniform(-2, 2, (B, 8)).astype(dtype)
+    y0 = np.zeros((B, 8), dtype)
+    solver = (optx.Chord if chord else optx.Newton)(tol, tol)
+    sol = optx.root_find(fam, solver, torch.as_tensor(y0, device=DEV), (torch.as_tensor(Smat.reshape(-1), device=DEV), torch.as_tensor(b, device=DEV)),
+                         throw=False, max_steps=512)
+    ref = S.newton_chord(_cubic_numpy(Smat), y0, b, rtol=tol, atol=tol, chord=chord, max_steps=512)
+    assert (to_np(sol.result) == ref["result"]).all()
+    if dtype == np.float64:
+        assert np.array_equal(to_np(sol.stats["num_steps"]), ref["num_steps"])  # identical iteration counts
+        assert np.allclose(to_np(sol.value), ref["value"], rtol=1e-10, atol=1e-12)
+    else:
+        assert np.mean(to_np(sol.stats["num_steps"]) == ref["num_steps"]) >= 0.95
+        assert np.allclose(to_np(sol.value), ref["value"], rtol=1e-3, atol=1e-4)
+    ok = ref["result"] == 0  # Chord (Jacobian frozen at y0 = 0) does not converge for every right-hand side
+    assert ok.mean() > (0.5 if chord else 0.99)
+    F = to_np(sol.value) ** 3 + to_np(sol.value) @ Smat.T - b
+    assert np.abs(F[ok]).max() < (1e-8 if dtype == np.float64 else 1e-3)
+    # host entry point gives the same bits; the generic step-kernel path the same roots
+    host = optx.root_find(fam, solver, y0, (Smat.reshape(-1), b), throw=False, max_steps=512)
+    assert np.array_equal(host.value, to_np(sol.value))
+    if dtype == np.float64 and not chord:
+        St = torch.as_tensor(Smat, device=DEV)
+        gen = optx.root_find(lambda y, a: y**3 + a[0] @ y - a[1], solver, torch.as_tensor(y0, device=DEV), (St, torch.as_tensor(b, device=DEV)),
+                             args_in_dims=(None, 0), throw=False, max_steps=512)
+        assert torch.equal(gen.stats["num_steps"], sol.stats["num_steps"])
+        assert torch.allclose(gen.value, sol.value, rtol=1e-10, atol=1e-12)
