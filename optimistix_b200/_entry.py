@@ -146,7 +146,7 @@ def _finish(buf, single, throw, value, num_steps, result, max_steps, extra_stats
                 f"{bad.size} of {res_host.size} solves failed; first failure (problem {int(bad[0])}): "
                 f"{RESULTS.name(code)}: {RESULTS[code]}"
             )
-    stats = {"num_steps": num_steps, "max_steps": max_steps}
+    stats = {"num_steps": num_steps, "max_steps": (None if max_steps is None or max_steps >= 2**31 - 1 else max_steps)}
     if extra_stats:
         stats.update(extra_stats)
     if single:
@@ -173,6 +173,28 @@ def _stream_ptr(buf, like):
     if not buf.device:
         return None
     return _torch().cuda.current_stream(like.device).cuda_stream
+
+
+_UNBOUNDED = 2**31 - 1  # max_steps=None (_iterate.py:194-268 with no bound): the kernels count steps in int32
+
+
+def _solve_with_aux(entry, fn, solver, y0, args, options, *, args_in_dims=None, **kw):
+    """has_aux=True (reference: fn returns (out, aux), Solution.aux carries the auxiliary output): solve with the first
+    output, then evaluate the auxiliary output once more at the returned value."""
+    if isinstance(fn, RegisteredModel):
+        raise NotImplementedError("has_aux=True: registered model families return no auxiliary output")
+    t = _torch()
+    sol = entry(lambda y, a: fn(y, a)[0], solver, y0, args, options, has_aux=False, args_in_dims=args_in_dims, **kw)
+    v = sol.value.detach()
+    if v.ndim == 1:
+        aux = fn(v, args)[1]
+    elif v.shape[0] == 0:
+        aux = None
+    elif args_in_dims is None:
+        aux = t.func.vmap(lambda y: fn(y, args)[1])(v)
+    else:
+        aux = t.func.vmap(lambda y, a: fn(y, a)[1], in_dims=(0, args_in_dims))(v, args)
+    return Solution(value=sol.value, result=sol.result, aux=aux, stats=sol.stats, state=sol.state)
 
 
 def _check_common(fn, options, has_aux, adjoint):
@@ -203,6 +225,9 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
                   adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), _root_near_zero=False, chunk: int = 0,
                   args_in_dims=None):
     """Solve (a batch of) nonlinear least-squares problems. Reference: optimistix/_least_squares.py:44-135."""
+    if has_aux:
+        return _solve_with_aux(least_squares, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw,
+                               tags=tags, _root_near_zero=_root_near_zero, chunk=chunk, args_in_dims=args_in_dims)
     if isinstance(solver, AbstractMinimiser):
         # _least_squares.py:36-41,102-114: minimise 0.5 * sum(residual^2)
         if isinstance(fn, RegisteredModel):
@@ -215,7 +240,7 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     _check_common(fn, options, has_aux, adjoint)
     _check_defaults(solver)
     if max_steps is None:
-        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+        max_steps = _UNBOUNDED
     if not isinstance(fn, RegisteredModel):
         from ._generic import least_squares_generic
 
@@ -271,9 +296,12 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
 def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
               adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, args_in_dims=None):
     """Solve (a batch of) root-finding problems. Reference: optimistix/_root_find.py:119-241."""
+    if has_aux:
+        return _solve_with_aux(root_find, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw,
+                               tags=tags, chunk=chunk, args_in_dims=args_in_dims)
     _check_common(fn, options, has_aux, adjoint)
     if max_steps is None:
-        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+        max_steps = _UNBOUNDED
     if isinstance(solver, AbstractLeastSquaresSolver):
         # _root_find.py:200-225: least-squares solver wrapped in _LstsqToRoot (extra `norm(f) < atol` test)
         return least_squares(fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw, _root_near_zero=True,
@@ -395,9 +423,12 @@ def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_s
 
     def _to_root_fn(y, a):  # _fixed_point.py:35-47
         out = fn(y, a)
+        aux = None
+        if has_aux:
+            out, aux = out
         if out.shape != y.shape:
             raise ValueError("The input and output of `fixed_point_fn` must have the same structure")
-        return out - y
+        return (out - y, aux) if has_aux else out - y
 
     return root_find(_to_root_fn, solver, y0, args, options, has_aux=has_aux, max_steps=max_steps, adjoint=adjoint, throw=throw,
                      args_in_dims=args_in_dims)
@@ -408,6 +439,9 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False,
              args_in_dims=None, _implicit=None):
     """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
+    if has_aux:
+        return _solve_with_aux(minimise, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags,
+                               chunk=chunk, return_hessian_inv=return_hessian_inv, args_in_dims=args_in_dims, _implicit=_implicit)
     _check_common(fn, options, has_aux, adjoint)
     if not isinstance(solver, (BFGS, DFP)):
         raise TypeError(f"minimise: unsupported solver {type(solver).__name__}")
@@ -416,14 +450,15 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
         from ._generic import minimise_generic
 
         return minimise_generic(fn, solver, y0, args, max_steps=max_steps, throw=throw, args_in_dims=args_in_dims,
-                                return_hessian_inv=return_hessian_inv, adjoint=adjoint, implicit=_implicit)
+                                return_hessian_inv=return_hessian_inv, adjoint=adjoint, implicit=_implicit,
+                                autodiff_mode=(options or {}).get("autodiff_mode", "bwd"))
     if fn.kind != KIND_MIN:
         raise TypeError(f"model {fn.name} is not a minimisation family")
     if isinstance(solver, DFP) or not solver.use_inverse:
         raise NotImplementedError("registered minimisation families run BFGS(use_inverse=True) in the persistent kernel; "
                                   "DFP / use_inverse=False take a Python callable (generic step kernel)")
     if max_steps is None:
-        raise NotImplementedError("max_steps=None (unbounded) is not supported by the persistent kernel")
+        max_steps = _UNBOUNDED
     lib = _lib.load()
     y0, buf, single = _prepare_y0(y0)
     B, n = y0.shape

@@ -118,7 +118,7 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
             code = int(rh[bad[0]])
             raise RuntimeError(f"{bad.size} of {rh.size} solves failed; first failure (problem {int(bad[0])}): "
                                f"{RESULTS.name(code)}: {RESULTS[code]}")
-    stats = {"num_steps": steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    stats = {"num_steps": steps, "max_steps": (None if max_steps is None or max_steps >= 2**31 - 1 else max_steps), "step_kernel_launches": launches}
     kind, ifn = implicit or ("root" if root_near_zero else "lstsq", fn)
     y = attach_if_needed(adjoint, kind, ifn, y, args, args_in_dims)
     value, result = y, res
@@ -191,7 +191,7 @@ def _empty_solution(Y0, max_steps):
     """A batch of zero problems: nothing to launch (and torch.func.vmap refuses an empty batch axis)."""
     t = _torch()
     z = t.zeros((0,), dtype=t.int32, device=Y0.device)
-    return Solution(value=Y0.clone(), result=z, aux=None, stats={"num_steps": z.clone(), "max_steps": max_steps}, state=None)
+    return Solution(value=Y0.clone(), result=z, aux=None, stats={"num_steps": z.clone(), "max_steps": (None if max_steps is None or max_steps >= 2**31 - 1 else max_steps)}, state=None)
 
 
 def _throw_if_failed(res):
@@ -294,13 +294,13 @@ def root_find_generic(fn, solver, y0, args, options, *, max_steps, throw, args_i
     _lib.check(lib.b200opt_root_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_root_step_finish")
     if throw:
         _throw_if_failed(res)
-    stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches}
+    stats = {"num_steps": steps[0] if single else steps, "max_steps": (None if max_steps is None or max_steps >= 2**31 - 1 else max_steps), "step_kernel_launches": launches}
     y = attach_if_needed(adjoint, "root", fn, y, args, args_in_dims)
     return Solution(value=y[0] if single else y, result=res[0] if single else res, aux=None, stats=stats, state=state)
 
 
 def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=None, root_fn=None, return_hessian_inv=False,
-                     adjoint=None, implicit=None):
+                     adjoint=None, implicit=None, autodiff_mode="bwd"):
     """BFGS (inverse Hessian, backtracking Armijo) for an arbitrary scalar `fn(y, args)`: torch evaluates f and its
     gradient (jax.linearize + linear_transpose at quasi_newton.py:214-227), `b200opt_bfgs_step` does the rest.
 
@@ -321,7 +321,10 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
         return out.reshape(())
 
     args_fwd = _detached(args)
-    gv = _vmapped(lambda y, a: t.func.grad_and_value(lambda z: one(z, a))(y), args_fwd, args_in_dims)
+    if autodiff_mode == "fwd":  # options["autodiff_mode"] (_misc.py:245-258): gradient by forward-mode JVPs
+        gv = _vmapped(lambda y, a: t.func.jacfwd(lambda z: (one(z, a), one(z, a)), has_aux=True)(y), args_fwd, args_in_dims)
+    else:
+        gv = _vmapped(lambda y, a: t.func.grad_and_value(lambda z: one(z, a))(y), args_fwd, args_in_dims)
     rootv = None
     if root_fn is not None:
         norm = solver.norm
@@ -362,7 +365,7 @@ def minimise_generic(fn, solver, y0, args, *, max_steps, throw, args_in_dims=Non
     _lib.check(lib.b200opt_bfgs_step_finish(dtype_code, B, n, state.data_ptr(), res.data_ptr(), stream), "b200opt_bfgs_step_finish")
     if throw:
         _throw_if_failed(res)
-    stats = {"num_steps": steps[0] if single else steps, "max_steps": max_steps, "step_kernel_launches": launches,
+    stats = {"num_steps": steps[0] if single else steps, "max_steps": (None if max_steps is None or max_steps >= 2**31 - 1 else max_steps), "step_kernel_launches": launches,
              "num_accepted_steps": state[:, n * n + 2 * n + 4].to(t.int32)}
     st = {"f": state[:, n * n + 2 * n], "grad": state[:, n * n : n * n + n]}
     if return_hessian_inv:

@@ -324,3 +324,29 @@ def test_generic_limits_are_reported():
         optx.minimise(lambda y, _: y, optx.BFGS(1e-8, 1e-8), torch.zeros(2, dtype=torch.float64, device=DEV))  # not a scalar
     sol = optx.minimise(lambda y, _: ((y - 2.0) ** 2).sum(), optx.BFGS(1e-8, 1e-8), torch.zeros(200, dtype=torch.float64, device=DEV))
     assert torch.allclose(sol.value, torch.full((200,), 2.0, dtype=torch.float64, device=DEV), atol=1e-6)  # n > 64: H^-1 in HBM
+
+
+# ---- has_aux, options["autodiff_mode"], max_steps=None (reference: _minimise.py:37-119, _misc.py:245-258, _iterate.py:194-268)
+def test_has_aux_autodiff_mode_and_unbounded_steps():
+    y0 = torch.tensor([2.0, 0.0], dtype=torch.float64, device=DEV)
+    args = (1.5, 2.25, 2.625)
+    a = optx.minimise(F.beale, optx.BFGS(1e-8, 1e-8), y0, args, max_steps=None)  # unbounded, like compat.minimize without maxiter
+    b = optx.minimise(F.beale, optx.BFGS(1e-8, 1e-8), y0, args, options=dict(autodiff_mode="fwd"), max_steps=10_000)
+    assert np.allclose(to_np(a.value), [3.0, 0.5], rtol=1e-5, atol=1e-5) and a.stats["max_steps"] is None
+    assert torch.allclose(a.value, b.value, rtol=1e-8, atol=1e-10)
+    # has_aux: fn returns (out, aux); Solution.aux is the auxiliary output at the solution
+    sol = optx.minimise(lambda y, c: (F.beale(y, c), y * 2.0), optx.BFGS(1e-8, 1e-8), y0, args, has_aux=True, max_steps=10_000)
+    assert torch.allclose(sol.aux, 2.0 * sol.value) and torch.allclose(sol.value, a.value)
+    ys = torch.ones(5, 1, dtype=torch.float64, device=DEV)
+    cs = torch.arange(2.0, 7.0, dtype=torch.float64, device=DEV)
+    sol = optx.root_find(lambda y, c: (y * y - c, {"residual": y * y - c, "c": c}), optx.Newton(1e-10, 1e-10), ys, cs, has_aux=True,
+                         args_in_dims=0)
+    assert torch.allclose(sol.value[:, 0], cs.sqrt()) and torch.allclose(sol.aux["c"], cs) and float(sol.aux["residual"].abs().max()) < 1e-9
+    sol = optx.least_squares(lambda y, _: (y - 3.0, y.sum()), optx.GaussNewton(1e-5, 1e-5), torch.zeros(2, dtype=torch.float64, device=DEV),
+                             has_aux=True, max_steps=None)
+    assert torch.equal(sol.value, torch.full((2,), 3.0, dtype=torch.float64, device=DEV)) and float(sol.aux) == 6.0
+    sol = optx.fixed_point(lambda y, c: (torch.cos(c * y), c), optx.Newton(1e-10, 1e-10), torch.full((3,), 0.5, dtype=torch.float64, device=DEV),
+                           torch.tensor(1.0, dtype=torch.float64, device=DEV), has_aux=True)
+    assert torch.allclose(torch.cos(sol.value), sol.value, atol=1e-9) and float(sol.aux) == 1.0
+    with pytest.raises(NotImplementedError):
+        optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), torch.zeros(4, dtype=torch.float64, device=DEV), has_aux=True)
