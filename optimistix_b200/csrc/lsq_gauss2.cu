@@ -29,28 +29,6 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
 }
 
-// half-warp-per-problem variant (lsq_solve_kernel_p2h): m is a template parameter
-template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2h(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2h<PModel, TRUST, NPAIRS>;
-  constexpr int M = NPAIRS * 32;
-  const size_t per_warp = HalfReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)2 * (3 + PModel::NAUX) * M;
-  const size_t smem = sizeof(float) * ((size_t)M + kLsqWarpsPerBlock * per_warp);
-  static thread_local bool attr_set = false;
-  static thread_local int blocks_per_sm = 1;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy")) return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-    attr_set = true;
-  }
-  const int64_t need = (p.batch + 2 * kLsqWarpsPerBlock - 1) / (2 * kLsqWarpsPerBlock);
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
-  const int grid = (int)(need < cap ? need : cap);
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2h launch");
-}
-
 int lsq_launch_gauss2(const LsqArgs& a) {
   static const bool scalar_only = getenv("B200OPT_LSQ_SCALAR") != nullptr;  // A/B switch for profiling
   const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
@@ -77,9 +55,7 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.vec_ok = 1;
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
     int rc;
-    static const bool full_warp = getenv("B200OPT_LSQ_FULLWARP") != nullptr;  // A/B switch: one problem per warp
-    if (a.m == 256 && !full_warp) rc = lm ? lsq_launch_p2h<Gauss2P2, true, 8>(p, a.stream) : lsq_launch_p2h<Gauss2P2, false, 8>(p, a.stream);
-    else if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
+    if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
     else rc = lm ? lsq_launch_p2<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 0>(p, a.stream);
     if (rc >= 0) return rc;
   }

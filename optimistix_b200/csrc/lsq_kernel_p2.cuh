@@ -302,244 +302,8 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Half-warp-per-problem variant.  In the kernel above every lane of a warp repeats the 8 x 8 algebra of its problem (the
-// predicted reduction, the damped Cholesky solve, the bookkeeping: ~560 of the 957 instructions of a step).  Here the two
-// halves of a warp own two DIFFERENT problems: the same instructions do that algebra for both, so its cost per problem
-// halves, while the row sweeps keep their cost (16 lanes x 2 packed rows x NPAIRS = m rows per problem).  Accept / reject
-// and the iteration count may differ between the halves: the branches simply diverge (SIMT), and every warp-level
-// primitive inside them is restricted to the 16 lanes of its own problem (`hmask`).
-template <typename T, int K> struct HalfReduceLayout {  // WarpReduceLayout with one totals line per half-warp
-  using L = WarpReduceLayout<T, K>;
-  static constexpr int elems = 32 * L::KP + 2 * L::KPAD;
-};
-
-template <typename T, int K> __device__ __forceinline__ void half_allreduce_array(T (&v)[K], T* sm, int lane, unsigned hmask) {
-  using L = WarpReduceLayout<T, K>;
-  using Vec = typename Num<T>::Vec;
-  constexpr int V = L::V;
-  static_assert(L::KQ <= 16, "one quad-column per lane of the half-warp");
-  const int half = lane >> 4, hl = lane & 15;
-  T* row = sm + lane * L::KP;
-#pragma unroll
-  for (int q = 0; q < L::KQ; ++q) {
-    Vec w;
-    T* ww = reinterpret_cast<T*>(&w);
-#pragma unroll
-    for (int e = 0; e < V; ++e) ww[e] = (q * V + e < K) ? v[q * V + e] : T(0);
-    *reinterpret_cast<Vec*>(row + q * V) = w;
-  }
-  __syncwarp(hmask);
-  T* tot = sm + 32 * L::KP + half * L::KPAD;
-  if (hl < L::KQ) {  // lane hl sums quad-column hl over the 16 rows of its half, in row order (deterministic)
-    T a[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) a[e] = T(0);
-#pragma unroll
-    for (int l = 0; l < 16; ++l) {
-      const Vec w = *reinterpret_cast<const Vec*>(sm + (half * 16 + l) * L::KP + hl * V);
-      const T* ww = reinterpret_cast<const T*>(&w);
-#pragma unroll
-      for (int e = 0; e < V; ++e) a[e] += ww[e];
-    }
-    Vec w;
-    T* ww = reinterpret_cast<T*>(&w);
-#pragma unroll
-    for (int e = 0; e < V; ++e) ww[e] = a[e];
-    *reinterpret_cast<Vec*>(tot + hl * V) = w;
-  }
-  __syncwarp(hmask);
-#pragma unroll
-  for (int q = 0; q < L::KQ; ++q) {
-    const Vec w = *reinterpret_cast<const Vec*>(tot + q * V);
-    const T* ww = reinterpret_cast<const T*>(&w);
-#pragma unroll
-    for (int e = 0; e < V; ++e)
-      if (q * V + e < K) v[q * V + e] = ww[e];
-  }
-  __syncwarp(hmask);
-}
-
-__device__ __forceinline__ float half_sum(float v, unsigned hmask) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(hmask, v, o);
-  return v;
-}
-
-// NPAIRS = m / 32 row pairs per lane (compile time; 8 for m = 256)
-template <class PModel, bool TRUST, int NPAIRS>
-__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, 3) lsq_solve_kernel_p2h(const LsqParams<float> p) {
-  using T = float;
-  constexpr int N = PModel::N;
-  constexpr int NG = Tri<N>::size;
-  constexpr int NAUX = PModel::NAUX;
-  constexpr int M = NPAIRS * 32;  // rows per problem
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int half = lane >> 4, hl = lane & 15;
-  const unsigned hmask = 0xFFFFu << (16 * half);
-  constexpr int SCR = HalfReduceLayout<T, NG + N>::elems;
-  T* xs = reinterpret_cast<T*>(smem_raw);
-  T* wbase = xs + M + (size_t)wib * (SCR + (size_t)2 * (3 + NAUX) * M);
-  T* scratch = wbase;
-  T* ds = wbase + SCR + (size_t)half * (3 + NAUX) * M;  // this half's problem: data | residual A | residual B | aux[NAUX]
-  T* racc = ds + M;
-  T* rtry = racc + M;
-  T* auxs = rtry + M;
-  const T rtol = p.rtol, atol = p.atol;
-
-  for (int i = threadIdx.x; i < M; i += blockDim.x) xs[i] = p.shared[i];
-  __syncthreads();
-  const float2* xs2 = reinterpret_cast<const float2*>(xs);
-  const float2* ds2 = reinterpret_cast<const float2*>(ds);
-
-  const int64_t first = ((int64_t)blockIdx.x * kLsqWarpsPerBlock + wib) * 2 + half;
-  const int64_t stride = (int64_t)gridDim.x * kLsqWarpsPerBlock * 2;
-  for (int64_t prob = first; prob < p.batch; prob += stride) {
-    T y[N], ye[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);
-    const T* drow = p.prob + prob * p.prob_stride;
-#pragma unroll
-    for (int i = hl; i < M / 4; i += 16) reinterpret_cast<float4*>(ds)[i] = __ldg(reinterpret_cast<const float4*>(drow) + i);
-#pragma unroll
-    for (int i = hl; i < M / 4; i += 16) reinterpret_cast<float4*>(racc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp(hmask);
-
-    T G[NG], g[N];
-#pragma unroll
-    for (int a = 0; a < NG; ++a) G[a] = T(0);
-#pragma unroll
-    for (int j = 0; j < N; ++j) g[j] = T(0);
-    T rr = T(0);
-    T delta = T(1);
-    bool first_step = true, terminate = false;
-    bool yfin = true;
-#pragma unroll
-    for (int j = 0; j < N; ++j) yfin = yfin && t_finite(y[j]);
-    int result = yfin ? RES_OK : RES_NONFINITE;
-    int steps = 0, naccept = 0;
-
-    while (!terminate && result == RES_OK && steps < p.max_steps) {
-      bool y_old_finite = true;
-#pragma unroll
-      for (int j = 0; j < N; ++j) y_old_finite = y_old_finite && t_finite(y[j]);
-
-      // ---- residual at the trial point (gauss_newton.py:253): 16 lanes x 2 packed rows x NPAIRS
-      const typename PModel::Consts pc = PModel::prepare(ye);
-      float2 part = make_float2(0.f, 0.f);
-      float2* rtry2 = reinterpret_cast<float2*>(rtry);
-      float2* auxs2 = reinterpret_cast<float2*>(auxs);
-#pragma unroll
-      for (int k = 0; k < NPAIRS; ++k) {
-        const int idx = k * 16 + hl;
-        float2 aux[NAUX];
-        const float2 r = PModel::residual(pc, xs2[idx], ds2[idx], aux);
-        rtry2[idx] = r;
-#pragma unroll
-        for (int q = 0; q < NAUX; ++q) auxs2[q * (M >> 1) + idx] = aux[q];
-        part = fma2(r, r, part);
-      }
-      const T rre = half_sum(part.x + part.y, hmask);
-
-      T d[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) d[j] = ye[j] - y[j];
-
-      // ---- search (trust_region.py:86-104 / learning_rate.py:24-35)
-      bool accept = true;
-      if (TRUST) {
-        T lin = T(0), quad = T(0);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          T gd = T(0);
-#pragma unroll
-          for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
-          quad += d[i] * gd;
-          lin += d[i] * g[i];
-        }
-        const T pred = lin + T(0.5) * quad;
-        const T df = T(0.5) * rre - T(0.5) * rr;
-        accept = (df <= T(0.01) * pred) || first_step;
-        const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first_step;
-        delta *= accept ? (good ? T(3.5) : T(1)) : T(0.25);
-      } else {
-        delta = T(1);
-      }
-
-      if (accept) {  // may diverge between the two halves of the warp
-        bool yconv = true;
-#pragma unroll
-        for (int j = 0; j < N; ++j) yconv = yconv && (t_abs(d[j]) < atol + rtol * t_abs(ye[j]));
-        ++naccept;
-#pragma unroll
-        for (int j = 0; j < N; ++j) y[j] = ye[j];
-        rr = rre;
-        float2 acc2[NG + N];
-        bool fconv = true;
-        const float2* racc2 = reinterpret_cast<const float2*>(racc);
-#pragma unroll
-        for (int k = 0; k < NPAIRS; ++k) {
-          const int idx = k * 16 + hl;
-          float2 aux[NAUX], j[N];
-#pragma unroll
-          for (int q = 0; q < NAUX; ++q) aux[q] = auxs2[q * (M >> 1) + idx];
-          const float2 re = rtry2[idx], ro = racc2[idx];
-          PModel::jac(pc, xs2[idx], aux, j);
-#pragma unroll
-          for (int a = 0; a < N; ++a) {
-#pragma unroll
-            for (int b = 0; b <= a; ++b) acc2[Tri<N>::at(a, b)] = (k == 0) ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
-            acc2[NG + a] = (k == 0) ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
-          }
-          fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
-        }
-        T acc[NG + N];
-#pragma unroll
-        for (int a = 0; a < NG + N; ++a) acc[a] = acc2[a].x + acc2[a].y;
-        half_allreduce_array<T, NG + N>(acc, scratch, lane, hmask);
-#pragma unroll
-        for (int a = 0; a < NG; ++a) G[a] = acc[a];
-#pragma unroll
-        for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
-        fconv = (__ballot_sync(hmask, fconv) & hmask) == hmask;
-        terminate = yconv && fconv;
-        T* t = racc;
-        racc = rtry;
-        rtry = t;
-      } else {
-        terminate = false;
-      }
-
-      // ---- descent (levenberg_marquardt.py:55-57,66-75,132 / gauss_newton.py:64-78,126-127)
-      T lam = T(0);
-      if (TRUST) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
-      T pstep[N];
-      spd_solve<T, N>(G, lam, g, pstep);
-      bool pfin = true;
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        pfin = pfin && t_finite(pstep[j]);
-        ye[j] = y[j] - pstep[j];
-      }
-      result = pfin ? RES_OK : RES_SINGULAR;
-      if (!y_old_finite) result = RES_NONFINITE;
-      first_step = false;
-      ++steps;
-    }
-    if (result == RES_OK && !terminate) result = RES_NL_MAX_STEPS;
-
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (hl == j) p.y_out[prob * N + j] = y[j];
-    if (hl == 0) {
-      p.num_steps[prob] = steps;
-      p.result[prob] = result;
-      if (p.step_size_out) p.step_size_out[prob] = delta;
-      if (p.num_accepted) p.num_accepted[prob] = naccept;
-    }
-    __syncwarp(hmask);
-  }
-}
+// (A half-warp-per-problem variant - two problems per warp sharing the replicated 8 x 8 algebra - was measured and dropped:
+// 10% fewer instructions but only 22.8 of 32 lanes active on average (accept / reject and iteration counts differ between the
+// two problems) and 12 instead of 16 warps per SM: 16.8 ms against 15.6 ms for 1 Mi fits.  See git history and profiles/README.md.)
 
 }  // namespace b200opt
