@@ -184,7 +184,7 @@ def bench_gram(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from optimistix_b200._gn_large import N, OUT_FLOATS, CudaOps
+    from optimistix_b200._gn_large import N, OUT_FLOATS, CudaOps, PeerExchange
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -217,8 +217,16 @@ def bench_gram(args, rank, world, local_rank):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
 
     fused = not args.unfused
+    xchg = None
+    if world > 1 and fused and args.exchange == "peer":
+        xchg = PeerExchange(dev)  # CUDA IPC mapping of every rank's exchange buffer; handles swapped once through torch.distributed
 
     def step():
+        if xchg is not None:
+            parity, seq = xchg.next()
+            ops.residual_gram_xchg(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out, xchg, parity, seq)  # Gram + publication over NVLink
+            ops.solve_xchg(xchg, parity, seq, 0.0, p, status, summary)                            # wait for all flags, sum, solve
+            return
         if fused:
             ops.residual_gram(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out)
         else:
@@ -246,14 +254,20 @@ def bench_gram(args, rank, world, local_rank):
         if not fused:
             ops.residual(J, y, d, r, r_old, 1e-4, 1e-4, fmax)
         ev[1].record()
-        if fused:
+        if xchg is not None:
+            parity, seq = xchg.next()
+            ops.residual_gram_xchg(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out, xchg, parity, seq)
+        elif fused:
             ops.residual_gram(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out)
         else:
             ops.gram(J, r, out)
         ev[2].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-        ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)
+        if xchg is not None:
+            ops.solve_xchg(xchg, parity, seq, 0.0, p, status, summary)
+        else:
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out)
+            ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)
         ev[3].record()
         torch.cuda.synchronize()
         t_res += ev[0].elapsed_time(ev[1])
@@ -304,7 +318,10 @@ def bench_gram(args, rank, world, local_rank):
                 "vs_baseline": None, "dtype": "tf32 x tf32 -> f32 (TMEM)", "data": "synthetic",
                 "config": {"workload": "GaussNewton least squares, J materialised row-major in HBM (BASELINE configs[4])", "rows_total": rows,
                            "fused_residual": fused,
-                           "rows_per_gpu": m_local, "n": N, "parallelism": f"row-sharded x{world}, one all-gather of {N * N + N + 2} floats per rank per iteration, summed in rank order inside the solve kernel",
+                           "rows_per_gpu": m_local, "n": N, "parallelism": (f"row-sharded x{world}; per iteration each rank's {N * N + N + 2}-float block is "
+                                           + ("stored into every peer's exchange buffer by the Gram reduction kernel (P2P over NVLink, flag-signalled)"
+                                              if xchg is not None else "all-gathered (NCCL)")
+                                           + ", summed in rank order inside the solve kernel"),
                            "l2": "J shard (>= 8 GB) exceeds the 126 MB L2"},
                 "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_gram / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg_bytes / (ms_gram / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note,
@@ -315,6 +332,9 @@ def bench_gram(args, rank, world, local_rank):
                 "breakdown_ms": {"residual_pass": ms_res, "gram": ms_gram, "allgather+solve": ms - ms_res - ms_gram},
                 "gpu_launches": (3 if fused else 4) * K, "clocks": clocks, "checks": checks, "cpu_baseline": None, "e2e": None}
         print(json.dumps(line))
+    if xchg is not None:
+        barrier()
+        xchg.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -359,6 +379,8 @@ def main():
     ap.add_argument("--rows", type=int, default=64 << 20, help="gram workload: total rows of J over all ranks")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the BASELINE config)")
     ap.add_argument("--chunk", type=int, default=1 << 15, help="problems per pipeline stage in the host entry point")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="gram workload, N > 1: peer = our kernels exchange the Gram blocks over peer memory; nccl = all_gather_into_tensor")
     ap.add_argument("--unfused", action="store_true", help="gram workload: separate residual pass (J read twice per iteration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -53,6 +53,7 @@ extern "C" {
 #define B200OPT_EINVAL (-1)   /* bad argument (unknown model/dtype/solver, n or m not supported by the model) */
 #define B200OPT_ECUDA (-2)    /* CUDA runtime error (launch failure, out of memory in a _host call) */
 #define B200OPT_ENOTIMPL (-3) /* combination not compiled into this build */
+#define B200OPT_EXCHANGE_TIMEOUT (-4) /* device-side status: a peer of the row-sharded exchange never published its block */
 
 /* dtype of y / args / outputs: the arithmetic type of the whole solve (jax_enable_x64 analogue) */
 #define B200OPT_F32 0
@@ -275,6 +276,26 @@ int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float*
  * total r^T r and the maximum f-statistic.  nparts == 1 needs no f-statistic slot unless summary_out is given. */
 int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda,
                                float* p_out, int32_t* status_out, float* summary_out, void* workspace, void* stream);
+/* ---- peer-memory exchange of the row-sharded problem: the collective INSIDE our own kernels (no NCCL on the data path) ----
+ * Every rank owns one exchange buffer (b200opt_xchg_bytes bytes, cudaMalloc'ed by b200opt_xchg_alloc, which also returns
+ * its 64-byte CUDA IPC handle).  The ranks swap handles out of band (torch.distributed all_gather_object), map each other's
+ * buffers with b200opt_xchg_open and put the `world` base pointers (own buffer = the local pointer) into a device array.
+ * b200opt_gn_gram_linear_xchg is b200opt_gn_gram_linear whose reduction kernel also stores this rank's
+ * [G | g | r^T r | f-statistic] block into its slot of EVERY peer's buffer (P2P stores over NVLink / NVSwitch) and, from the
+ * last CTA, raises this rank's flag there (sequence number `seq`, slot parity `parity` = seq & 1).  b200opt_gn_solve_xchg is
+ * b200opt_gn_solve_parts on the local buffer after a bounded wait for all `world` flags; on time-out *status_out becomes
+ * B200OPT_EXCHANGE_TIMEOUT.  `out` must have n*n+n+2 floats and fmax_bits must point at its last slot. */
+int64_t b200opt_xchg_bytes(int32_t world, int32_t n);
+int32_t b200opt_xchg_alloc(int64_t bytes, void** ptr_out, void* ipc_handle_out);
+int32_t b200opt_xchg_open(const void* ipc_handle, void** ptr_out);
+int32_t b200opt_xchg_close(void* ptr);
+int32_t b200opt_xchg_free(void* ptr);
+int32_t b200opt_gn_gram_linear_xchg(const float* J, const float* y, const float* d, const float* r_old, float* r_out,
+                                    uint32_t* fmax_bits, float rtol, float atol, int64_t m_local, int32_t n, float* out,
+                                    void* workspace, const void* const* xchg_bases_dev, int32_t world, int32_t rank,
+                                    int32_t parity, uint32_t seq, void* stream);
+int32_t b200opt_gn_solve_xchg(const void* xchg_local, int32_t world, int32_t parity, uint32_t seq, int32_t n, double lambda,
+                              float* p_out, int32_t* status_out, float* summary_out, void* workspace, void* stream);
 /* r = J y - d for the "linear_rows" family (one coalesced pass over the row shard). If r_old is not NULL the
  * f-space half of cauchy_termination (optimistix/_misc.py:306-309) is fused in: *fmax_bits (device, caller-zeroed)
  * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */

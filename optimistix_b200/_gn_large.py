@@ -65,6 +65,21 @@ class CudaOps:
                                                    self._stream()), "b200opt_gn_gram_linear")
         self.launches += 2
 
+    def residual_gram_xchg(self, J, y, d, r_out, r_old, rtol, atol, fmax, out, xchg, parity, seq):
+        """residual_gram + publication of this rank's block into every peer's exchange buffer (same two kernels)."""
+        fmax.zero_()
+        _lib.check(self.lib.b200opt_gn_gram_linear_xchg(J.data_ptr(), y.data_ptr(), d.data_ptr(),
+                                                        r_old.data_ptr() if r_old is not None else None, r_out.data_ptr(),
+                                                        fmax.data_ptr(), rtol, atol, J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+                                                        xchg.bases.data_ptr(), xchg.world, xchg.rank, parity, seq, self._stream()),
+                   "b200opt_gn_gram_linear_xchg")
+        self.launches += 2
+
+    def solve_xchg(self, xchg, parity, seq, lam, p, status, summary):
+        _lib.check(self.lib.b200opt_gn_solve_xchg(xchg.local, xchg.world, parity, seq, N, float(lam), p.data_ptr(), status.data_ptr(),
+                                                  summary.data_ptr(), self.ws.data_ptr(), self._stream()), "b200opt_gn_solve_xchg")
+        self.launches += 1
+
     def solve(self, out, lam, p, status):
         _lib.check(self.lib.b200opt_gn_solve(out.data_ptr(), N, float(lam), p.data_ptr(), status.data_ptr(), self.ws.data_ptr(),
                                              self._stream()), "b200opt_gn_solve")
@@ -78,11 +93,66 @@ class CudaOps:
         self.launches += 1
 
 
-def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None, fused=True):
+class PeerExchange:
+    """The collective of the row-sharded problem done by our own kernels over peer memory (NVLink / NVSwitch): every rank
+    owns one exchange buffer, mapped into all peers with CUDA IPC; `b200opt_gn_gram_linear_xchg` stores this rank's
+    [G | g | rr | f-stat] block into every peer's buffer and raises a flag, `b200opt_gn_solve_xchg` waits for all flags
+    and sums the blocks in rank order.  torch.distributed is used ONCE, to swap the 64-byte IPC handles."""
+
+    def __init__(self, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.lib = _lib.load()
+        self.t = torch
+        self.device = device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = self.lib.b200opt_xchg_bytes(self.world, N)
+        if nbytes <= 0:
+            raise _lib.B200OptError("b200opt_xchg_bytes failed")
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(self.lib.b200opt_xchg_alloc(nbytes, C.byref(ptr), handle), "b200opt_xchg_alloc")
+        self.local = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peers = []
+        bases = []
+        with torch.cuda.device(device):
+            for q in range(self.world):
+                if q == self.rank:
+                    bases.append(self.local)
+                    continue
+                pp = C.c_void_p()
+                _lib.check(self.lib.b200opt_xchg_open(handles[q], C.byref(pp)), "b200opt_xchg_open")
+                self.peers.append(pp.value)
+                bases.append(pp.value)
+        self.bases = torch.tensor(bases, dtype=torch.int64, device=device)
+        self.seq = 0
+        dist.barrier(group=group)  # every buffer is zeroed and mapped before anybody publishes
+
+    def next(self):
+        self.seq += 1
+        return self.seq & 1, self.seq
+
+    def close(self):
+        for pp in self.peers:
+            self.lib.b200opt_xchg_close(pp)
+        self.peers = []
+        if self.local:
+            self.lib.b200opt_xchg_free(self.local)
+            self.local = None
+
+
+def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None, fused=True, exchange="peer"):
     """Solve min_y |J y - d|^2 with this rank's row shard (J [m_local, 256] fp32, d [m_local]); returns a Solution.
 
     `group`: a torch.distributed process group (None = the default group if initialised, else single rank).
-    `fused`: form the residual inside the Gram kernel (J is read once per iteration) when `ops` offers it."""
+    `fused`: form the residual inside the Gram kernel (J is read once per iteration) when `ops` offers it.
+    `exchange`: "peer" = the per-iteration exchange is done by our kernels over peer memory (PeerExchange; falls back to
+    "nccl" = one all_gather_into_tensor per iteration when CUDA IPC is not available or `ops` has no kernels for it)."""
     import torch
     import torch.distributed as dist
 
@@ -109,7 +179,26 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     out = torch.empty(OUT_FLOATS, dtype=torch.float32, device=dev)  # [G | g | rr | f-stat]: what one rank contributes
     fmax = out[N * N + N + 1:].view(torch.int32)  # IEEE bits of a non-negative float: integer max == float max
     world = dist.get_world_size(group) if distributed else 1
-    gathered = torch.empty(world * OUT_FLOATS, dtype=torch.float32, device=dev) if distributed else out
+    xchg = None
+    if distributed and exchange == "peer" and fused and hasattr(ops, "residual_gram_xchg"):
+        xchg = getattr(ops, "_xchg", None)
+        if xchg is None:
+            # collective decision: either every rank maps every peer, or all fall back to NCCL
+            try:
+                xchg = PeerExchange(dev, group)
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather")
+                xchg, ok = None, torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if xchg is not None:
+                    xchg.close()
+                xchg = None
+            ops._xchg = xchg
+    gathered = torch.empty(world * OUT_FLOATS, dtype=torch.float32, device=dev) if (distributed and xchg is None) else out
     summary = torch.zeros(2, dtype=torch.float32, device=dev)  # total r^T r, max f-stat
     p = torch.empty(N, dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -118,14 +207,20 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     steps = 0
     while not terminate and result == RESULTS.successful and steps < max_steps:
         y_fin_t = torch.isfinite(y).all()  # _iterate.py:216,238: finiteness of the carry's y from BEFORE this step
-        if fused:
+        if xchg is not None:
+            parity, seq = xchg.next()
+            ops.residual_gram_xchg(J, y_eval, d, r_new, r_old, rtol, atol, fmax, out, xchg, parity, seq)
+        elif fused:
             ops.residual_gram(J, y_eval, d, r_new, r_old, rtol, atol, fmax, out)  # one read of J per iteration
         else:
             ops.residual(J, y_eval, d, r_new, r_old, rtol, atol, fmax)  # gauss_newton.py:253 + f-space half of :280-288
             ops.gram(J, r_new, out)
-        if distributed:
-            dist.all_gather_into_tensor(gathered, out, group=group)  # the only exchange of the iteration
-        ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)  # NewtonDescent.query: newton = G^-1 g
+        if xchg is not None:
+            ops.solve_xchg(xchg, parity, seq, 0.0, p, status, summary)  # waits for every rank's flag, then as below
+        else:
+            if distributed:
+                dist.all_gather_into_tensor(gathered, out, group=group)  # the only exchange of the iteration
+            ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)  # NewtonDescent.query: newton = G^-1 g
         y_diff = y_eval - y
         y_conv_t = (y_diff.abs() / (atol + rtol * y_eval.abs())).max() < 1  # _misc.py:306-308
         f_conv_t = summary[1] < 1  # NaN compares false, like jnp.max
@@ -137,6 +232,8 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
         y_eval = y - p  # gauss_newton.py:126-127 with step_size 1
         r_old, r_new = r_new, r_old
         # `result` is the linear solve's (gauss_newton.py:316-318)
+        if result < 0:
+            raise _lib.B200OptError("peer exchange timed out: a rank never published its block of the normal equations")
         if not y_old_finite:
             result = RESULTS.nonfinite
         steps += 1

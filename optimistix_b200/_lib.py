@@ -87,6 +87,14 @@ _SIGNATURES = {
     "b200opt_gn_gram_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i64, _i32, _vp, _vp, _vp]),
     "b200opt_gn_solve": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp, _vp]),
     "b200opt_gn_solve_parts": (_i32, [_vp, _i32, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "b200opt_xchg_bytes": (_i64, [_i32, _i32]),
+    "b200opt_xchg_alloc": (_i32, [_i64, C.POINTER(_vp), _vp]),
+    "b200opt_xchg_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "b200opt_xchg_close": (_i32, [_vp]),
+    "b200opt_xchg_free": (_i32, [_vp]),
+    "b200opt_gn_gram_linear_xchg": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
+                                          C.c_uint32, _vp]),
+    "b200opt_gn_solve_xchg": (_i32, [_vp, _i32, _i32, C.c_uint32, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_linear_residual": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, C.c_float, C.c_float, _vp, _vp]),
 }
 

@@ -25,8 +25,11 @@ constexpr size_t SOLVE_SMEM = (size_t)(256 * SOLVE_LD + 3 * 256 + 3 * SOLVE_PW +
 // `parts` row-shard partials [G | g | rr | f-statistic bits] (stride `part_stride` floats) are summed here, in rank order
 // and in fp64, so that after ONE all-gather every rank holds bit-identical normal equations (and the max of the
 // f-space termination statistic) without a second collective.
+// `flags` (optional): the peer-exchange flags of this iteration's parity; the kernel first waits until every rank has
+// published sequence number `seq` (bounded spin: a missing peer becomes an error code, not a hang).
 __global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out, int nparts, int64_t part_stride, int n, double lambda,
-                                                           double* A, float* p_out, int32_t* status, float* summary) {
+                                                           double* A, float* p_out, int32_t* status, float* summary,
+                                                           const unsigned* flags, unsigned seq) {
   extern __shared__ double sm[];
   double* Lp = sm;                          // [256][SOLVE_LD] finished panel of the factor (rows c0..n-1 used)
   double* z = Lp + 256 * SOLVE_LD;          // [256] right-hand side -> L^-1 g
@@ -35,26 +38,46 @@ __global__ void __launch_bounds__(1024, 1) gn_solve_kernel(const float* gram_out
   double* zs = pv + 256;                    // [SOLVE_PW] panel right-hand side of the backward sweep
   double* colbuf = zs + SOLVE_PW;           // [2][SOLVE_PW] unscaled column of the diagonal block (ping-pong)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  if (flags) {
+    int ok = 1;
+    if (tid < nparts) {
+      const volatile unsigned* f = flags + tid;
+      const long long t0 = clock64();
+      while (*f != seq) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never published
+          ok = 0;
+          break;
+        }
+      }
+    }
+    __threadfence_system();  // acquire: the peers' stores that preceded their flags are visible to the loads below
+    ok = __syncthreads_and(ok);
+    if (!ok) {
+      if (tid == 0 && status) *status = B200OPT_EXCHANGE_TIMEOUT;
+      return;
+    }
+  }
   // lower triangle of G + lambda I in fp64
   for (int e = tid; e < n * n; e += nt) {
     const int i = e / n, j = e - i * n;
     if (j <= i) {
       double acc = 0.0;
-      for (int q = 0; q < nparts; ++q) acc += (double)gram_out[q * part_stride + e];
+      for (int q = 0; q < nparts; ++q) acc += (double)__ldcg(gram_out + q * part_stride + e);  // L2: peers write these
       A[e] = acc + (i == j ? lambda : 0.0);
     }
   }
   for (int i = tid; i < n; i += nt) {
     double acc = 0.0;
-    for (int q = 0; q < nparts; ++q) acc += (double)gram_out[q * part_stride + n * n + i];
+    for (int q = 0; q < nparts; ++q) acc += (double)__ldcg(gram_out + q * part_stride + n * n + i);
     z[i] = acc;
   }
   if (summary && tid == 0) {
     double rr = 0.0;
     float fs = 0.f;
     for (int q = 0; q < nparts; ++q) {
-      rr += (double)gram_out[q * part_stride + n * n + n];
-      fs = nan_max(fs, gram_out[q * part_stride + n * n + n + 1]);
+      rr += (double)__ldcg(gram_out + q * part_stride + n * n + n);
+      fs = nan_max(fs, __ldcg(gram_out + q * part_stride + n * n + n + 1));
     }
     summary[0] = (float)rr;
     summary[1] = fs;
@@ -251,8 +274,9 @@ int32_t b200opt_gn_solve(const float* gram_out, int32_t n, double lambda, float*
   return b200opt_gn_solve_parts(gram_out, 1, 0, n, lambda, p_out, status_out, nullptr, workspace, stream);
 }
 
-int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda, float* p_out,
-                               int32_t* status_out, float* summary_out, void* workspace, void* stream) {
+static int32_t gn_solve_impl(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda, float* p_out,
+                             int32_t* status_out, float* summary_out, void* workspace, void* stream, const unsigned* xchg_flags,
+                             unsigned xchg_seq) {
   const float* gram_out = parts;
   if (n < 1 || n > 256 || !gram_out || !p_out || !workspace || nparts < 1 || (nparts > 1 && part_stride < (int64_t)n * n + n + 2)) {
     set_error("gn_solve: need 1 <= n <= 256, nparts >= 1, part_stride >= n*n + n + 2 and non-NULL buffers");
@@ -268,8 +292,26 @@ int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_
     attr_set = true;
   }
   gn_solve_kernel<<<1, 1024, SOLVE_SMEM, static_cast<cudaStream_t>(stream)>>>(gram_out, nparts, part_stride, n, lambda, A, p_out, status_out,
-                                                                              summary_out);
+                                                                              summary_out, xchg_flags, xchg_seq);
   return check_cuda(cudaGetLastError(), "gn_solve_kernel launch");
+}
+
+int32_t b200opt_gn_solve_parts(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda, float* p_out,
+                               int32_t* status_out, float* summary_out, void* workspace, void* stream) {
+  return gn_solve_impl(parts, nparts, part_stride, n, lambda, p_out, status_out, summary_out, workspace, stream, nullptr, 0);
+}
+
+int32_t b200opt_gn_solve_xchg(const void* xchg_local, int32_t world, int32_t parity, uint32_t seq, int32_t n, double lambda,
+                              float* p_out, int32_t* status_out, float* summary_out, void* workspace, void* stream) {
+  if (!xchg_local || world < 1 || world > 64 || (parity != 0 && parity != 1) || n != 256) {
+    set_error("gn_solve_xchg: bad arguments");
+    return B200OPT_EINVAL;
+  }
+  const int64_t stride = (int64_t)n * n + n + 4;  // gram::XCHG_STRIDE
+  const unsigned char* base = static_cast<const unsigned char*>(xchg_local);
+  const float* parts = reinterpret_cast<const float*>(base) + (size_t)parity * world * stride;
+  const unsigned* flags = reinterpret_cast<const unsigned*>(base + (size_t)2 * world * stride * sizeof(float)) + parity * world;
+  return gn_solve_impl(parts, world, stride, n, lambda, p_out, status_out, summary_out, workspace, stream, flags, seq);
 }
 
 int32_t b200opt_linear_residual(const float* J, const float* y, const float* d, int64_t m_local, int32_t n, float* r,

@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -379,21 +380,62 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
   }
 }
 
+// Exchange buffer of the row-sharded problem (one per rank, mapped into every peer by CUDA IPC):
+//   float    slots[2 parities][world][XCHG_STRIDE]   slot [p][q] = rank q's [G | g | rr | f-stat] of an iteration with parity p
+//   uint32   flags[2][world]                           flags[p][q] = sequence number of the last block rank q published there
+//   uint32   done                                      local "last block" counter of the publishing kernel
+constexpr int XCHG_STRIDE = N * N + N + 4;
+__host__ __device__ inline size_t xchg_flags_offset(int world) { return (size_t)2 * world * XCHG_STRIDE * sizeof(float); }
+__host__ __device__ inline size_t xchg_bytes(int world) { return xchg_flags_offset(world) + (size_t)(2 * world + 4) * sizeof(unsigned); }
+
+struct PeerXchg {
+  unsigned char* const* bases;  // device array [world]: every rank's exchange buffer as mapped in THIS process (NULL: no exchange)
+  int world, rank, parity;
+  unsigned seq;
+};
+
 // Deterministic reduction of the per-CTA partials, mirroring the triangle that was not computed.
-// out = [G (N*N, full symmetric) | g (N) | rr]
-__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out) {
+// out = [G (N*N, full symmetric) | g (N) | rr]   (slot N*N+N+1, the f-statistic, was written by gram_kernel's atomicMax)
+// With an exchange (row-sharded problem on several GPUs) the same kernel also PUBLISHES the block: every value is stored
+// straight into the slot of this rank in every peer's exchange buffer (P2P stores over NVLink / NVSwitch), and the last CTA to
+// finish raises this rank's flag on every peer.  The collective is therefore part of the reduction kernel; the consumer
+// (gn_solve_kernel) waits on the flags.  No NCCL call, no extra launch, no host involvement.
+__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out, PeerXchg x) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * N + N + 1) return;
-  int src = idx;
-  if (idx < N * N) {
-    const int a = idx / N, b = idx % N;
-    if (a >= 128 && b < 128) src = b * N + a;  // lower-left block: read the transposed entry of the upper-right block
-  }
+  const int total = N * N + N + 1;
   float s = 0.f;
-  const bool is_gram = idx < N * N;
-  const int count = is_gram ? live_parts : parts;  // CTAs without tiles never wrote their Gram block
-  for (int c = 0; c < count; ++c) s += ws[(size_t)c * WS_STRIDE + src];
-  out[idx] = s;
+  if (idx < total) {
+    int src = idx;
+    if (idx < N * N) {
+      const int a = idx / N, b = idx % N;
+      if (a >= 128 && b < 128) src = b * N + a;  // lower-left block: read the transposed entry of the upper-right block
+    }
+    const bool is_gram = idx < N * N;
+    const int count = is_gram ? live_parts : parts;  // CTAs without tiles never wrote their Gram block
+    for (int c = 0; c < count; ++c) s += ws[(size_t)c * WS_STRIDE + src];
+    out[idx] = s;
+  } else if (idx == total) {
+    s = out[idx];  // the f-statistic slot rides along
+  }
+  if (x.bases == nullptr) return;
+  if (idx <= total) {
+    const size_t off = ((size_t)(x.parity * x.world + x.rank) * XCHG_STRIDE + idx) * sizeof(float);
+    for (int q = 0; q < x.world; ++q) *reinterpret_cast<float*>(x.bases[q] + off) = s;
+  }
+  __threadfence_system();  // this thread's peer stores are visible system-wide before the block is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* done = reinterpret_cast<unsigned*>(x.bases[x.rank] + xchg_flags_offset(x.world)) + 2 * x.world;
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {  // last CTA: every other CTA has fenced and counted
+      *done = 0;
+      __threadfence_system();
+      for (int q = 0; q < x.world; ++q) {
+        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(x.bases[q] + xchg_flags_offset(x.world)) + x.parity * x.world + x.rank;
+        *flag = x.seq;
+      }
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -425,7 +467,8 @@ int64_t b200opt_gn_gram_workspace_size(int32_t n) {
 }
 
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
-                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream);
+                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream,
+                            gram::PeerXchg x = gram::PeerXchg{nullptr, 0, 0, 0, 0});
 
 int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
   return gn_gram_impl(J, r, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, m_local, n, out, workspace, stream);
@@ -445,10 +488,64 @@ int32_t b200opt_gn_gram_linear(const float* J, const float* y, const float* d, c
   return gn_gram_impl(J, d, y, r_old, r_out, fmax_bits, rtol, atol, m_local, n, out, workspace, stream);
 }
 
+int64_t b200opt_xchg_bytes(int32_t world, int32_t n) {
+  if (n != gram::N || world < 1 || world > 64) return -1;
+  return (int64_t)gram::xchg_bytes(world);
+}
+
+int32_t b200opt_xchg_alloc(int64_t bytes, void** ptr_out, void* ipc_handle_out) {
+  if (!ptr_out || !ipc_handle_out || bytes <= 0) {
+    set_error("xchg_alloc: bad arguments");
+    return B200OPT_EINVAL;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI hands IPC handles around as 64 opaque bytes");
+  void* p = nullptr;
+  if (check_cuda(cudaMalloc(&p, (size_t)bytes), "xchg cudaMalloc")) return B200OPT_ECUDA;
+  if (check_cuda(cudaMemset(p, 0, (size_t)bytes), "xchg memset")) return B200OPT_ECUDA;
+  if (check_cuda(cudaDeviceSynchronize(), "xchg sync")) return B200OPT_ECUDA;
+  cudaIpcMemHandle_t h;
+  if (check_cuda(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle")) {
+    cudaFree(p);
+    return B200OPT_ECUDA;
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return 0;
+}
+
+int32_t b200opt_xchg_open(const void* ipc_handle, void** ptr_out) {
+  if (!ipc_handle || !ptr_out) {
+    set_error("xchg_open: bad arguments");
+    return B200OPT_EINVAL;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  return check_cuda(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int32_t b200opt_xchg_close(void* ptr) { return ptr ? check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle") : 0; }
+int32_t b200opt_xchg_free(void* ptr) { return ptr ? check_cuda(cudaFree(ptr), "xchg cudaFree") : 0; }
+
+int32_t b200opt_gn_gram_linear_xchg(const float* J, const float* y, const float* d, const float* r_old, float* r_out,
+                                    uint32_t* fmax_bits, float rtol, float atol, int64_t m_local, int32_t n, float* out,
+                                    void* workspace, const void* const* xchg_bases_dev, int32_t world, int32_t rank, int32_t parity,
+                                    uint32_t seq, void* stream) {
+  if (!y || !d || !r_out || !xchg_bases_dev || world < 1 || rank < 0 || rank >= world || (parity != 0 && parity != 1)) {
+    set_error("gn_gram_linear_xchg: bad arguments");
+    return B200OPT_EINVAL;
+  }
+  if (fmax_bits != reinterpret_cast<uint32_t*>(out + gram::N * gram::N + gram::N + 1)) {
+    set_error("gn_gram_linear_xchg: the f-statistic must live in slot n*n+n+1 of `out` (it is published with the block)");
+    return B200OPT_EINVAL;
+  }
+  gram::PeerXchg x{reinterpret_cast<unsigned char* const*>(const_cast<void* const*>(xchg_bases_dev)), world, rank, parity, seq};
+  return gn_gram_impl(J, d, y, r_old, r_out, fmax_bits, rtol, atol, m_local, n, out, workspace, stream, x);
+}
+
 }  // extern "C"
 
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
-                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
+                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream, gram::PeerXchg x) {
   if (n != gram::N) {
     set_error("gn_gram: this build supports n = %d parameters only (got %d)", gram::N, n);
     return B200OPT_EINVAL;
@@ -472,6 +569,10 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   if (grid > 256) grid = 256;
   if (num_tiles < grid) grid = num_tiles > 0 ? num_tiles : 1;
   if (m_local == 0) {
+    if (x.bases) {
+      set_error("gn_gram: a rank of a peer exchange must own at least one row");
+      return B200OPT_EINVAL;
+    }
     if (check_cuda(cudaMemsetAsync(out, 0, sizeof(float) * (gram::N * gram::N + gram::N + 1), st), "memset")) return B200OPT_ECUDA;
     return 0;
   }
@@ -504,7 +605,7 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;
-  gram::gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grid, grid, out);
+  gram::gram_reduce_kernel<<<(total + 1 + 255) / 256, 256, 0, st>>>(ws, grid, grid, out, x);
   return check_cuda(cudaGetLastError(), "gram_reduce_kernel launch");
 }
 

@@ -195,3 +195,52 @@ def test_gn_solve_parts_sums_gathered_partials():
     _lib.check(lib.b200opt_gn_solve_parts(parts.data_ptr(), 3, stride, N, 0.0, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
                                           ws.data_ptr(), st), "gn_solve_parts")
     assert torch.isnan(summary[1])
+
+
+def test_peer_exchange_kernels_single_rank():
+    """b200opt_gn_gram_linear_xchg + b200opt_gn_solve_xchg with world = 1 (the exchange buffer is the rank's own): the block is
+    published into slot [parity][0], the flag carries the sequence number, and the solve equals the plain path bit for bit."""
+    lib = _lib.load()
+    m = 65536
+    w = synthetic.linear_lsq_rows(m, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y = torch.zeros(N, dtype=torch.float32, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    nbytes = lib.b200opt_xchg_bytes(1, N)
+    ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+    _lib.check(lib.b200opt_xchg_alloc(nbytes, C.byref(ptr), handle), "xchg_alloc")
+    bases = torch.tensor([ptr.value], dtype=torch.int64, device=DEV)
+    try:
+        ref = None
+        for seq in (1, 2, 3):
+            parity = seq & 1
+            out = torch.zeros(N * N + N + 2, dtype=torch.float32, device=DEV)
+            r = torch.empty(m, dtype=torch.float32, device=DEV)
+            fmax = out[N * N + N + 1:].view(torch.int32)
+            _lib.check(lib.b200opt_gn_gram_linear_xchg(J.data_ptr(), y.data_ptr(), d.data_ptr(), None, r.data_ptr(), fmax.data_ptr(), 1e-4, 1e-4,
+                                                       m, N, out.data_ptr(), ws.data_ptr(), bases.data_ptr(), 1, 0, parity, seq, st), "gram_xchg")
+            p = torch.empty(N, dtype=torch.float32, device=DEV)
+            status = torch.full((1,), -9, dtype=torch.int32, device=DEV)
+            summary = torch.zeros(2, dtype=torch.float32, device=DEV)
+            _lib.check(lib.b200opt_gn_solve_xchg(ptr.value, 1, parity, seq, N, 0.0, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
+                                                 ws.data_ptr(), st), "solve_xchg")
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0
+            p2 = torch.empty_like(p)
+            s2 = torch.zeros(2, dtype=torch.float32, device=DEV)
+            _lib.check(lib.b200opt_gn_solve_parts(out.data_ptr(), 1, N * N + N + 2, N, 0.0, p2.data_ptr(), status.data_ptr(), s2.data_ptr(),
+                                                  ws.data_ptr(), st), "solve_parts")
+            torch.cuda.synchronize()
+            assert torch.equal(p, p2) and torch.equal(summary, s2)
+            ref = p if ref is None else ref
+            assert torch.equal(p, ref)  # same inputs every time, both parities
+        # a sequence number nobody published: bounded wait, then the time-out code instead of a hang
+        status = torch.zeros(1, dtype=torch.int32, device=DEV)
+        _lib.check(lib.b200opt_gn_solve_xchg(ptr.value, 1, 0, 12345, N, 0.0, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
+                                             ws.data_ptr(), st), "solve_xchg")
+        torch.cuda.synchronize()
+        assert int(status.item()) == -4
+    finally:
+        lib.b200opt_xchg_free(ptr)
