@@ -247,9 +247,9 @@ def bench_gram(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_step = t_gram = t_res = 0.0
-    for _ in range(K):
+    # K steps enqueued back to back (the host runs ahead; nothing synchronises inside the timed region), 4 events per step
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for ev in evs:
         ev[0].record()
         if not fused:
             ops.residual(J, y, d, r, r_old, 1e-4, 1e-4, fmax)
@@ -269,10 +269,10 @@ def bench_gram(args, rank, world, local_rank):
                 dist.all_gather_into_tensor(gathered, out)
             ops.solve_parts(gathered, world, OUT_FLOATS, 0.0, p, status, summary)
         ev[3].record()
-        torch.cuda.synchronize()
-        t_res += ev[0].elapsed_time(ev[1])
-        t_gram += ev[1].elapsed_time(ev[2])
-        t_step += ev[0].elapsed_time(ev[3])
+    torch.cuda.synchronize()
+    t_step = evs[0][0].elapsed_time(evs[-1][3])  # first launch to last completion: the K steps including any gaps
+    t_res = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
+    t_gram = sum(ev[1].elapsed_time(ev[2]) for ev in evs)
     barrier()
     clocks = sampler.stop()
     # size-independent property at the full size (outside the timed region): Gauss-Newton from y = 0 must recover the
