@@ -74,8 +74,9 @@ def least_squares_generic(fn, solver, y0, args, *, max_steps, throw, root_near_z
     single = y0.ndim == 1
     Y0 = (y0[None] if single else y0).contiguous()
     B, n = Y0.shape
-    if n > 16:
-        raise NotImplementedError("generic least-squares step kernel supports n <= 16 parameters (register-resident Gram)")
+    if n > 64:
+        raise NotImplementedError("generic least-squares step kernels support n <= 64 parameters (n <= 16: Gram in registers, one warp "
+                                  "per problem; n <= 64: Gram in shared memory, one CTA per problem)")
     dtype_code = _lib.F32 if y0.dtype == t.float32 else _lib.F64
     if B == 0:
         return _empty_solution(Y0, max_steps)

@@ -184,6 +184,194 @@ template <typename T, int NP> __global__ void __launch_bounds__(kStepWarps * 32)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 16 < n <= 64: the Gram matrix no longer fits one thread's registers.  One CTA (128 threads) per problem, G in shared
+// memory / in the state buffer as a full n x n matrix; same state machine, same carry semantics as lsq_step_kernel.
+//   state: [ G (n*n) | g (n) | rr | delta | first | terminate | num_accepted | r_accepted (m) ]
+constexpr int kBigThreads = 128;
+constexpr int kBigNMax = 64;
+__host__ __device__ inline int big_state_head(int n) { return n * n + n + 5; }
+
+template <typename T> __device__ __forceinline__ T big_block_sum(T v, T* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+template <typename T> __device__ __forceinline__ T big_block_nanmax(T v, T* red) {
+  v = warp_nanmax(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return nan_max(nan_max(red[0], red[1]), nan_max(red[2], red[3]));
+}
+// norm of a non-negative quantity distributed over the threads (max / two / rms, NaN-propagating max)
+template <typename T> __device__ __forceinline__ T big_norm(T local, int kind, int count, T* red) {
+  if (kind == B200OPT_NORM_MAX) return big_block_nanmax(local, red);
+  const T s = big_block_sum(local, red);
+  return kind == B200OPT_NORM_TWO ? t_sqrt(s) : t_sqrt(s / T(count));
+}
+
+template <typename T> __global__ void __launch_bounds__(kBigThreads) lsq_step_big_kernel(const StepParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T red[4];
+  const int n = p.n, m = p.m, tid = threadIdx.x, ld = n + 1;
+  T* Gs = reinterpret_cast<T*>(smem_raw);  // [n][n+1]: G, later the Cholesky factor
+  T* gs = Gs + n * ld;                     // g
+  T* dv = gs + n;                          // d = y_eval - y
+  T* pv = dv + n;                          // solve scratch / step
+  const int64_t prob = blockIdx.x;
+  T* st = p.state + prob * p.state_stride;
+  T* stG = st;
+  T* stg = st + n * n;
+  T* sc = stg + n;  // rr, delta, first, terminate, num_accepted
+  T* st_r = sc + 5;
+  int result = p.result[prob];
+  int steps = p.num_steps[prob];
+  bool terminate = sc[3] != T(0);
+  if (terminate || result != RES_OK || steps >= p.max_steps) return;  // block-uniform
+  T rr = sc[0], delta = sc[1];
+  const bool first = sc[2] != T(0);
+  const T rtol = p.rtol, atol = p.atol;
+  const T* re = p.r_eval + prob * m;
+  const T* Je = p.J_eval + prob * (int64_t)m * n;
+
+  bool fin = true;
+  for (int j = tid; j < n; j += kBigThreads) {
+    const T yj = p.y[prob * n + j];
+    dv[j] = p.y_eval[prob * n + j] - yj;
+    gs[j] = stg[j];
+    fin = fin && t_finite(yj);
+  }
+  for (int e = tid; e < n * n; e += kBigThreads) Gs[(e / n) * ld + e % n] = stG[e];
+  const bool y_old_finite = __syncthreads_and(fin ? 1 : 0) != 0;
+  T part = T(0);
+  for (int i = tid; i < m; i += kBigThreads) part += re[i] * re[i];
+  const T rre = big_block_sum(part, red);
+
+  bool accept = true;
+  if (p.trust) {  // trust_region.py:86-104, predicted reduction d.g + 0.5 d.G d
+    T lq = T(0);
+    for (int i = tid; i < n; i += kBigThreads) {
+      T gd = T(0);
+      for (int j = 0; j < n; ++j) gd += Gs[i * ld + j] * dv[j];
+      lq += dv[i] * (gs[i] + T(0.5) * gd);
+    }
+    const T pred = big_block_sum(lq, red);
+    const T df = T(0.5) * rre - T(0.5) * rr;
+    accept = (df <= T(0.01) * pred) || first;
+    const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
+    delta *= accept ? (good ? T(3.5) : T(1)) : T(0.25);
+  } else {
+    delta = T(1);
+  }
+
+  if (accept) {  // gauss_newton.py:276-291
+    T yl = T(0);
+    for (int j = tid; j < n; j += kBigThreads) {
+      const T q = t_abs(dv[j]) / (atol + rtol * t_abs(p.y_eval[prob * n + j]));
+      yl = (p.norm == B200OPT_NORM_MAX) ? nan_max(yl, q) : yl + q * q;
+    }
+    const T ynorm = big_norm(yl, p.norm, n, red);
+    // Gram matrix and gradient of the accepted point: entry e = a * n + b by thread e % 128 (coalesced over b)
+    __syncthreads();
+    for (int e = tid; e < n * n; e += kBigThreads) {
+      const int a = e / n, b = e % n;
+      T acc = T(0);
+      for (int i = 0; i < m; ++i) acc += Je[(int64_t)i * n + a] * Je[(int64_t)i * n + b];
+      Gs[a * ld + b] = acc;
+      stG[e] = acc;
+    }
+    for (int a = tid; a < n; a += kBigThreads) {
+      T acc = T(0);
+      for (int i = 0; i < m; ++i) acc += Je[(int64_t)i * n + a] * re[i];
+      gs[a] = acc;
+      stg[a] = acc;
+    }
+    T fl = T(0), zl = T(0);
+    for (int i = tid; i < m; i += kBigThreads) {
+      const T r = re[i], ro = st_r[i];
+      const T q = t_abs(r - ro) / (atol + rtol * t_abs(r));
+      const T z = t_abs(first ? r : ro);
+      if (p.norm == B200OPT_NORM_MAX) {
+        fl = nan_max(fl, q);
+        zl = nan_max(zl, z);
+      } else {
+        fl += q * q;
+        zl += z * z;
+      }
+      st_r[i] = r;
+    }
+    const T fnorm = big_norm(fl, p.norm, m, red);
+    terminate = (ynorm < T(1)) && (fnorm < T(1));
+    if (p.root_near_zero) terminate = terminate && (big_norm(zl, p.norm, m, red) < atol);  // _root_find.py:64-73
+    rr = rre;
+  } else {
+    terminate = false;
+  }
+  __syncthreads();
+
+  // ---- descent: (G + lam I) p = g by Cholesky in shared memory (levenberg_marquardt.py:55-75 in normal-equation form)
+  T lam = T(0);
+  if (p.trust) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
+  for (int j = tid; j < n; j += kBigThreads) Gs[j * ld + j] += lam;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const T dk = t_sqrt(Gs[k * ld + k]);  // non-positive pivot -> NaN -> non-finite step -> `singular`
+    __syncthreads();
+    for (int i = k + tid; i < n; i += kBigThreads) Gs[i * ld + k] = (i == k) ? dk : Gs[i * ld + k] / dk;
+    __syncthreads();
+    const int rem = n - k - 1;
+    for (int e = tid; e < rem * rem; e += kBigThreads) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      if (j <= i) Gs[i * ld + j] -= Gs[i * ld + k] * Gs[j * ld + k];
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {  // substitutions: one warp, serial in k
+    const int lane = tid;
+    for (int i = lane; i < n; i += 32) pv[i] = gs[i];
+    __syncwarp();
+    for (int k = 0; k < n; ++k) {
+      const T zk = pv[k] / Gs[k * ld + k];
+      __syncwarp();
+      if (lane == 0) pv[k] = zk;
+      for (int i = k + 1 + lane; i < n; i += 32) pv[i] -= Gs[i * ld + k] * zk;
+      __syncwarp();
+    }
+    for (int k = n - 1; k >= 0; --k) {
+      const T xk = pv[k] / Gs[k * ld + k];
+      __syncwarp();
+      if (lane == 0) pv[k] = xk;
+      for (int i = lane; i < k; i += 32) pv[i] -= Gs[k * ld + i] * xk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  bool pfin = true;
+  for (int j = tid; j < n; j += kBigThreads) {
+    const T yj = accept ? p.y_eval[prob * n + j] : p.y[prob * n + j];
+    pfin = pfin && t_finite(pv[j]);
+    p.y[prob * n + j] = yj;
+    p.y_eval[prob * n + j] = yj - pv[j];
+  }
+  const bool all_fin = __syncthreads_and(pfin ? 1 : 0) != 0;
+  result = all_fin ? RES_OK : RES_SINGULAR;
+  if (!y_old_finite) result = RES_NONFINITE;
+  ++steps;
+  if (tid == 0) {
+    sc[0] = rr;
+    sc[1] = delta;
+    sc[2] = T(0);
+    sc[3] = terminate ? T(1) : T(0);
+    if (accept) sc[4] = sc[4] + T(1);
+    p.num_steps[prob] = steps;
+    p.result[prob] = result;
+    if (p.active_count && !terminate && result == RES_OK && steps < p.max_steps) atomicAdd(p.active_count, 1);
+  }
+}
+
 template <typename T> __global__ void lsq_step_init_kernel(int64_t batch, int n, int head, int64_t stride, int ng_np, const T* y0,
                                                            T* y, T* y_eval, T* state, int32_t* num_steps, int32_t* result) {
   const int64_t prob = blockIdx.x;
@@ -217,6 +405,8 @@ template <typename T> __global__ void lsq_step_finish_kernel(int64_t batch, int6
 
 static int pad_n(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 0)); }
 static int head_for(int np) { return np == 4 ? step_state_head<4>() : (np == 8 ? step_state_head<8>() : step_state_head<16>()); }
+// state head (elements before the accepted residuals) for any supported n: register kernel up to 16, CTA kernel up to 64
+static int head_any(int n) { return pad_n(n) ? head_for(pad_n(n)) : big_state_head(n); }
 
 template <typename T, int NP> static int step_launch(const StepParams<T>& p, cudaStream_t stream) {
   auto kern = lsq_step_kernel<T, NP>;
@@ -236,12 +426,13 @@ static int step_typed(int solver, int64_t batch, int n, int m, const void* r_eva
                       void* state, const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
   const int np = pad_n(n);
   StepParams<T> p;
+  const int head_sel = head_any(n);
   p.r_eval = static_cast<const T*>(r_eval);
   p.J_eval = static_cast<const T*>(J_eval);
   p.y = static_cast<T*>(y);
   p.y_eval = static_cast<T*>(y_eval);
   p.state = static_cast<T*>(state);
-  p.state_stride = step_state_stride(head_for(np), m);
+  p.state_stride = step_state_stride(head_sel, m);
   p.num_steps = num_steps;
   p.result = result;
   p.active_count = active;
@@ -255,6 +446,11 @@ static int step_typed(int solver, int64_t batch, int n, int m, const void* r_eva
   p.root_near_zero = o->root_near_zero;
   p.trust = solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
   if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
+  if (np == 0) {  // 16 < n <= 64
+    const size_t smem = sizeof(T) * ((size_t)n * (n + 1) + 3 * (size_t)n);
+    lsq_step_big_kernel<T><<<(unsigned)batch, kBigThreads, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "lsq_step_big_kernel launch");
+  }
   if (np == 4) return step_launch<T, 4>(p, st);
   if (np == 8) return step_launch<T, 8>(p, st);
   return step_launch<T, 16>(p, st);
@@ -268,8 +464,8 @@ static int step_check(const char* who, int dtype, int64_t batch, int n, int m) {
     set_error("%s: unknown dtype %d", who, dtype);
     return B200OPT_EINVAL;
   }
-  if (batch < 0 || m < 1 || n < 1 || pad_n(n) == 0) {
-    set_error("%s: need batch >= 0, m >= 1 and 1 <= n <= 16 (n=%d, m=%d)", who, n, m);
+  if (batch < 0 || batch > 2147483647LL || m < 1 || n < 1 || n > kBigNMax) {
+    set_error("%s: need 0 <= batch < 2^31, m >= 1 and 1 <= n <= 64 (n=%d, m=%d)", who, n, m);
     return B200OPT_EINVAL;
   }
   return 0;
@@ -279,14 +475,14 @@ extern "C" {
 
 int64_t b200opt_lsq_step_state_size(int32_t dtype, int32_t n, int32_t m) {
   if (step_check("lsq_step_state_size", dtype, 0, n, m)) return -1;
-  return step_state_stride(head_for(pad_n(n)), m) * (dtype == B200OPT_F32 ? 4 : 8);
+  return step_state_stride(head_any(n), m) * (dtype == B200OPT_F32 ? 4 : 8);
 }
 
 int32_t b200opt_lsq_step_init(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* y0, void* y, void* y_eval,
                               void* state, int32_t* num_steps, int32_t* result, void* stream) {
   if (int e = step_check("lsq_step_init", dtype, batch, n, m)) return e;
   if (batch == 0) return 0;
-  const int np = pad_n(n), head = head_for(np);
+  const int head = head_any(n);
   const int64_t stride = step_state_stride(head, m);
   const int ng_np = head - 5;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -324,7 +520,7 @@ int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t
                                 void* stream) {
   if (int e = step_check("lsq_step_finish", dtype, batch, n, m)) return e;
   if (batch == 0) return 0;
-  const int head = head_for(pad_n(n));
+  const int head = head_any(n);
   const int64_t stride = step_state_stride(head, m);
   const int term_off = head - 5 + 3;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

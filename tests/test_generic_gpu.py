@@ -350,3 +350,46 @@ def test_has_aux_autodiff_mode_and_unbounded_steps():
     assert torch.allclose(torch.cos(sol.value), sol.value, atol=1e-9) and float(sol.aux) == 1.0
     with pytest.raises(NotImplementedError):
         optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8), torch.zeros(4, dtype=torch.float64, device=DEV), has_aux=True)
+
+
+# tests/test_least_squares.py:27-53 of the reference: LM and GN on the WHOLE least-squares zoo (n = 20 problems included:
+# 16 < n <= 64 runs in the CTA-per-problem step kernel), sum r^2 ~ minimum at 1e-4; iterates against the oracle
+@pytest.mark.parametrize("solver_cls,oracle", [(optx.LevenbergMarquardt, S.levenberg_marquardt), (optx.GaussNewton, S.gauss_newton)])
+@pytest.mark.parametrize("name,fn,minimum,y0,args", F.LEAST_SQUARES, ids=[p[0] for p in F.LEAST_SQUARES])
+def test_least_squares_zoo_all_sizes(name, fn, minimum, y0, args, solver_cls, oracle):
+    sol = optx.least_squares(fn, solver_cls(1e-8, 1e-8), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000, throw=False)
+    r = fn(sol.value, _dev(args))
+    assert np.allclose(float((r * r).sum()), minimum, atol=1e-4, rtol=1e-4)
+    ref = oracle(F.batched_lsq(fn), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000, linsolve="gram")
+    assert _res_name(sol) == S.RESULT_NAMES[ref["result"][0]]
+    assert abs(int(sol.stats["num_steps"]) - int(ref["num_steps"][0])) <= max(1, int(0.05 * ref["num_steps"][0]))
+    assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-6, atol=1e-9)
+
+
+# tests/test_root_find.py:25-28,32-55: LM as a root finder on the 28-dimensional fixed-point problems too
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4])
+def test_root_find_via_lm_n28(idx):
+    name, fn, y0, args = F.FIXED_POINT[idx]
+    sol = optx.fixed_point(fn, optx.LevenbergMarquardt(1e-8, 1e-8), torch.as_tensor(y0, device=DEV), _dev(args), max_steps=10_000, throw=False)
+    out = fn(sol.value, _dev(args)) - sol.value
+    assert np.allclose(to_np(out), 0.0, atol=1e-5, rtol=1e-5)
+    ref = S.levenberg_marquardt(F.batched_lsq(F.as_root(fn)), y0[None], args, rtol=1e-8, atol=1e-8, max_steps=10_000,
+                                root_near_zero=True, linsolve="gram")
+    assert _res_name(sol) == S.RESULT_NAMES[ref["result"][0]]
+    assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-6, atol=1e-10)
+
+
+def test_generic_lm_step_kernels_agree_across_the_size_boundary():
+    """The same 16-parameter problem through the register kernel (n = 16) and, padded with a decoupled 17th unknown, through
+    the CTA kernel (n = 17): identical iteration counts, the same solution."""
+    g = torch.Generator(device=DEV).manual_seed(2)
+    A = torch.randn(40, 16, generator=g, dtype=torch.float64, device=DEV)
+    b = torch.randn(40, generator=g, dtype=torch.float64, device=DEV)
+    f16 = lambda y, _: torch.tanh(A @ y) - 0.3 * b
+    f17 = lambda y, _: torch.cat([torch.tanh(A @ y[:16]) - 0.3 * b, y[16:] - 2.0])
+    s16 = optx.least_squares(f16, optx.LevenbergMarquardt(1e-9, 1e-9), torch.zeros(16, dtype=torch.float64, device=DEV), None, throw=False,
+                             max_steps=1000)
+    s17 = optx.least_squares(f17, optx.LevenbergMarquardt(1e-9, 1e-9), torch.zeros(17, dtype=torch.float64, device=DEV), None, throw=False,
+                             max_steps=1000)
+    assert _res_name(s16) == _res_name(s17) == "successful"
+    assert torch.allclose(s17.value[:16], s16.value, rtol=1e-6, atol=1e-8) and abs(float(s17.value[16]) - 2.0) < 1e-8
