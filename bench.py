@@ -38,7 +38,7 @@ WORKLOADS = {
     "newton": ("Newton implicit-Euler root finds n=32 fp64 rtol=atol=1e-8 (BASELINE configs[2])", 1 << 18, 528, "f64"),
     "bfgs": ("BFGS chained-Rosenbrock minimisations n=64 fp64 rtol=atol=1e-8 max_steps=4096 (BASELINE configs[3])", 1 << 16, 1032, "f64"),
 }
-CPU_SAMPLE = {"gauss2": 32768, "exp_decay": 4096, "newton": 8192, "bfgs": 256}
+CPU_SAMPLE = {"gauss2": 32768, "exp_decay": 4096, "newton": 262144, "bfgs": 16384}
 
 
 def _peaks():
@@ -355,17 +355,18 @@ def cpu_reference(name, inp, sample, linsolve="qr"):
                                            max_steps=256, linsolve=linsolve, nthreads=cores)
         dt = time.perf_counter() - t0
         return out, dt, cores, "C+OpenMP restatement (oracle/c), augmented-QR solve as in the reference"
-    from oracle import models as M
-    from oracle import solvers as S
-
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     if name == "newton":
-        a = dict(A=inp["A"], B=inp["B"], y_prev=inp["y_prev"][:sample], dt=inp["dt"][:sample])
-        out = S.newton_chord(M.implicit_euler, inp["y0"][:sample], a, rtol=1e-8, atol=1e-8)
+        out = c_oracle.newton_implicit_euler(inp["y0"][:sample], inp["A"], inp["B"], inp["y_prev"][:sample], inp["dt"][:sample],
+                                             rtol=1e-8, atol=1e-8, nthreads=cores)
     else:
-        out = S.bfgs(M.rosenbrock, inp["y0"][:sample], None, rtol=1e-8, atol=1e-8, max_steps=4096)
+        out = c_oracle.bfgs_rosenbrock(inp["y0"][:sample], rtol=1e-8, atol=1e-8, max_steps=4096, nthreads=cores)
     dt = time.perf_counter() - t0
-    return out, dt, 1, "NumPy restatement (oracle/solvers.py), batched, single thread + BLAS"
+    return out, dt, cores, "C+OpenMP restatement (oracle/c/nb_oracle.c) of the reference step, cross-checked against the NumPy oracle"
 
 
 # ------------------------------------------------------------------------------------------------ main

@@ -29,6 +29,12 @@ def load():
                                          C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int]
         _lib.oracle_max_threads.restype = C.c_int
+        _lib.oracle_newton_implicit_euler.restype = C.c_int
+        _lib.oracle_newton_implicit_euler.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.oracle_bfgs_rosenbrock.restype = C.c_int
+        _lib.oracle_bfgs_rosenbrock.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_int]
     return _lib
 
 
@@ -52,4 +58,33 @@ def levenberg_marquardt(model: str, y0, x, d, *, rtol, atol, max_steps=256, lins
                              res.ctypes.data, nthreads)
     if rc != 0:
         raise RuntimeError(f"oracle_lm_solve failed: {rc}")
+    return dict(value=y, num_steps=steps, result=res)
+
+
+def newton_implicit_euler(y0, A, B, y_prev, dt, *, rtol, atol, max_steps=256, chord=False, nthreads=0):
+    """Newton / Chord on the implicit-Euler family (fp64, max_norm, Cauchy termination), C + OpenMP."""
+    lib = load()
+    y0, A, B, y_prev, dt = (np.ascontiguousarray(a, dtype=np.float64) for a in (y0, A, B, y_prev, dt))
+    Bn, n = y0.shape
+    y = np.empty_like(y0)
+    steps = np.empty(Bn, np.int32)
+    res = np.empty(Bn, np.int32)
+    rc = lib.oracle_newton_implicit_euler(Bn, n, A.ctypes.data, B.ctypes.data, y_prev.ctypes.data, dt.ctypes.data, y0.ctypes.data, rtol, atol,
+                                          max_steps, int(chord), y.ctypes.data, steps.ctypes.data, res.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_newton_implicit_euler failed: {rc}")
+    return dict(value=y, num_steps=steps, result=res)
+
+
+def bfgs_rosenbrock(y0, *, rtol, atol, max_steps=256, nthreads=0):
+    """BFGS (inverse update, backtracking Armijo) on the chained Rosenbrock function (fp64, max_norm), C + OpenMP."""
+    lib = load()
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    Bn, n = y0.shape
+    y = np.empty_like(y0)
+    steps = np.empty(Bn, np.int32)
+    res = np.empty(Bn, np.int32)
+    rc = lib.oracle_bfgs_rosenbrock(Bn, n, y0.ctypes.data, rtol, atol, max_steps, y.ctypes.data, steps.ctypes.data, res.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_bfgs_rosenbrock failed: {rc}")
     return dict(value=y, num_steps=steps, result=res)

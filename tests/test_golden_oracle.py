@@ -49,3 +49,29 @@ def test_bfgs_golden():
     g = _load("bfgs_rosenbrock_f64")
     assert np.array_equal(out["result"], g["result"][:8])
     assert np.allclose(out["value"], g["value"][:8], rtol=1e-6, atol=1e-8)
+
+
+def test_c_newton_and_bfgs_oracles_match_the_numpy_oracle():
+    """oracle/c/nb_oracle.c (the multi-core CPU baseline of bench.py for configs[2] / configs[3]) against oracle/solvers.py."""
+    from optimistix_b200 import synthetic
+    from oracle import c_oracle, models as M, solvers as S
+
+    w = synthetic.implicit_euler_batch(512)
+    a = dict(A=w["A"], B=w["B"], y_prev=w["y_prev"], dt=w["dt"])
+    for chord in (False, True):
+        ref = S.newton_chord(M.implicit_euler, w["y0"], a, rtol=1e-8, atol=1e-8, chord=chord)
+        c = c_oracle.newton_implicit_euler(w["y0"], w["A"], w["B"], w["y_prev"], w["dt"], rtol=1e-8, atol=1e-8, chord=chord)
+        assert np.array_equal(c["num_steps"], ref["num_steps"]) and np.array_equal(c["result"], ref["result"])
+        assert np.allclose(c["value"], ref["value"], rtol=1e-13, atol=1e-15)
+    w = synthetic.rosenbrock_batch(16)
+    for k in (1, 3, 10):
+        ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, max_steps=k)
+        c = c_oracle.bfgs_rosenbrock(w["y0"], rtol=1e-8, atol=1e-8, max_steps=k)
+        assert np.array_equal(c["num_steps"], ref["num_steps"]) and np.array_equal(c["result"], ref["result"])
+        assert np.allclose(c["value"], ref["value"], rtol=1e-12, atol=1e-14)
+    ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, max_steps=4096)
+    c = c_oracle.bfgs_rosenbrock(w["y0"], rtol=1e-8, atol=1e-8, max_steps=4096)
+    assert np.array_equal(c["result"], ref["result"])
+    fc, _ = M.rosenbrock(c["value"])
+    fr, _ = M.rosenbrock(ref["value"])
+    assert np.allclose(fc, fr, atol=1e-8)
