@@ -20,7 +20,7 @@ from typing import Any
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _pytree
 from ._models import KIND_LSQ, KIND_MIN, KIND_ROOT, RegisteredModel
 from ._solution import RESULTS, Solution
 from ._solvers import (
@@ -223,8 +223,12 @@ def _check_defaults(solver):
 # ------------------------------------------------------------------------------------------ least squares
 def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
                   adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), _root_near_zero=False, chunk: int = 0,
-                  args_in_dims=None):
+                  args_in_dims=None, y0_in_dims=None):
     """Solve (a batch of) nonlinear least-squares problems. Reference: optimistix/_least_squares.py:44-135."""
+    if y0_in_dims is not None or not _pytree.is_array_like(y0):  # pytree-valued y (and residuals): ravel on the host side
+        return _pytree.dispatch(least_squares, "vector", fn, solver, y0, args, options, y0_in_dims, has_aux,
+                                dict(max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags, _root_near_zero=_root_near_zero,
+                                     chunk=chunk, args_in_dims=args_in_dims))
     if has_aux:
         return _solve_with_aux(least_squares, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw,
                                tags=tags, _root_near_zero=_root_near_zero, chunk=chunk, args_in_dims=args_in_dims)
@@ -294,8 +298,11 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
 
 # ------------------------------------------------------------------------------------------ root find
 def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, args_in_dims=None):
+              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, args_in_dims=None, y0_in_dims=None):
     """Solve (a batch of) root-finding problems. Reference: optimistix/_root_find.py:119-241."""
+    if y0_in_dims is not None or not _pytree.is_array_like(y0):
+        return _pytree.dispatch(root_find, "vector", fn, solver, y0, args, options, y0_in_dims, has_aux,
+                                dict(max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags, chunk=chunk, args_in_dims=args_in_dims))
     if has_aux:
         return _solve_with_aux(root_find, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw,
                                tags=tags, chunk=chunk, args_in_dims=args_in_dims)
@@ -412,9 +419,12 @@ def _pack_root_args(fn, a, buf, dev, B, n, single):
 
 # ------------------------------------------------------------------------------------------ fixed point
 def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
-                adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), args_in_dims=None):
+                adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), args_in_dims=None, y0_in_dims=None):
     """Find a fixed point. Reference: optimistix/_fixed_point.py:50-154: with a root finder / least-squares
     solver / minimiser this is `root_find` on `fn(y, args) - y` (:35-47, :115-129)."""
+    if (y0_in_dims is not None or not _pytree.is_array_like(y0)) and not isinstance(fn, RegisteredModel):
+        return _pytree.dispatch(fixed_point, "same", fn, solver, y0, args, options, y0_in_dims, has_aux,
+                                dict(max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags, args_in_dims=args_in_dims))
     if isinstance(fn, RegisteredModel):
         raise TypeError("registered model families are residual/root/objective functions, not fixed-point maps; "
                         "use root_find, or pass a Python callable")
@@ -437,8 +447,12 @@ def fixed_point(fn, solver, y0, args=None, options=None, *, has_aux=False, max_s
 # ------------------------------------------------------------------------------------------ minimise
 def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_steps: int | None = 256,
              adjoint=ImplicitAdjoint(), throw: bool = True, tags=frozenset(), chunk: int = 0, return_hessian_inv=False,
-             args_in_dims=None, _implicit=None):
+             args_in_dims=None, _implicit=None, y0_in_dims=None):
     """Minimise (a batch of) scalar functions. Reference: optimistix/_minimise.py:37-119."""
+    if y0_in_dims is not None or not _pytree.is_array_like(y0):
+        return _pytree.dispatch(minimise, "scalar", fn, solver, y0, args, options, y0_in_dims, has_aux,
+                                dict(max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags, chunk=chunk,
+                                     return_hessian_inv=return_hessian_inv, args_in_dims=args_in_dims, _implicit=_implicit))
     if has_aux:
         return _solve_with_aux(minimise, fn, solver, y0, args, options, max_steps=max_steps, adjoint=adjoint, throw=throw, tags=tags,
                                chunk=chunk, return_hessian_inv=return_hessian_inv, args_in_dims=args_in_dims, _implicit=_implicit)

@@ -26,6 +26,118 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Tuning switches of the replicated 8 x 8 algebra (bit mask; A/B builds: tools/lm_variants.sh):
+//   1  hardware rsqrt / reciprocal (MUFU, no denormal fix-up sequence) in the Cholesky solve and for lambda = 1 / Delta;
+//      back-substitution sums the newest unknown LAST (dependent chain of 1 instead of N - 1 - i FMAs per row)
+//   2  predicted reduction through the symmetric form  sum_i d_i (G_ii d_i + 2 sum_{j<i} G_ij d_j)  (36 instead of 64 FMAs)
+//   4  (off) packed adds (FADD2) in the column sums of the warp all-reduce (same order of additions: bit-identical sums)
+//   8  (off) predicted reduction from the Cholesky factor of the solve that produced d:  with L z = g, L^T p = z, d = -p:
+//      d.g + 0.5 d.G d = -0.5 (|z|^2 + lambda |d|^2)  - 16 FMAs, but exact only for an exact solve
+// Measured on 1 Mi gauss2 fits (ms per launch): 0: 15.63, 1: 15.12, 3: 14.55, 7: 14.62, 15: 14.32.  Bit 4 removes 32
+// instructions from a part of the step that is latency bound (no gain); bit 8 is the fastest but it is NOT the reference's
+// predicted reduction in floating point: mean iteration count 10.85 instead of 10.51 and 9x more `max_steps` results on
+// the same inputs, so it stays an experiment.
+#ifndef LSQ_P2_FAST
+#define LSQ_P2_FAST 3
+#endif
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // x < 0 or NaN -> NaN, x == 0 -> +inf (reported as `singular`)
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// (G + lam I) p = g as spd_solve (common.cuh), fp32 only: hardware rsqrt, newest unknown last in the back-substitution.
+template <int N>
+__device__ __forceinline__ void spd_solve_fast(const float (&G)[Tri<N>::size], float lam, const float (&g)[N], float (&p)[N], float& zz) {
+  float L[Tri<N>::size];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float s = G[Tri<N>::at(j, j)] + lam;
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[Tri<N>::at(j, k)] * L[Tri<N>::at(j, k)];
+    const float inv = rsqrt_approx(s);
+    L[Tri<N>::at(j, j)] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      float t = G[Tri<N>::at(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[Tri<N>::at(i, k)] * L[Tri<N>::at(j, k)];
+      L[Tri<N>::at(i, j)] = t * inv;
+    }
+  }
+  float z[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[Tri<N>::at(i, k)] * z[k];
+    z[i] = s * L[Tri<N>::at(i, i)];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    float s = z[i];
+#pragma unroll
+    for (int k = N - 1; k > i; --k) s -= L[Tri<N>::at(k, i)] * p[k];
+    p[i] = s * L[Tri<N>::at(i, i)];
+  }
+  zz = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) zz += z[i] * z[i];
+}
+
+// warp_allreduce_array (lsq_kernel.cuh) for fp32 with the 16-row column sums done two columns per instruction.
+template <int K> __device__ __forceinline__ void warp_allreduce_array_f2(float (&v)[K], float* sm, int lane) {
+  using L = WarpReduceLayout<float, K>;
+  float* row = sm + lane * L::KP;
+#pragma unroll
+  for (int q = 0; q < L::KQ; ++q) {
+    float4 w;
+    float* ww = reinterpret_cast<float*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ww[e] = (q * 4 + e < K) ? v[q * 4 + e] : 0.f;
+    *reinterpret_cast<float4*>(row + q * 4) = w;
+  }
+  __syncwarp();
+  float* tot = sm + 32 * L::KP;
+  static_assert(L::KQ <= 16, "one pass of 16 quad columns");
+  {
+    const int q = lane & 15, h = lane >> 4;
+    const bool on = q < L::KQ;
+    const unsigned mask = __ballot_sync(kFull, on);
+    if (on) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const float4 w = *reinterpret_cast<const float4*>(sm + (h * 16 + l) * L::KP + q * 4);
+        a01 = add2(a01, make_float2(w.x, w.y));
+        a23 = add2(a23, make_float2(w.z, w.w));
+      }
+      float a[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float o = __shfl_xor_sync(mask, a[e], 16);
+        a[e] = (h == 0) ? a[e] + o : o + a[e];
+      }
+      if (h == 0) *reinterpret_cast<float4*>(tot + q * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < L::KQ; ++q) {
+    const float4 w = *reinterpret_cast<const float4*>(tot + q * 4);
+    const float* ww = reinterpret_cast<const float*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (q * 4 + e < K) v[q * 4 + e] = ww[e];
+  }
+  __syncwarp();
+}
+
 // exp(-0.5 * t) for a pair of non-negative t
 __device__ __forceinline__ float2 exp_mhalf2(float2 t) {
   const float K = -0.72134752044448170368f;  // -log2(e) / 2
@@ -137,6 +249,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
     for (int j = 0; j < N; ++j) g[j] = T(0);
     T rr = T(0);
     T delta = T(1);
+    T predn = T(0);  // LSQ_P2_FAST & 8 only
     bool first = true, terminate = false;
     bool yfin = true;
 #pragma unroll
@@ -180,13 +293,28 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
       bool accept = true;
       if (TRUST) {
         T lin = T(0), quad = T(0);
+        if (LSQ_P2_FAST & 8) {
+          lin = predn;
+        } else if (LSQ_P2_FAST & 2) {
+          T hq = T(0);  // 0.5 d.G d = sum_i d_i (0.5 G_ii d_i + sum_{j<i} G_ij d_j)
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          T gd = T(0);
+          for (int i = 0; i < N; ++i) {
+            T gd = T(0.5) * G[Tri<N>::at(i, i)] * d[i];
 #pragma unroll
-          for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
-          quad += d[i] * gd;
-          lin += d[i] * g[i];
+            for (int j = 0; j < i; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
+            hq += d[i] * gd;
+            lin += d[i] * g[i];
+          }
+          quad = hq + hq;
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            T gd = T(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
+            quad += d[i] * gd;
+            lin += d[i] * g[i];
+          }
         }
         const T pred = lin + T(0.5) * quad;
         const T df = T(0.5) * rre - T(0.5) * rr;
@@ -257,7 +385,8 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
             }
           }
         }
-        warp_allreduce_array<T, NG + N>(acc, scratch, lane);
+        if (LSQ_P2_FAST & 4) warp_allreduce_array_f2<NG + N>(acc, scratch, lane);
+        else warp_allreduce_array<T, NG + N>(acc, scratch, lane);
 #pragma unroll
         for (int a = 0; a < NG; ++a) G[a] = acc[a];
 #pragma unroll
@@ -273,9 +402,20 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 
       // ---- descent (levenberg_marquardt.py:55-57,66-75,132 / gauss_newton.py:64-78,126-127)
       T lam = T(0);
-      if (TRUST) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
+      if (TRUST) lam = (delta > Num<T>::eps()) ? ((LSQ_P2_FAST & 1) ? rcp_approx(delta) : T(1) / delta) : Num<T>::max();
       T pstep[N];
-      spd_solve<T, N>(G, lam, g, pstep);
+      if (LSQ_P2_FAST & 1) {
+        T zz;
+        spd_solve_fast<N>(G, lam, g, pstep, zz);
+        if (LSQ_P2_FAST & 8) {
+          T pp = T(0);
+#pragma unroll
+          for (int j = 0; j < N; ++j) pp += pstep[j] * pstep[j];
+          predn = T(-0.5) * (zz + lam * pp);
+        }
+      } else {
+        spd_solve<T, N>(G, lam, g, pstep);
+      }
       bool pfin = true;
 #pragma unroll
       for (int j = 0; j < N; ++j) {

@@ -18,6 +18,7 @@ def compare(sol, ref, rtol, atol, label=""):
     # difference in units of the solver's own termination scale (atol + rtol*|y|)
     scaled = np.max(np.abs(val - rv) / (atol + rtol * np.abs(rv)), axis=1)
     rel = np.max(np.abs(val - rv) / np.maximum(np.abs(rv), 1e-300), axis=1)
+    both_ok = (res == RESULTS.successful) & (rr == RESULTS.successful)  # diverged / max-steps iterates are not comparable
     stats = dict(
         n=len(steps),
         result_match=float(np.mean(res == rr)),
@@ -30,6 +31,9 @@ def compare(sol, ref, rtol, atol, label=""):
         rel_same_p99=float(np.percentile(rel[same_steps], 99)) if same_steps.any() else 0.0,
         rel_same_max=float(rel[same_steps].max()) if same_steps.any() else 0.0,
         within_tol=float(np.mean(scaled <= 1.0)),
+        both_ok=float(np.mean(both_ok)),
+        within_tol_ok=float(np.mean(scaled[both_ok] <= 1.0)) if both_ok.any() else 1.0,
+        within_2tol_ok=float(np.mean(scaled[both_ok] <= 2.0)) if both_ok.any() else 1.0,
     )
     print(f"[parity {label}] " + " ".join(f"{k}={v}" for k, v in stats.items()))
     return stats
