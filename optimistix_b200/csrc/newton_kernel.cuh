@@ -107,6 +107,73 @@ __device__ __forceinline__ double t_rcp(double x) {
 __device__ __forceinline__ double t_rcp(double x) { return __drcp_rn(x); }
 #endif
 
+#ifndef ROOT_LOOKAHEAD
+#define ROOT_LOOKAHEAD 1
+#endif
+#if ROOT_LOOKAHEAD
+// Look-ahead form: step k first brings column k + 1 up to date (one FMA per lane), starts the arg-max of step k + 1 on it
+// (two dependent REDUX + a ballot, ~70 cycles of latency) and only then applies the rest of step k's row update, which no
+// longer sits behind that latency.  The update is predicated, not branched, so that the whole step is one basic block the
+// assembler can schedule.  Same arithmetic, same pivots, same results as the plain form below.
+template <typename T, int N>
+__device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T* rowbuf, unsigned char* piv, int lane) {
+  using Vec = typename Num<T>::Vec;
+  constexpr int V = Num<T>::kVec;
+  static_assert(N % V == 0, "N must be a multiple of the 128-bit vector width");
+  bool done = lane >= N;
+  mycol = N;
+  rinv = T(0);
+  int p = warp_argmax_abs(a[0], !done);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int k0 = (k / V) * V;
+    if (lane == p) {
+      if (sizeof(T) == 8 && ROOT_STS64) {
+#pragma unroll
+        for (int j = k; j < N; ++j) rowbuf[j] = a[j];
+      } else {
+#pragma unroll
+        for (int j = k0; j < N; j += V) {
+          Vec v;
+          T* vv = reinterpret_cast<T*>(&v);
+#pragma unroll
+          for (int q = 0; q < V; ++q) vv[q] = a[j + q];
+          *reinterpret_cast<Vec*>(rowbuf + j) = v;
+        }
+      }
+      piv[k] = (unsigned char)p;
+    }
+    __syncwarp();
+    T row[N];  // the part of the pivot row still in use (entries below k0 are never read)
+#pragma unroll
+    for (int j = k0; j < N; j += V) {
+      const Vec v = *reinterpret_cast<const Vec*>(rowbuf + j);
+      const T* vv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int q = 0; q < V; ++q) row[j + q] = vv[q];
+    }
+    const T r = t_rcp(row[k]);
+    const bool elim = !done && lane != p;
+    if (lane == p) {
+      done = true;
+      mycol = k;
+      rinv = r;
+    }
+    const T l = a[k] * r;
+    if (elim) a[k] = l;
+    int pn = 0;
+    if (k + 1 < N) {
+      if (elim) a[k + 1] -= l * row[k + 1];
+      pn = warp_argmax_abs(a[k + 1], !done);
+    }
+#pragma unroll
+    for (int j = k + 2; j < N; ++j)
+      if (elim) a[j] -= l * row[j];
+    p = pn;
+    __syncwarp();
+  }
+}
+#else
 template <typename T, int N>
 __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T* rowbuf, unsigned char* piv, int lane) {
   using Vec = typename Num<T>::Vec;
@@ -177,6 +244,8 @@ __device__ __forceinline__ void warp_lu_factor(T (&a)[N], int& mycol, T& rinv, T
   }
 }
 
+#endif  // ROOT_LOOKAHEAD
+
 // Solve with the factors above.  In: rhs (this lane's row entry).  Out: x_lane (solution component `lane`).
 template <typename T, int N>
 __device__ __forceinline__ T warp_lu_solve(const T (&a)[N], int mycol, T rinv, T rhs, const unsigned char* piv, int lane) {
@@ -194,6 +263,78 @@ __device__ __forceinline__ T warp_lu_solve(const T (&a)[N], int mycol, T rinv, T
     if (mycol < k) rhs -= a[k] * xk;
     if (lane == k) x = xk;
   }
+  return x;
+}
+
+// Newton (a fresh Jacobian every step, factors never reused): Gauss-Jordan elimination with partial pivoting on the
+// augmented rows [J_i | f_i].  In the row-per-lane layout the elimination of the rows ABOVE the pivot costs no extra
+// instruction (the same predicated FMAs simply run on more lanes), and it removes both substitution sweeps - 64
+// dependent shuffle-broadcast steps, ~650 of the ~4100 instructions of a Newton iteration.  Pivots, multipliers and the
+// rows of U are those of the LU above bit for bit; only the order of the operations that would be the back-substitution
+// differs (rounding-level differences in the solution).  Chord keeps the LU: it reuses the factors.
+// The arg-max of step k + 1 is started as soon as column k + 1 is up to date (look-ahead, see warp_lu_factor).
+#ifndef ROOT_GJ
+#define ROOT_GJ 1
+#endif
+template <typename T, int N>
+__device__ __forceinline__ T warp_gj_solve(T (&a)[N], T rhs, T* rowbuf, int lane) {
+  using Vec = typename Num<T>::Vec;
+  constexpr int V = Num<T>::kVec;
+  static_assert(N % V == 0, "N must be a multiple of the 128-bit vector width");
+  const bool act = lane < N;
+  bool done = !act;
+  int mycol = 0;
+  T rinv = T(0);
+  int p = warp_argmax_abs(a[0], !done);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int k0 = (k / V) * V;
+    if (lane == p) {
+#pragma unroll
+      for (int j = k0; j < N; j += V) {
+        Vec v;
+        T* vv = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int q = 0; q < V; ++q) vv[q] = a[j + q];
+        *reinterpret_cast<Vec*>(rowbuf + j) = v;
+      }
+      rowbuf[N] = rhs;
+    }
+    __syncwarp();
+    T row[N];
+#pragma unroll
+    for (int j = k0; j < N; j += V) {
+      const Vec v = *reinterpret_cast<const Vec*>(rowbuf + j);
+      const T* vv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int q = 0; q < V; ++q) row[j + q] = vv[q];
+    }
+    const T rb = rowbuf[N];
+    const T r = t_rcp(row[k]);
+    const bool other = act && lane != p;  // every other row, already used as a pivot or not
+    if (lane == p) {
+      done = true;
+      mycol = k;
+      rinv = r;
+    }
+    const T l = a[k] * r;
+    int pn = 0;
+    if (k + 1 < N) {
+      if (other) a[k + 1] -= l * row[k + 1];
+      pn = warp_argmax_abs(a[k + 1], !done);
+    }
+#pragma unroll
+    for (int j = k + 2; j < N; ++j)
+      if (other) a[j] -= l * row[j];
+    if (other) rhs -= l * rb;
+    p = pn;
+    __syncwarp();
+  }
+  // row `lane` is now e_mycol * U[mycol][mycol]: unknown number mycol sits in this lane; route it to lane mycol
+  if (act) rowbuf[mycol] = rhs * rinv;
+  __syncwarp();
+  const T x = act ? rowbuf[lane] : T(0);
+  __syncwarp();
   return x;
 }
 
@@ -305,8 +446,13 @@ __global__ void __launch_bounds__(kRootWarpsPerBlock * 32, ROOT_MINBLOCKS) root_
       T fx = T(0);
       if (act) Model::eval_row(sh, ys, ctx, lane, fx, a, !p.chord);
       __syncwarp();
-      if (!p.chord) warp_lu_factor<T, N>(a, mycol, rinv, rowbuf, piv, lane);
-      const T sol = warp_lu_solve<T, N>(a, mycol, rinv, fx, piv, lane);
+      T sol;
+      if (ROOT_GJ && !p.chord) {
+        sol = warp_gj_solve<T, N>(a, fx, rowbuf, lane);
+      } else {
+        if (!p.chord) warp_lu_factor<T, N>(a, mycol, rinv, rowbuf, piv, lane);
+        sol = warp_lu_solve<T, N>(a, mycol, rinv, fx, piv, lane);
+      }
       lin_result = __all_sync(kFull, !act || t_finite(sol)) ? RES_OK : RES_SINGULAR;
       T new_y = y - sol;
       T d = sol;
