@@ -18,6 +18,12 @@
 //     redundantly, and evaluates f/grad and all dot products itself.  Identical instruction sequences give
 //     bit-identical values in all four warps, so control flow is CTA-uniform without communication, and a
 //     REJECTED step (74% of all steps on the Rosenbrock workload) needs no barrier at all.
+//   * the backtracking search is evaluated four trial points at a time (BFGS_SPEC): warp w evaluates the point the
+//     sequential search would try w rejections from now, y - 0.5^w alpha H^-1 g - the four warps' otherwise redundant
+//     evaluations become useful.  One barrier later every warp adopts the first accepted trial; `num_steps` advances
+//     by the number of trials the sequential search would have made.  The trials are the same floating-point
+//     expressions as in the sequential search (0.5^w is exact), so iterates, counts and result codes are unchanged.
+//     78% of all steps on the Rosenbrock workload are rejected ones, each a ~900-cycle dependent chain.
 //   * HBM traffic per problem: y0 in; y, num_steps, result (and optionally f, H^-1) out.
 #pragma once
 #include "common.cuh"
@@ -72,11 +78,30 @@ template <typename T> __device__ __forceinline__ T warp_dot2(T a0, T a1, T b0, T
 #ifndef BFGS_MINBLOCKS
 #define BFGS_MINBLOCKS 4
 #endif
+// BFGS_FACTORED: the rank-2 update of quasi_newton.py:379-385,
+//     H' = H + c1 s s^T - c2 (Hq s^T + s Hq^T),   c1 = (q.s + q.Hq) / (q.s)^2,  c2 = 1 / (q.s),
+// is applied as  H'_ij = H_ij + s_i a_j + b_i s_j  with  a = c1 s - c2 Hq  (one vector per step) and  b = -c2 Hq:
+// 2 FMAs per element instead of 3 multiplies + 3 FMAs.  Same update to rounding (the element-wise form is not bit-symmetric
+// either once the compiler contracts it into FMAs); 0: the element-wise form, kept for A/B runs.
+#ifndef BFGS_FACTORED
+#define BFGS_FACTORED 1
+#endif
+#ifndef BFGS_SPEC
+#define BFGS_SPEC 1
+#endif
 template <class Model, typename T>
 __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kernel(const MinParams<T> p) {
   constexpr int N = kBfgsN;
   __shared__ __align__(16) T vq[4][N], vs[4][N], vg[4][N];  // per-warp private copies: q, s, new gradient
   __shared__ __align__(16) T xhq[2][N], xnt[2][N];          // cross-warp exchange, double buffered
+#if BFGS_FACTORED
+  __shared__ __align__(16) T va[4][N];                      // per-warp: a = c1 s - c2 Hq
+#endif
+#if BFGS_SPEC
+  __shared__ __align__(16) T xye[2][4][N], xge[2][4][N];    // the four warps' trial points and gradients, double buffered
+  __shared__ T xfe[2][4];
+  __shared__ int xacc[2][4];
+#endif
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = 16 * w + (lane >> 1), hb = lane & 1, c0 = 32 * hb;
   const int n = p.n;
@@ -96,8 +121,50 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
     int result = __all_sync(kFull, t_finite(y0) && t_finite(y1)) ? RES_OK : RES_NONFINITE;
     int steps = 0, naccept = 0, buf = 0;
 
+#if BFGS_SPEC
+    int par = 0;
+#endif
     while (!terminate && result == RES_OK && steps < p.max_steps) {
       const bool y_old_finite = __all_sync(kFull, t_finite(y0) && t_finite(y1));
+#if BFGS_SPEC
+      // ---- four trial points of the backtracking search at once: warp w takes the one w rejections ahead
+      const int left = p.max_steps - steps;
+      const int nev = y_old_finite ? (left < 4 ? left : 4) : 1;  // a non-finite y ends the solve after ONE step (_iterate.py:216)
+      T aw = alpha;
+      for (int i = 0; i < w; ++i) aw = T(0.5) * aw;               // alpha after w rejections (backtracking.py:96-99), exact
+      ye0 = y0 - aw * nt0;                                         // gauss_newton.py:126-127 (the first step has nt = 0: y_eval = y0)
+      ye1 = y1 - aw * nt1;
+      T fe, ge0, ge1;
+      Model::eval(ye0, ye1, n, lane, fe, ge0, ge1);
+      T d0 = ye0 - y0, d1 = ye1 - y1;
+      {
+        const T pred = warp_dot2(g0, g1, d0, d1);
+        const T dfw = fe - f;
+        const bool acc_w = first || ((dfw <= T(0.1) * pred) && (pred <= T(0)));
+        xye[par][w][e0] = ye0, xye[par][w][e1] = ye1;
+        xge[par][w][e0] = ge0, xge[par][w][e1] = ge1;
+        if (lane == 0) xfe[par][w] = fe, xacc[par][w] = acc_w ? 1 : 0;
+      }
+      __syncthreads();
+      int kstar = -1;
+#pragma unroll
+      for (int k = 3; k >= 0; --k)
+        if (k < nev && xacc[par][k]) kstar = k;
+      const bool accept = kstar >= 0;
+      if (accept) {  // adopt trial kstar (every warp, so that the four copies of the vector state stay bit-identical)
+        ye0 = xye[par][kstar][e0], ye1 = xye[par][kstar][e1];
+        ge0 = xge[par][kstar][e0], ge1 = xge[par][kstar][e1];
+        fe = xfe[par][kstar];
+        d0 = ye0 - y0, d1 = ye1 - y1;
+        steps += kstar;  // + 1 below
+        alpha = T(1);
+      } else {
+        for (int i = 0; i < nev; ++i) alpha = T(0.5) * alpha;
+        steps += nev - 1;
+      }
+      par ^= 1;  // a slot is rewritten two rounds later: every warp has passed the next round's barrier by then
+      const T df = fe - f;
+#else
       // ---- f and gradient at the trial point (quasi_newton.py:214-216, lin_to_grad :227)
       T fe, ge0, ge1;
       Model::eval(ye0, ye1, n, lane, fe, ge0, ge1);
@@ -107,6 +174,7 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
       const T df = fe - f;
       const bool accept = first || ((df <= T(0.1) * pred) && (pred <= T(0)));
       alpha = accept ? T(1) : T(0.5) * alpha;
+#endif
       if (accept) {
         // ---- update_hessian (quasi_newton.py:342-415)
         const T q0 = ge0 - g0, q1 = ge1 - g1;
@@ -131,6 +199,11 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
           c2 = T(1) / inner;                                 // term2 coefficient (:380)
           s_i = vs[w][row];
           hq_i = xhq[buf][row];
+#if BFGS_FACTORED
+          va[w][e0] = c1 * d0 - c2 * hq0, va[w][e1] = c1 * d1 - c2 * hq1;
+          hq_i = -c2 * hq_i;  // b_i
+          __syncwarp();
+#endif
         }
         // pass 2: H' = H + c1 s s^T - c2 (Hq s^T + s Hq^T)  fused with  newton = H' g_new  (gauss_newton.py:60-61)
         T nacc = T(0);
@@ -138,8 +211,12 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
         for (int jj = 0; jj < 32; ++jj) {
           const int j = c0 + jj;
           if (update) {
+#if BFGS_FACTORED
+            h[jj] = fma(hq_i, vs[w][j], fma(s_i, va[w][j], h[jj]));
+#else
             const T s_j = vs[w][j], hq_j = xhq[buf][j];
             h[jj] = h[jj] + c1 * (s_i * s_j) - c2 * (hq_i * s_j + s_i * hq_j);
+#endif
           }
           nacc += h[jj] * vg[w][j];
         }
@@ -161,9 +238,11 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
       } else {
         terminate = false;
       }
+#if !BFGS_SPEC
       // ---- descent step (gauss_newton.py:126-127): y_eval = y - step_size * newton
       ye0 = y0 - alpha * nt0;
       ye1 = y1 - alpha * nt1;
+#endif
       result = RES_OK;
       if (!y_old_finite) result = RES_NONFINITE;
       first = false;
