@@ -77,6 +77,20 @@ template <typename T> __device__ __forceinline__ T warp_nanmax(T v) {
   return v;
 }
 
+// NaN-propagating max of NON-NEGATIVE values (x >= +0, +inf or NaN - what the scaled norms below feed it): such floats
+// order like their bit patterns read as unsigned integers, with every NaN above +inf, so the warp maximum is one integer
+// REDUX (two for a double: high words, then the low words of the lanes that hold the maximal high word) instead of five
+// shuffle rounds of compare-and-select.  Exact, like any max.
+__device__ __forceinline__ float warp_nanmax_nonneg(float v) {
+  return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v)));
+}
+__device__ __forceinline__ double warp_nanmax_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
 // ---- norms over a small per-lane-replicated vector and over warp-distributed rows -----------------------------
 // acc_* implement max_norm / two_norm / rms_norm (lineax.internal, re-exported at optimistix/_misc.py:41-45)
 template <typename T> struct NormAcc {
@@ -89,7 +103,7 @@ template <typename T> struct NormAcc {
   }
   // combine across the warp (rows distributed over lanes)
   __device__ __forceinline__ void warp_combine() {
-    if (kind == B200OPT_NORM_MAX) v = warp_nanmax(v);
+    if (kind == B200OPT_NORM_MAX) v = warp_nanmax_nonneg(v);
     else v = warp_sum(v);
   }
   __device__ __forceinline__ T finish(int count) const {

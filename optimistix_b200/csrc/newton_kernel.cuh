@@ -317,16 +317,18 @@ __device__ __forceinline__ T warp_gj_solve(T (&a)[N], T rhs, T* rowbuf, int lane
       mycol = k;
       rinv = r;
     }
-    const T l = a[k] * r;
+    // the multiplier is zeroed for the pivot row itself (and for lanes that own no row) so that the updates below are plain
+    // FMAs.  0 * inf = NaN can then reach a row that a branch would have left alone - only when the pivot row holds a
+    // non-finite entry, in which case the solution is non-finite (`singular`) either way.
+    const T l = other ? a[k] * r : T(0);
     int pn = 0;
     if (k + 1 < N) {
-      if (other) a[k + 1] -= l * row[k + 1];
+      a[k + 1] -= l * row[k + 1];
       pn = warp_argmax_abs(a[k + 1], !done);
     }
 #pragma unroll
-    for (int j = k + 2; j < N; ++j)
-      if (other) a[j] -= l * row[j];
-    if (other) rhs -= l * rb;
+    for (int j = k + 2; j < N; ++j) a[j] -= l * row[j];
+    rhs -= l * rb;
     p = pn;
     __syncwarp();
   }
