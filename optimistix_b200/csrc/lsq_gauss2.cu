@@ -1,6 +1,6 @@
 #include <stdlib.h>
 
-#include "lsq_kernel_p2c.cuh"
+#include "lsq_kernel_p2.cuh"
 #include "lsq_launch.cuh"
 namespace b200opt {
 
@@ -29,24 +29,6 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
 }
 
-// cooperative-algebra kernel (lsq_kernel_p2c.cuh): W problems per CTA, their 8 x 8 algebra in W lanes of one warp
-template <bool TRUST, int W, int MINB> static int lsq_launch_p2c(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2c<Gauss2P2, TRUST, 4, W, MINB>;
-  const size_t smem = lsq_coop_smem_bytes<W>(p.m_pad, Gauss2P2::N, Gauss2P2::NAUX);
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem), "occupancy")) return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-  }
-  const int64_t need = (p.batch + W - 1) / W;
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
-  const int grid = (int)(need < cap ? need : cap);
-  kern<<<grid, W * 32, smem, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2c launch");
-}
-
 int lsq_launch_gauss2(const LsqArgs& a) {
   static const bool scalar_only = getenv("B200OPT_LSQ_SCALAR") != nullptr;  // A/B switch for profiling
   const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
@@ -72,11 +54,6 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.root_near_zero = 0;
     p.vec_ok = 1;
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
-    static const int coop = getenv("B200OPT_LSQ_COOP") ? atoi(getenv("B200OPT_LSQ_COOP")) : 0;  // A/B switch: 0 = one warp does it all
-    if (coop && a.m == 256 && a.batch > 0) {
-      if (coop == 4) return lm ? lsq_launch_p2c<true, 4, 4>(p, a.stream) : lsq_launch_p2c<false, 4, 4>(p, a.stream);
-      return lm ? lsq_launch_p2c<true, 8, 2>(p, a.stream) : lsq_launch_p2c<false, 8, 2>(p, a.stream);
-    }
     int rc;
     if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
     else rc = lm ? lsq_launch_p2<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 0>(p, a.stream);

@@ -442,6 +442,11 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
   }
 }
 
+// (A cooperative-algebra variant - a CTA of W = 4 / 8 warps iterating W problems in lock step, the 8 x 8 algebra of all W problems
+// in W lanes of one warp between two block barriers - was measured and dropped: bit-identical results, 530 instead of 878
+// instructions per problem-iteration, but 24.1 / 26.0 ms against 14.55 ms.  The kernel is bound by the LATENCY of a problem's
+// step (sweeps + algebra chain) times the 16 problems resident per SM; taking the algebra out of 3 of 4 warps removes issue
+// pressure that was not the limit and halves the warps available to hide that latency.  See git history and DESIGN.md section 10.)
 // (A half-warp-per-problem variant - two problems per warp sharing the replicated 8 x 8 algebra - was measured and dropped:
 // 10% fewer instructions but only 22.8 of 32 lanes active on average (accept / reject and iteration counts differ between the
 // two problems) and 12 instead of 16 warps per SM: 16.8 ms against 15.6 ms for 1 Mi fits.  See git history and profiles/README.md.)
