@@ -1,7 +1,6 @@
-#include <stdio.h>
 #include <stdlib.h>
 
-#include "lsq_kernel_p2l.cuh"
+#include "lsq_kernel_p2.cuh"
 #include "lsq_launch.cuh"
 namespace b200opt {
 
@@ -30,27 +29,6 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
 }
 
-// register-lean variant (lsq_kernel_p2l.cuh): same results, 96 registers, five CTAs per SM
-template <bool TRUST> static int lsq_launch_p2l(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2l<Gauss2P2, TRUST, 4>;
-  const size_t per_warp = WarpReduceLayout<float, Tri<Gauss2P2::N>::size + Gauss2P2::N>::elems + (size_t)(3 + Gauss2P2::NAUX) * p.m_pad;
-  const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout")) return B200OPT_ECUDA;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy")) return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-    if (getenv("B200OPT_LSQ_VERBOSE")) fprintf(stderr, "[b200opt] lsq_solve_kernel_p2l: %d CTAs/SM, %zu B smem\n", blocks_per_sm, smem);
-  }
-  const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
-  const int grid = (int)(need < cap ? need : cap);
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2l launch");
-}
-
 int lsq_launch_gauss2(const LsqArgs& a) {
   static const bool scalar_only = getenv("B200OPT_LSQ_SCALAR") != nullptr;  // A/B switch for profiling
   const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
@@ -76,8 +54,6 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.root_near_zero = 0;
     p.vec_ok = 1;
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
-    static const bool lean = getenv("B200OPT_LSQ_LEAN") != nullptr;  // A/B switch until measured
-    if (lean && a.m == 256) return lm ? lsq_launch_p2l<true>(p, a.stream) : lsq_launch_p2l<false>(p, a.stream);
     int rc;
     if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
     else rc = lm ? lsq_launch_p2<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 0>(p, a.stream);

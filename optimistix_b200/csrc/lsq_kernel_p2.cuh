@@ -447,6 +447,10 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 // instructions per problem-iteration, but 24.1 / 26.0 ms against 14.55 ms.  The kernel is bound by the LATENCY of a problem's
 // step (sweeps + algebra chain) times the 16 problems resident per SM; taking the algebra out of 3 of 4 warps removes issue
 // pressure that was not the limit and halves the warps available to hide that latency.  See git history and DESIGN.md section 10.)
+// (A register-lean variant - G and g resident in shared memory between reductions, the Gram sweep in three parts, 94 registers
+// without spills, FIVE CTAs = 20 problems per SM - was measured and dropped as well: bit-identical results, 15.15 ms against
+// 14.55 ms.  The extra shared-memory traffic and Jacobian-row recomputation cost more than the fifth CTA hides: this kernel has
+// no single limiter (ncu, lsq_r10: issue slots 62%, FMA pipe 57%, shared-memory wavefronts 45% of peak).)
 // (A half-warp-per-problem variant - two problems per warp sharing the replicated 8 x 8 algebra - was measured and dropped:
 // 10% fewer instructions but only 22.8 of 32 lanes active on average (accept / reject and iteration counts differ between the
 // two problems) and 12 instead of 16 warps per SM: 16.8 ms against 15.6 ms for 1 Mi fits.  See git history and profiles/README.md.)
