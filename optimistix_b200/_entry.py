@@ -16,7 +16,6 @@ There is no CPU implementation behind these functions: without the CUDA library 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any
 
 import numpy as np
 

@@ -11,7 +11,7 @@ written with torch ops, so that `fn(y, args)` can still be *evaluated* like the 
 from __future__ import annotations
 
 import dataclasses
-from typing import Any, Callable
+from typing import Callable
 
 KIND_LSQ, KIND_ROOT, KIND_MIN = 0, 1, 2
 

@@ -2,7 +2,6 @@
 respect to `args` by the implicit function theorem, against closed forms and finite differences of the solve itself
 (the reference's own check: tests/test_root_find.py:58-130, test_least_squares.py:56-129, test_minimise.py:65-129
 compare the JVP with finite differences / the unrolled solve).  GPU."""
-import numpy as np
 import pytest
 import torch
 
