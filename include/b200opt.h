@@ -297,6 +297,39 @@ int32_t b200opt_gn_gram_linear_xchg(const float* J, const float* y, const float*
                                     int32_t parity, uint32_t seq, void* stream);
 int32_t b200opt_gn_solve_xchg(const void* xchg_local, int32_t world, int32_t parity, uint32_t seq, int32_t n, double lambda,
                               float* p_out, int32_t* status_out, float* summary_out, void* workspace, void* stream);
+/* ---- state-driven iteration of the large problem: the whole Gauss-Newton loop on the device ----------------------------
+ * Replaces, for the "linear_rows" family, the body of the reference's while loop (optimistix/_iterate.py:194-268 around
+ * AbstractGaussNewton.step, _solver/gauss_newton.py:243-334, with LearningRate(1.0) and NewtonDescent): the carry
+ * (y, y_eval, num_steps, terminate, result) lives in a device `state` of b200opt_gn_state_size() bytes.
+ *   b200opt_gn_init     writes the initial carry (y = y_eval = y0; nonfinite y0 => result nonfinite), zero-fills the residual
+ *                       buffer the first f-space test compares against (r_old0 = the `r1` later given to _iterate) and the
+ *                       counters in `workspace`.  solver: 0 = equilibrated fp32 blocked Cholesky + fp64 refinement with an
+ *                       fp64 fallback when the refinement step is not small, 1 = fp64 Cholesky only.  timeout_ms bounds the
+ *                       in-kernel wait for the peers (<= 0: 30 s).
+ *   b200opt_gn_iterate  enqueues ONE iteration = two kernels: (1) the fused residual + tcgen05 Gram pass at state.y_eval
+ *                       (J read once), the cross-CTA reduction and - when xchg_bases_dev / xchg_local are given - the
+ *                       publication of this rank's [G | g | r^T r | f-statistic] into every peer's exchange buffer, all in
+ *                       one cooperative launch; (2) one CTA that waits for every rank's flag, sums the blocks in rank order
+ *                       in fp64, solves (G + lambda I) p = g, applies the Cauchy test on y and f (_misc.py:291-310), and
+ *                       advances the carry (y <- y_eval, y_eval <- y_eval - p, num_steps + 1, result).
+ *                       Once state.terminate is set, state.result != successful or num_steps == max_steps, both kernels
+ *                       return at once: the host may enqueue iterations ahead and read `state` back every few calls.
+ * Residual buffers r0, r1 [m_local] (16-byte aligned): step k writes r[k & 1] and compares against r[(k & 1) ^ 1].
+ * `out` [n*n+n+2] fp32 receives this rank's block; `workspace` as for b200opt_gn_gram.  State layout (little-endian):
+ * float y[256]; float y_eval[256]; int32 num_steps, terminate, result, max_steps; float rtol, atol, r^T r, f-statistic;
+ * int32 timeout_ms, solver, fallbacks, pad. */
+/* The solver of the state-driven iteration as a stand-alone call (n == 256; parts as for b200opt_gn_solve_parts, 16-byte
+ * aligned, part_stride a multiple of 4).  solver 0: equilibrated fp32 blocked Cholesky in shared memory + fp64 refinement,
+ * fp64 fallback; 1: fp64.  info_out (optional, device int32): 1 = the fp32 + refinement path produced the solution. */
+int32_t b200opt_gn_solve_fast(const float* parts, int32_t nparts, int64_t part_stride, int32_t n, double lambda, int32_t solver,
+                              float* p_out, int32_t* status_out, float* summary_out, int32_t* info_out, void* workspace,
+                              void* stream);
+int64_t b200opt_gn_state_size(void);
+int32_t b200opt_gn_init(void* state, const float* y0, int32_t n, double rtol, double atol, int32_t max_steps, int32_t solver,
+                        int32_t timeout_ms, float* r_old0, int64_t m_local, float* out, void* workspace, void* stream);
+int32_t b200opt_gn_iterate(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, void* state,
+                           float* out, void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world,
+                           int32_t rank, double rtol, double atol, double lambda, void* stream);
 /* r = J y - d for the "linear_rows" family (one coalesced pass over the row shard). If r_old is not NULL the
  * f-space half of cauchy_termination (optimistix/_misc.py:306-309) is fused in: *fmax_bits (device, caller-zeroed)
  * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */

@@ -86,7 +86,13 @@ def implicit_attach(rewrite, Y, args, args_in_dims):
                     J = t.func.vmap(t.func.jacfwd(lambda y: rewrite(y, a)))(Ystar)
                 else:
                     J = t.func.vmap(t.func.jacfwd(rewrite), in_dims=(0, args_in_dims))(Ystar, a)
-                w, _ = lu_solve(J.transpose(1, 2), v.contiguous())
+                w, status = lu_solve(J.transpose(1, 2), v.contiguous())
+                # lx.linear_solve inside implicit_jvp (_ad.py:110) raises on a singular operator; a silent NaN gradient
+                # would be worse than the synchronisation this check costs
+                nbad = int((status != 0).sum().item())
+                if nbad:
+                    raise RuntimeError(f"ImplicitAdjoint: d(optimality residual)/dy is singular at the solution of {nbad} of "
+                                       f"{status.numel()} problems; the implicit gradient does not exist there")
                 _, vjp_fn = t.func.vjp(lambda *ls: batched_rewrite(Ystar, *ls), *dl)
                 grads = vjp_fn(-w)
             return (None, *grads)

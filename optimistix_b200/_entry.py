@@ -168,6 +168,16 @@ def _attach_registered(adjoint, kind, model, a, y_out, buf):
     return attach_if_needed(adjoint, kind, lambda y, ad: model.torch_fn(y, ad), y_out, a, in_dims)
 
 
+def _on_device_of(buf, like):
+    """Kernels launch on the CURRENT device: make it the one that holds the buffers (a caller with tensors on cuda:1 need
+    not have switched devices, exactly as with torch's own operators)."""
+    import contextlib
+
+    if not buf.device:
+        return contextlib.nullcontext()
+    return _torch().cuda.device(like.device)
+
+
 def _stream_ptr(buf, like):
     if not buf.device:
         return None
@@ -280,9 +290,10 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     if buf.device:
         step_size = buf.empty((B,), y0)
         nacc = buf.empty_i32((B,), y0)
-        code = lib.b200opt_least_squares(solver_id, fn.model_id, buf.dtype_code, B, n, m, buf.ptr(y0), buf.ptr(shared),
-                                         buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res),
-                                         buf.ptr(step_size), buf.ptr(nacc), _stream_ptr(buf, y0))
+        with _on_device_of(buf, y0):
+            code = lib.b200opt_least_squares(solver_id, fn.model_id, buf.dtype_code, B, n, m, buf.ptr(y0), buf.ptr(shared),
+                                             buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res),
+                                             buf.ptr(step_size), buf.ptr(nacc), _stream_ptr(buf, y0))
         extra = {"step_size": step_size, "num_accepted_steps": nacc}
     else:
         t = _torch()
@@ -350,9 +361,10 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
     steps = buf.empty_i32((B,), y0)
     res = buf.empty_i32((B,), y0)
     if buf.device:
-        code = lib.b200opt_root_find(solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared), buf.ptr(prob),
-                                     stride, buf.ptr(lower), buf.ptr(upper), C.byref(opts), buf.ptr(y_out), buf.ptr(steps),
-                                     buf.ptr(res), _stream_ptr(buf, y0))
+        with _on_device_of(buf, y0):
+            code = lib.b200opt_root_find(solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared), buf.ptr(prob),
+                                         stride, buf.ptr(lower), buf.ptr(upper), C.byref(opts), buf.ptr(y_out), buf.ptr(steps),
+                                         buf.ptr(res), _stream_ptr(buf, y0))
     else:
         if lower is not None or upper is not None:
             raise NotImplementedError("lower/upper bounds are only wired on the device-pointer entry point")
@@ -484,9 +496,10 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
         f_out = buf.empty((B,), y0)
         nacc = buf.empty_i32((B,), y0)
         hinv = buf.empty((B, n, n), y0) if return_hessian_inv else None
-        code = lib.b200opt_minimise(_lib.SOLVER_BFGS, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), None, None, 0,
-                                    C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res), buf.ptr(f_out),
-                                    buf.ptr(hinv), buf.ptr(nacc), _stream_ptr(buf, y0))
+        with _on_device_of(buf, y0):
+            code = lib.b200opt_minimise(_lib.SOLVER_BFGS, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), None, None, 0,
+                                        C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res), buf.ptr(f_out),
+                                        buf.ptr(hinv), buf.ptr(nacc), _stream_ptr(buf, y0))
         extra = {"num_accepted_steps": nacc}
         state = {"f": f_out, "hessian_inv": hinv}
     else:

@@ -38,8 +38,12 @@ def _batched_r_and_J(fn, args, args_in_dims, jac_mode, single):
             r = fn(y, args)
             return r.reshape(-1)
 
+        def value_and_aux(z):
+            r = one(z)  # ONE evaluation of the user function per Jacobian pass: the residual rides along as `aux`
+            return r, r
+
         def both(y):
-            J, r = jacf(lambda z: (one(z), one(z)), has_aux=True)(y)
+            J, r = jacf(value_and_aux, has_aux=True)(y)
             return r, J
 
         return t.func.vmap(both)
@@ -48,7 +52,11 @@ def _batched_r_and_J(fn, args, args_in_dims, jac_mode, single):
         return fn(y, a).reshape(-1)
 
     def both_a(y, a):
-        J, r = jacf(lambda z: (one_a(z, a), one_a(z, a)), has_aux=True)(y)
+        def value_and_aux(z):
+            r = one_a(z, a)
+            return r, r
+
+        J, r = jacf(value_and_aux, has_aux=True)(y)
         return r, J
 
     vm = t.func.vmap(both_a, in_dims=(0, args_in_dims))

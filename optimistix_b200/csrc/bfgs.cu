@@ -22,12 +22,9 @@ static int min_launch(int64_t batch, int n, const void* y0, const b200opt_option
   p.norm = o->norm;
   p.max_steps = o->max_steps;
   auto kern = bfgs_solve_kernel<Model, T>;
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBfgsThreads, 0), "occupancy")) return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-  }
+  static LaunchCache cache;
+  const int blocks_per_sm = cache.configure(kern, kBfgsThreads, 0);
+  if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
   const int grid = (int)(batch < cap ? batch : cap);
   kern<<<grid, kBfgsThreads, 0, stream>>>(p);

@@ -91,6 +91,23 @@ __device__ __forceinline__ double warp_nanmax_nonneg(double v) {
   return __hiloint2double((int)mh, (int)ml);
 }
 
+// ---- predicted reduction of ClassicalTrustRegion (trust_region.py:182-186) from the carried Gram quantities ------------
+// The reference evaluates  0.5 (|J d + r|^2 - |r|^2)  by forming both squared norms in floating point and subtracting
+// them: its value is quantised to the spacing of |r|^2 and is exactly 0 once the step is too small to move |r|^2.  The
+// accept test `df <= 0.01 pred` near convergence depends on that (df is 0 or +-1 spacing there): with the exactly
+// evaluated d.g + 0.5 d.G d < 0 a step with df == 0 is rejected, with the reference's quantity it is accepted, and the
+// exact form costs +2-3 % iterations on the LM workloads (measured with the oracle: tests/test_oracle_pred_modes.py).
+// So |J d + r|^2 is formed through the Gram identity  r.r + (2 d.g + d.G d)  and then rounded and subtracted exactly as the
+// reference does.  `lin` = d.g, `quad` = d.G d, `rr` = r.r.  The adds are explicit (no contraction, no re-association).
+__device__ __forceinline__ float predicted_reduction(float lin, float quad, float rr) {
+  const float jt = __fadd_rn(rr, __fmaf_rn(2.f, lin, quad));  // |J d + r|^2 at the precision of |r|^2
+  return 0.5f * __fsub_rn(jt, rr);
+}
+__device__ __forceinline__ double predicted_reduction(double lin, double quad, double rr) {
+  const double jt = __dadd_rn(rr, __fma_rn(2.0, lin, quad));
+  return 0.5 * __dsub_rn(jt, rr);
+}
+
 // ---- norms over a small per-lane-replicated vector and over warp-distributed rows -----------------------------
 // acc_* implement max_norm / two_norm / rms_norm (lineax.internal, re-exported at optimistix/_misc.py:41-45)
 template <typename T> struct NormAcc {
@@ -158,6 +175,49 @@ __device__ __forceinline__ void spd_solve(const T (&G)[Tri<N>::size], T lam, con
 // thread-local last-error string (host side)
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+}  // namespace b200opt
+#include <mutex>
+namespace b200opt {
+
+// Launch configuration of ONE kernel (one `static LaunchCache` per launcher instantiation), kept PER DEVICE ORDINAL and
+// shared by all host threads: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, process-wide property of a
+// kernel, so a host thread that drives cuda:0 and then cuda:1 (the `_host` entry points take a device argument) has to
+// raise it on each device, and the value may only ever grow (another thread's launch may rely on the larger one).
+struct LaunchCache {
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu;
+  size_t smem_set[kMaxDevices];  // largest dynamic shared-memory size the attribute was raised to on this device
+  size_t occ_smem[kMaxDevices];  // shared-memory size the cached occupancy belongs to
+  int blocks[kMaxDevices];       // resident blocks per SM at occ_smem
+  LaunchCache() {
+    for (int d = 0; d < kMaxDevices; ++d) smem_set[d] = 0, occ_smem[d] = ~size_t(0), blocks[d] = 1;
+  }
+  // Makes `smem` bytes of dynamic shared memory launchable on the current device and returns the number of resident
+  // blocks per SM for (threads, smem) (>= 1), or -1 after set_error().
+  template <class Kernel> int configure(Kernel kern, int threads, size_t smem) {
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+    if (dev < 0 || dev >= kMaxDevices) {
+      set_error("device ordinal %d outside the launch cache (%d devices)", dev, kMaxDevices);
+      return -1;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > smem_set[dev] && smem > 48 * 1024) {
+      if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                     "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+        return -1;
+      smem_set[dev] = smem;
+    }
+    if (occ_smem[dev] != smem) {
+      int occ = 0;
+      if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+        return -1;
+      blocks[dev] = occ > 0 ? occ : 1;
+      occ_smem[dev] = smem;
+    }
+    return blocks[dev];
+  }
+};
 #endif
 
 }  // namespace b200opt

@@ -32,9 +32,13 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "gn_state.cuh"
 
 namespace b200opt {
 int device_sm_count();
+// workspace layout (b200opt_gn_gram_workspace_size): [256 per-CTA partials][fp64 n x n scratch of the solve][counters, 4 KiB]
+size_t gn_workspace_solve_offset() { return (size_t)256 * (256 * 256 + 256 + 4) * 4; }
+size_t gn_workspace_sync_offset() { return gn_workspace_solve_offset() + (size_t)256 * 256 * 8; }
 
 namespace gram {
 
@@ -135,6 +139,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Exchange buffer of the row-sharded problem (one per rank, mapped into every peer by CUDA IPC):
+//   float    slots[2 parities][world][XCHG_STRIDE]   slot [p][q] = rank q's [G | g | rr | f-stat] of an iteration with parity p
+//   uint32   flags[2][world]                           flags[p][q] = sequence number of the last block rank q published there
+//   uint32   done                                      local "last block" counter of the publishing kernel
+//   uint32   seq_counter                               local: sequence number of the last COMPLETED exchange (state-driven path)
+constexpr int XCHG_STRIDE = N * N + N + 4;
+__host__ __device__ inline size_t xchg_flags_offset(int world) { return (size_t)2 * world * XCHG_STRIDE * sizeof(float); }
+__host__ __device__ inline size_t xchg_bytes(int world) { return xchg_flags_offset(world) + (size_t)(2 * world + 4) * sizeof(unsigned); }
+
+struct PeerXchg {
+  unsigned char* const* bases;  // device array [world]: every rank's exchange buffer as mapped in THIS process (NULL: no exchange)
+  int world, rank, parity;
+  unsigned seq;
+  const unsigned* seq_counter;  // state-driven path: seq = *seq_counter + 1, parity = seq & 1 (the solve kernel advances it)
+};
+
 struct Params {
   const float* r;      // [m] residual (plain mode), or the data vector d (fused mode: r = J y - d is formed in-kernel)
   const float* y;      // [N] fused mode: current iterate; NULL = plain mode
@@ -145,7 +165,16 @@ struct Params {
   int64_t m;
   float* ws;           // per-CTA partials: [grid][N*N + N + 1] (+ padding to a multiple of 4 floats)
   int num_tiles;
-  int debug;            // ablation switches for profiling only (env B200OPT_GRAM_DEBUG): 1 no MMA, 2 no g loop, 4 no fused r
+  // ---- state-driven iteration (b200opt_gn_iterate): y_eval, the residual ping-pong parity and the frozen flag come from
+  // the device state; the cross-CTA reduction, the mirror of the triangle and the publication to the peers are folded into
+  // this kernel (cooperative launch: the CTAs meet at a grid-wide counter before each reduces its slice of the output).
+  const GnState* state;  // NULL: y / r_old / r_out above are used as given
+  float* rbuf0;          // residual buffers; step k writes rbuf[k & 1] and compares against rbuf[(k & 1) ^ 1]
+  float* rbuf1;
+  float* out;            // fold: [G | g | rr | f-stat]; NULL: per-CTA partials only (gram_reduce_kernel follows)
+  unsigned* sync;        // fold: two grid-wide counters (arrived, reduced), zero between launches
+  PeerXchg x;            // fold: publication of `out` into every peer's exchange buffer
+  int debug;            // ablation switches for profiling only (build-time constant in the launcher): 1 no MMA, 2 no g loop, 4 no fused r
 };
 constexpr int WS_STRIDE = N * N + N + 4;
 
@@ -163,6 +192,16 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
   uint64_t* accum_done = empty + STAGES;                                    // last MMA retired -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
 
+  const float* y_ptr = p.y;
+  const float* r_old_ptr = p.r_old;
+  float* r_out_ptr = p.r_out;
+  if (p.state) {
+    if (gn_frozen(p.state)) return;  // uniform over the grid: the solve has ended, this iteration is a no-op
+    const int par = p.state->steps & 1;
+    y_ptr = p.state->y_eval;
+    r_out_ptr = par ? p.rbuf1 : p.rbuf0;
+    r_old_ptr = par ? p.rbuf0 : p.rbuf1;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -194,13 +233,13 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
         const int64_t row0 = tile * KROWS;
         const int64_t rows_left = p.m - row0;
         const uint32_t r_bytes = (uint32_t)((rows_left < KROWS ? rows_left : KROWS) * 4);
-        const bool with_old = p.y != nullptr && p.r_old != nullptr;
+        const bool with_old = y_ptr != nullptr && r_old_ptr != nullptr;
         mbar_expect_tx(&full[s], TILE_BYTES + r_bytes * (with_old ? 2u : 1u));  // OOB rows are zero-filled and still counted
         unsigned char* dst = tiles + (size_t)s * TILE_BYTES;
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) tma_load_2d(dst + g * GROUP_BYTES, &tmap, g * BOX_COLS, (int)row0, &full[s]);
         bulk_load_1d(rs + s * KROWS, p.r + row0, r_bytes, &full[s]);
-        if (with_old) bulk_load_1d(ros + s * KROWS, p.r_old + row0, r_bytes, &full[s]);
+        if (with_old) bulk_load_1d(ros + s * KROWS, r_old_ptr + row0, r_bytes, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -234,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     // immediately accumulates J[row][c] * r[row] into its 32 column partials of g.  Shared memory is read exactly once
     // (512 wavefronts per 64 KiB tile) - it is the contended resource: the tensor core streams its operands from it too.
     const int b = threadIdx.x - 64;                 // 0..255
-    const bool fused = p.y != nullptr;
+    const bool fused = y_ptr != nullptr;
     constexpr int LPR = 8;                          // lanes per row
     constexpr int RPP = 32 / LPR;                   // rows per warp per pass (4)
     constexpr int PASSES = KROWS / (8 * RPP);       // passes per tile (2 for 64-row tiles)
@@ -247,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
 #pragma unroll
     for (int j = 0; j < NGRP; ++j)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yreg[j * 8 + e] = fused ? p.y[(gsel + 2 * j) * 32 + my_atom * 8 + (e ^ (flip << 2))] : 0.f;
+      for (int e = 0; e < 8; ++e) yreg[j * 8 + e] = fused ? y_ptr[(gsel + 2 * j) * 32 + my_atom * 8 + (e ^ (flip << 2))] : 0.f;
     float acc_g[NGRP * 8];
 #pragma unroll
     for (int c = 0; c < NGRP * 8; ++c) acc_g[c] = 0.f;
@@ -293,8 +332,8 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
           if (row >= rows) rv = 0.f;                 // ragged last tile: J rows are zero-filled, r / d rows are stale
           if (sub == 0 && row < rows) {
             if (fused) {
-              p.r_out[tile * KROWS + row] = rv;
-              if (p.r_old) worst = nan_max(worst, fabsf(rv - ros[s * KROWS + row]) / (p.atol + p.rtol * fabsf(rv)));
+              r_out_ptr[tile * KROWS + row] = rv;
+              if (r_old_ptr) worst = nan_max(worst, fabsf(rv - ros[s * KROWS + row]) / (p.atol + p.rtol * fabsf(rv)));
             }
             acc_rr = fmaf(rv, rv, acc_rr);
           }
@@ -372,6 +411,70 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    if (p.out) {
+      // ================================ folded reduction + publication ================================
+      // Every CTA's partial is in the workspace: meet at the grid-wide counter (all CTAs are co-resident: cooperative
+      // launch, one CTA per SM), then CTA c adds slice c of the output over the partials in CTA order - the same fixed
+      // order as gram_reduce_kernel, so the two paths are bit-identical - mirrors the triangle that was not computed and,
+      // in a row-sharded run, stores each value straight into this rank's slot of every peer's exchange buffer (P2P
+      // stores over NVLink / NVSwitch).  The last CTA to finish raises this rank's flag on every peer.
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (b == 0) {
+        atomicAdd(p.sync, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(p.sync) < gridDim.x) __nanosleep(64);
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      constexpr int TOTAL = N * N + N + 2;  // G | g | rr | f-stat
+      const int per = (TOTAL + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int lo = (int)blockIdx.x * per;
+      const int hi = lo + per < TOTAL ? lo + per : TOTAL;
+      unsigned seq = p.x.seq;
+      int parity = p.x.parity;
+      if (p.x.bases && p.x.seq_counter) {
+        seq = *p.x.seq_counter + 1u;
+        parity = (int)(seq & 1u);
+      }
+      for (int idx = lo + b; idx < hi; idx += 256) {
+        float sv;
+        if (idx < N * N + N + 1) {
+          int src = idx;
+          if (idx < N * N) {
+            const int a = idx / N, c = idx % N;
+            if (a >= 128 && c < 128) src = c * N + a;  // lower-left block: the transposed entry of the upper-right block
+          }
+          sv = 0.f;
+          const float* w = p.ws + src;
+#pragma unroll 4
+          for (int c = 0; c < (int)gridDim.x; ++c) sv += __ldcg(w + (size_t)c * WS_STRIDE);
+          p.out[idx] = sv;
+        } else {
+          sv = __ldcg(p.out + idx);  // the f-statistic (atomicMax target of every CTA; complete after the grid-wide meeting)
+        }
+        if (p.x.bases) {
+          const size_t off = ((size_t)(parity * p.x.world + p.x.rank) * XCHG_STRIDE + idx) * sizeof(float);
+          for (int q = 0; q < p.x.world; ++q) *reinterpret_cast<float*>(p.x.bases[q] + off) = sv;
+        }
+      }
+      if (p.x.bases) __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA is counted
+      else __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (b == 0) {
+        const unsigned prev = atomicAdd(p.sync + 1, 1u);
+        if (prev == gridDim.x - 1) {  // last CTA: every other CTA has fenced and counted
+          p.sync[0] = 0;
+          p.sync[1] = 0;
+          if (p.x.bases) {
+            __threadfence_system();
+            for (int q = 0; q < p.x.world; ++q) {
+              volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(p.x.bases[q] + xchg_flags_offset(p.x.world)) + parity * p.x.world + p.x.rank;
+              *flag = seq;
+            }
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -379,20 +482,6 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
-
-// Exchange buffer of the row-sharded problem (one per rank, mapped into every peer by CUDA IPC):
-//   float    slots[2 parities][world][XCHG_STRIDE]   slot [p][q] = rank q's [G | g | rr | f-stat] of an iteration with parity p
-//   uint32   flags[2][world]                           flags[p][q] = sequence number of the last block rank q published there
-//   uint32   done                                      local "last block" counter of the publishing kernel
-constexpr int XCHG_STRIDE = N * N + N + 4;
-__host__ __device__ inline size_t xchg_flags_offset(int world) { return (size_t)2 * world * XCHG_STRIDE * sizeof(float); }
-__host__ __device__ inline size_t xchg_bytes(int world) { return xchg_flags_offset(world) + (size_t)(2 * world + 4) * sizeof(unsigned); }
-
-struct PeerXchg {
-  unsigned char* const* bases;  // device array [world]: every rank's exchange buffer as mapped in THIS process (NULL: no exchange)
-  int world, rank, parity;
-  unsigned seq;
-};
 
 // Deterministic reduction of the per-CTA partials, mirroring the triangle that was not computed.
 // out = [G (N*N, full symmetric) | g (N) | rr]   (slot N*N+N+1, the f-statistic, was written by gram_kernel's atomicMax)
@@ -462,13 +551,18 @@ extern "C" {
 
 int64_t b200opt_gn_gram_workspace_size(int32_t n) {
   if (n != gram::N) return -1;
-  // per-CTA partials for up to 256 CTAs + an fp64 n x n scratch for b200opt_gn_solve
-  return (int64_t)256 * gram::WS_STRIDE * 4 + (int64_t)n * n * 8 + 4096;
+  // per-CTA partials for up to 256 CTAs + an fp64 n x n scratch for the solve kernel + 4 KiB (grid-wide counters)
+  return (int64_t)gn_workspace_sync_offset() + 4096;
 }
 
+// `fold`: state-driven iteration (b200opt_gn_iterate) - reduction and publication inside gram_kernel (cooperative launch)
+struct GnFold {
+  const GnState* state;
+  float *rbuf0, *rbuf1;
+};
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
                             float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream,
-                            gram::PeerXchg x = gram::PeerXchg{nullptr, 0, 0, 0, 0});
+                            gram::PeerXchg x = gram::PeerXchg{nullptr, 0, 0, 0, 0, nullptr}, const GnFold* fold = nullptr);
 
 int32_t b200opt_gn_gram(const float* J, const float* r, int64_t m_local, int32_t n, float* out, void* workspace, void* stream) {
   return gn_gram_impl(J, r, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, m_local, n, out, workspace, stream);
@@ -538,14 +632,35 @@ int32_t b200opt_gn_gram_linear_xchg(const float* J, const float* y, const float*
     set_error("gn_gram_linear_xchg: the f-statistic must live in slot n*n+n+1 of `out` (it is published with the block)");
     return B200OPT_EINVAL;
   }
-  gram::PeerXchg x{reinterpret_cast<unsigned char* const*>(const_cast<void* const*>(xchg_bases_dev)), world, rank, parity, seq};
+  gram::PeerXchg x{reinterpret_cast<unsigned char* const*>(const_cast<void* const*>(xchg_bases_dev)), world, rank, parity, seq, nullptr};
   return gn_gram_impl(J, d, y, r_old, r_out, fmax_bits, rtol, atol, m_local, n, out, workspace, stream, x);
 }
 
 }  // extern "C"
 
+namespace b200opt {
+// first half of b200opt_gn_iterate (gn_large.cu): fused residual + Gram pass driven by the device state, reduction and
+// publication folded into the kernel
+int32_t gn_iterate_gram(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, const void* state, float* out,
+                        void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world, int32_t rank, float rtol,
+                        float atol, void* stream) {
+  gram::PeerXchg x{nullptr, 0, 0, 0, 0, nullptr};
+  if (xchg_bases_dev) {
+    x.bases = reinterpret_cast<unsigned char* const*>(const_cast<void* const*>(xchg_bases_dev));
+    x.world = world;
+    x.rank = rank;
+    x.seq_counter = reinterpret_cast<const unsigned*>(static_cast<const unsigned char*>(xchg_local) + gram::xchg_flags_offset(world)) + 2 * world + 1;
+  }
+  GnFold fold{static_cast<const GnState*>(state), r0, r1};
+  uint32_t* fmax_bits = reinterpret_cast<uint32_t*>(out + gram::N * gram::N + gram::N + 1);
+  // y / r_old / r_out are taken from the state inside the kernel; `r0` stands in so that the argument checks see buffers
+  return gn_gram_impl(J, d, static_cast<const GnState*>(state)->y_eval, r1, r0, fmax_bits, rtol, atol, m_local, n, out, workspace, stream, x, &fold);
+}
+}  // namespace b200opt
+
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
-                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream, gram::PeerXchg x) {
+                            float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream, gram::PeerXchg x,
+                            const GnFold* fold) {
   if (n != gram::N) {
     set_error("gn_gram: this build supports n = %d parameters only (got %d)", gram::N, n);
     return B200OPT_EINVAL;
@@ -569,7 +684,7 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   if (grid > 256) grid = 256;
   if (num_tiles < grid) grid = num_tiles > 0 ? num_tiles : 1;
   if (m_local == 0) {
-    if (x.bases) {
+    if (x.bases || fold) {
       set_error("gn_gram: a rank of a peer exchange must own at least one row");
       return B200OPT_EINVAL;
     }
@@ -593,15 +708,24 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
     set_error("gn_gram: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     return B200OPT_ECUDA;
   }
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(gram::gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram::SMEM_BYTES),
-                   "gram smem attr"))
-      return B200OPT_ECUDA;
-    attr_set = true;
+  static LaunchCache cache;
+  if (cache.configure(gram::gram_kernel, gram::THREADS, gram::SMEM_BYTES) < 0) return B200OPT_ECUDA;
+  constexpr int debug = 0;  // ablation switch of profiles/README.md (1: TMA only, 2: TMA + MMA); a build-time constant in release
+  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, nullptr, nullptr, nullptr, nullptr, nullptr,
+                 gram::PeerXchg{nullptr, 0, 0, 0, 0, nullptr}, debug};
+  if (fold) {
+    // grid-wide meeting inside the kernel: cooperative launch guarantees that all CTAs are resident at the same time
+    p.state = fold->state;
+    p.rbuf0 = fold->rbuf0;
+    p.rbuf1 = fold->rbuf1;
+    p.out = out;
+    p.sync = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + gn_workspace_sync_offset());
+    p.x = x;
+    void* args[] = {&tmap, &p};
+    return check_cuda(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gram::gram_kernel), dim3(grid), dim3(gram::THREADS), args,
+                                                  gram::SMEM_BYTES, st),
+                      "gram_kernel cooperative launch");
   }
-  static const int debug = getenv("B200OPT_GRAM_DEBUG") ? atoi(getenv("B200OPT_GRAM_DEBUG")) : 0;
-  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, debug};
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;

@@ -10,18 +10,9 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   const size_t per_warp = WarpReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)(3 + PModel::NAUX) * p.m_pad;
   const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
   if (smem > 227 * 1024) return -1;  // caller falls back
-  static thread_local size_t smem_set = 0, occ_smem = ~size_t(0);
-  static thread_local int blocks_per_sm = 1;
-  if (smem > smem_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
-    smem_set = smem;
-  }
-  if (occ_smem != smem) {
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy")) return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-    occ_smem = smem;
-  }
+  static LaunchCache cache;
+  const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
+  if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
   const int grid = (int)(need < cap ? need : cap);
@@ -30,9 +21,8 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
 }
 
 int lsq_launch_gauss2(const LsqArgs& a) {
-  static const bool scalar_only = getenv("B200OPT_LSQ_SCALAR") != nullptr;  // A/B switch for profiling
   const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
-  if (!scalar_only && a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
+  if (a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
       !a.opts->root_near_zero) {
     LsqParams<float> p;
     p.y0 = static_cast<const float*>(a.y0);

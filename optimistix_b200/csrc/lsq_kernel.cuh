@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
           quad += d[i] * gd;
           lin += d[i] * g[i];
         }
-        const T pred = lin + T(0.5) * quad;  // == 0.5(|J d + r|^2 - |r|^2), trust_region.py:182-186
+        const T pred = predicted_reduction(lin, quad, rr);  // 0.5(|J d + r|^2 - |r|^2), trust_region.py:182-186
         const T df = T(0.5) * rre - T(0.5) * rr;
         accept = (df <= T(0.01) * pred) || first;
         const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;

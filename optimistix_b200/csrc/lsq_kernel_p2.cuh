@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
             lin += d[i] * g[i];
           }
         }
-        const T pred = lin + T(0.5) * quad;
+        const T pred = predicted_reduction(lin, quad, rr);
         const T df = T(0.5) * rre - T(0.5) * rr;
         accept = (df <= T(0.01) * pred) || first;
         const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;

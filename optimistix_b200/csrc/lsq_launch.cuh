@@ -27,21 +27,9 @@ template <class Model, typename T, bool TRUST> int lsq_launch_one(const LsqParam
     set_error("least_squares: m=%d needs %zu bytes of shared memory per block (limit 227 KB)", p.m, smem);
     return B200OPT_EINVAL;
   }
-  static thread_local size_t smem_set = 0;     // per instantiation
-  static thread_local size_t occ_smem = ~size_t(0);
-  static thread_local int blocks_per_sm = 1;
-  if (smem > smem_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
-      return B200OPT_ECUDA;
-    smem_set = smem;
-  }
-  if (occ_smem != smem) {
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsqWarpsPerBlock * 32, smem), "occupancy"))
-      return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-    occ_smem = smem;
-  }
+  static LaunchCache cache;  // per instantiation; per device inside
+  const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
+  if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;  // persistent: one resident wave, grid-stride
   const int grid = (int)(need < cap ? need : cap);

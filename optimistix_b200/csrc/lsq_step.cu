@@ -90,7 +90,7 @@ template <typename T, int NP> __global__ void __launch_bounds__(kStepWarps * 32)
       quad += d[i] * gd;
       lin += d[i] * g[i];
     }
-    const T pred = lin + T(0.5) * quad;
+    const T pred = predicted_reduction(lin, quad, rr);
     const T df = T(0.5) * rre - T(0.5) * rr;
     accept = (df <= T(0.01) * pred) || first;
     const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
@@ -251,14 +251,14 @@ template <typename T> __global__ void __launch_bounds__(kBigThreads) lsq_step_bi
   const T rre = big_block_sum(part, red);
 
   bool accept = true;
-  if (p.trust) {  // trust_region.py:86-104, predicted reduction d.g + 0.5 d.G d
+  if (p.trust) {  // trust_region.py:86-104, predicted reduction from d.g and d.G d (common.cuh predicted_reduction)
     T lq = T(0);
     for (int i = tid; i < n; i += kBigThreads) {
       T gd = T(0);
       for (int j = 0; j < n; ++j) gd += Gs[i * ld + j] * dv[j];
-      lq += dv[i] * (gs[i] + T(0.5) * gd);
+      lq += dv[i] * (T(2) * gs[i] + gd);
     }
-    const T pred = big_block_sum(lq, red);
+    const T pred = predicted_reduction(T(0), big_block_sum(lq, red), rr);
     const T df = T(0.5) * rre - T(0.5) * rr;
     accept = (df <= T(0.01) * pred) || first;
     const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
@@ -411,11 +411,8 @@ static int head_any(int n) { return pad_n(n) ? head_for(pad_n(n)) : big_state_he
 template <typename T, int NP> static int step_launch(const StepParams<T>& p, cudaStream_t stream) {
   auto kern = lsq_step_kernel<T, NP>;
   const size_t smem = sizeof(T) * kStepWarps * WarpReduceLayout<T, Tri<NP>::size + NP>::elems;
-  static thread_local bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return B200OPT_ECUDA;
-    attr_set = true;
-  }
+  static LaunchCache cache;
+  if (cache.configure(kern, kStepWarps * 32, smem) < 0) return B200OPT_ECUDA;
   const int grid = (int)((p.batch + kStepWarps - 1) / kStepWarps);
   kern<<<grid, kStepWarps * 32, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "lsq_step_kernel launch");

@@ -38,16 +38,9 @@ static int root_launch(int solver, int64_t batch, int n, const void* y0, const v
   p.chord = solver == B200OPT_SOLVER_CHORD;
   auto kern = root_solve_kernel<Model, T>;
   const size_t smem = root_smem_bytes<Model, T>();
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (smem > 48 * 1024)
-      if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))
-        return B200OPT_ECUDA;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRootWarpsPerBlock * 32, smem), "occupancy"))
-      return B200OPT_ECUDA;
-    blocks_per_sm = occ > 0 ? occ : 1;
-  }
+  static LaunchCache cache;
+  const int blocks_per_sm = cache.configure(kern, kRootWarpsPerBlock * 32, smem);
+  if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t need = (batch + kRootWarpsPerBlock - 1) / kRootWarpsPerBlock;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
   const int grid = (int)(need < cap ? need : cap);

@@ -36,7 +36,9 @@ static int omp_get_thread_num(void) { return 0; }
 #define RMAX 3.4028234663852886e+38f
 #include "lm_oracle_impl.h"
 
-/* dtype: 0 = f32, 1 = f64; model: 0 = exp_decay, 1 = gauss2; linsolve: 0 = QR (reference), 1 = Gram+Cholesky */
+/* dtype: 0 = f32, 1 = f64; model: 0 = exp_decay, 1 = gauss2; linsolve: 0 = QR (reference), 1 = Gram+Cholesky,
+ * 2 = kernel arithmetic (Gram+Cholesky and the predicted reduction through the Gram identity, rounded like the reference's),
+ * 3 = as 2 with the exactly evaluated d.g + 0.5 d.G d (the round-1 kernels; documents the iteration-count bias) */
 int oracle_lm_solve(int model, int dtype, int64_t batch, int n, int m, const void* y0, const void* x, const void* d,
                     int64_t d_stride, double rtol, double atol, int max_steps, int linsolve, void* y_out, int32_t* steps,
                     int32_t* result, int nthreads) {

@@ -149,7 +149,7 @@ static void FN(lm_one)(int model, int n, int m, const REAL* y0, const REAL* x, c
     int y_old_finite = FN(allfinite)(y, n);
     FN(model_eval)(model, n, m, ye, x, d, re, Je);
     for (int j = 0; j < n; ++j) dd[j] = ye[j] - y[j];
-    REAL rtr = 0, jt = 0, ree = 0;
+    REAL rtr = 0, jt = 0, ree = 0, pred_exact = 0;
     for (int i = 0; i < m; ++i) {
       REAL s = r[i];
       for (int j = 0; j < n; ++j) s += J[i * n + j] * dd[j];
@@ -157,7 +157,28 @@ static void FN(lm_one)(int model, int n, int m, const REAL* y0, const REAL* x, c
       rtr += r[i] * r[i];
       ree += re[i] * re[i];
     }
+    if (linsolve >= 2) {
+      /* kernel arithmetic: |J d + r|^2 through the Gram identity r.r + (2 d.g + d.G d), then rounded and subtracted
+       * like the reference's (optimistix_b200/csrc/common.cuh predicted_reduction) */
+      REAL lin = 0, quad = 0;
+      for (int a = 0; a < n; ++a) {
+        REAL ga = 0, gd = 0;
+        for (int i = 0; i < m; ++i) ga += J[i * n + a] * r[i];
+        for (int c = 0; c < n; ++c) {
+          REAL gac = 0;
+          for (int i = 0; i < m; ++i) gac += J[i * n + a] * J[i * n + c];
+          gd += gac * dd[c];
+        }
+        lin += dd[a] * ga;
+        quad += dd[a] * gd;
+      }
+      volatile REAL t = rtr + ((REAL)2 * lin + quad);
+      jt = t;
+      if (linsolve == 3) jt = rtr; /* see below */
+      pred_exact = lin + (REAL)0.5 * quad;
+    }
     REAL pred = (REAL)0.5 * (jt - rtr);
+    if (linsolve == 3) pred = pred_exact; /* d.g + 0.5 d.G d without the rounding to the spacing of |r|^2 (round-1 kernels) */
     REAL df = (REAL)0.5 * ree - (REAL)0.5 * rtr;
     int accept = (df <= (REAL)0.01 * pred) || first;
     int good = (df < (REAL)0.99 * pred) && (pred < 0) && !first;

@@ -54,7 +54,7 @@ def levenberg_marquardt(model: str, y0, x, d, *, rtol, atol, max_steps=256, lins
     steps = np.empty(B, np.int32)
     res = np.empty(B, np.int32)
     rc = lib.oracle_lm_solve(MODELS[model], 1 if dt == np.float64 else 0, B, n, m, y0.ctypes.data, x.ctypes.data, d.ctypes.data,
-                             d.shape[1], rtol, atol, max_steps, 0 if linsolve == "qr" else 1, y.ctypes.data, steps.ctypes.data,
+                             d.shape[1], rtol, atol, max_steps, {"qr": 0, "gram": 1, "kernel": 2, "kernel_exact_pred": 3}[linsolve], y.ctypes.data, steps.ctypes.data,
                              res.ctypes.data, nthreads)
     if rc != 0:
         raise RuntimeError(f"oracle_lm_solve failed: {rc}")

@@ -137,7 +137,7 @@ def _freeze(active, new, old):
 # ------------------------------------------------------------------ Gauss-Newton family (LM, GN)
 def gauss_newton_family(
     model, y0, args, *, rtol, atol, norm="max", max_steps=256, search="trust_region", linsolve="qr", trace=None,
-    root_near_zero=False,
+    root_near_zero=False, pred="residual",
 ):
     """LevenbergMarquardt (search="trust_region") / GaussNewton (search="learning_rate").
 
@@ -149,8 +149,20 @@ def gauss_newton_family(
     ``root_near_zero``: restate ``_LstsqToRoot`` (root_find / fixed_point through a least-squares
     solver, _root_find.py:45-80): additionally require ``norm(residual at the pre-step y) < atol``.
 
+    ``linsolve`` / ``pred`` select the arithmetic, not the algorithm:
+      * ``linsolve="qr", pred="residual"`` - the reference's own operations (lx.QR on the augmented system,
+        predicted reduction ``0.5(|J d + r|^2 - |r|^2)`` from the two squared norms).  The parity oracle.
+      * ``linsolve="gram", pred="gram"``   - the CUDA kernels' operations ("kernel arithmetic"): Cholesky of
+        ``J^T J + lambda I`` and ``|J d + r|^2`` formed through the Gram identity ``r.r + (2 d.g + d.G d)`` and
+        then rounded / subtracted like the reference's (csrc/common.cuh ``predicted_reduction``).
+      * ``pred="gram_exact"``              - ``d.g + 0.5 d.G d`` without the rounding to the spacing of ``|r|^2``:
+        what the round-1 kernels did; kept to document the +2-3 % iteration-count bias it causes
+        (tests/test_oracle_pred_modes.py).
+
     Returns dict(value, num_steps, result, step_size, num_accepted).
     """
+    if pred not in ("residual", "gram", "gram_exact"):
+        raise ValueError(pred)
     nrm = NORMS[norm]
     y0 = np.array(y0)
     dt = y0.dtype
@@ -191,19 +203,29 @@ def gauss_newton_family(
                 # trust_region.py:86-104,182-186
                 rtr = np.sum(r * r, axis=1)
                 jd = np.einsum("bmn,bn->bm", J, d) + r
-                pred = dt.type(0.5) * (np.sum(jd * jd, axis=1) - rtr)
+                if pred == "residual":
+                    pred_v = dt.type(0.5) * (np.sum(jd * jd, axis=1) - rtr)
+                else:
+                    Gm = np.einsum("bmi,bmj->bij", J, J)
+                    gv = np.einsum("bmi,bm->bi", J, r)
+                    lin = np.einsum("bi,bi->b", d, gv)
+                    quad = np.einsum("bi,bij,bj->b", d, Gm, d)
+                    if pred == "gram":
+                        pred_v = dt.type(0.5) * ((rtr + (dt.type(2) * lin + quad)) - rtr)
+                    else:
+                        pred_v = lin + dt.type(0.5) * quad
                 f_min = dt.type(0.5) * rtr
                 f_min_eval = dt.type(0.5) * np.sum(r_e * r_e, axis=1)
                 df = f_min_eval - f_min
-                accept = df <= dt.type(0.01) * pred
-                good = (df < dt.type(0.99) * pred) & (pred < 0)
+                accept = df <= dt.type(0.01) * pred_v
+                good = (df < dt.type(0.99) * pred_v) & (pred_v < 0)
                 good = good & ~first
                 accept = accept | first
                 mul = np.where(good, dt.type(3.5), dt.type(1.0))
                 mul = np.where(accept, mul, dt.type(0.25))
                 new_delta = mul * delta
                 noise = fi.eps * np.maximum(f_min, f_min_eval) + fi.tiny
-                mg = np.minimum(np.abs(df - dt.type(0.01) * pred), np.abs(df - dt.type(0.99) * pred)) / noise
+                mg = np.minimum(np.abs(df - dt.type(0.01) * pred_v), np.abs(df - dt.type(0.99) * pred_v)) / noise
                 mg = np.where(first, np.inf, mg)
                 margin = np.where(active, np.minimum(margin, mg), margin)
             else:

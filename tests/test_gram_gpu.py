@@ -244,3 +244,136 @@ def test_peer_exchange_kernels_single_rank():
         assert int(status.item()) == -4
     finally:
         lib.b200opt_xchg_free(ptr)
+
+
+# ---- state-driven iteration (b200opt_gn_iterate) and its solver ---------------------------------------------------------
+def _parts_from(Gs, gs):
+    stride = N * N + N + 4
+    parts = torch.zeros(len(Gs), stride, dtype=torch.float32)
+    for q, (Gq, gq) in enumerate(zip(Gs, gs)):
+        parts[q, : N * N] = Gq.reshape(-1)
+        parts[q, N * N : N * N + N] = gq
+        parts[q, N * N + N] = float(q + 1)
+        parts[q, N * N + N + 1] = 0.5 * (q + 1)
+    return parts, stride
+
+
+def _solve_fast(parts, stride, solver, lam=0.0):
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    parts = parts.to(DEV)
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(N), dtype=torch.uint8, device=DEV)
+    p = torch.empty(N, dtype=torch.float32, device=DEV)
+    status = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    summary = torch.zeros(2, dtype=torch.float32, device=DEV)
+    info = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.b200opt_gn_solve_fast(parts.data_ptr(), parts.shape[0], stride, N, lam, solver, p.data_ptr(), status.data_ptr(),
+                                         summary.data_ptr(), info.data_ptr(), ws.data_ptr(), st), "gn_solve_fast")
+    torch.cuda.synchronize()
+    return p.cpu(), int(status.item()), summary.cpu(), int(info.item())
+
+
+@pytest.mark.parametrize("nparts", [1, 3, 8])
+@pytest.mark.parametrize("col_scale", [0.0, -2.0, -4.0])
+def test_fast_solver_matches_fp64(nparts, col_scale):
+    """Equilibrated fp32 blocked Cholesky + fp64 refinement against torch's fp64 solve of the same (fp64-summed) system; the
+    column scaling of J (10^col_scale over the columns: kappa(G) up to 1e8+) is removed by the equilibration."""
+    gen = torch.Generator().manual_seed(17 + nparts)
+    scale = torch.logspace(0, col_scale, N, dtype=torch.float64)
+    Gs, gs = [], []
+    for _ in range(nparts):
+        A = torch.randn(2048, N, dtype=torch.float64, generator=gen) * scale
+        Gs.append((A.T @ A).float())
+        gs.append((A.T @ torch.randn(2048, dtype=torch.float64, generator=gen)).float())
+    parts, stride = _parts_from(Gs, gs)
+    G_tot = sum(G.double() for G in Gs)
+    g_tot = sum(g.double() for g in gs)
+    for lam in (0.0, 1e-3):
+        p_ref = torch.linalg.solve(G_tot + lam * torch.eye(N, dtype=torch.float64), g_tot)
+        p32, st32, sum32, info32 = _solve_fast(parts, stride, 0, lam)
+        p64, st64, sum64, info64 = _solve_fast(parts, stride, 1, lam)
+        assert st32 == 0 and st64 == 0 and info64 == 0
+        assert info32 == 1, "the fp32 + refinement path should have been accepted for this matrix"
+        e32 = ((p32.double() - p_ref).abs() / p_ref.abs().max()).max().item()
+        e64 = ((p64.double() - p_ref).abs() / p_ref.abs().max()).max().item()
+        print(f"[fast solve nparts={nparts} col_scale={col_scale} lam={lam}] max err / |p|_inf: fp32+refine {e32:.2e}, fp64 {e64:.2e}")
+        assert e64 <= 2e-7 and e32 <= 4e-7          # both at the resolution of the fp32 output
+        assert torch.equal(sum32, sum64)
+        assert sum32.tolist() == [float(sum(range(1, nparts + 1))), 0.5 * nparts]
+
+
+def test_fast_solver_falls_back_when_fp32_is_not_enough():
+    """A matrix whose EQUILIBRATED condition number is ~1e9 (nearly dependent columns): the fp32 factor is useless, the kernel
+    must notice (non-positive pivot or a large refinement step) and return exactly what the fp64 solver returns."""
+    gen = torch.Generator().manual_seed(3)
+    A = torch.randn(4096, N, dtype=torch.float64, generator=gen)
+    A[:, 1] = A[:, 0] + 3e-5 * A[:, 1]   # two columns equal to 3e-5
+    G = (A.T @ A).float()
+    g = (A.T @ torch.randn(4096, dtype=torch.float64, generator=gen)).float()
+    parts, stride = _parts_from([G], [g])
+    p32, st32, _, info32 = _solve_fast(parts, stride, 0)
+    p64, st64, _, info64 = _solve_fast(parts, stride, 1)
+    assert info32 == 0 and info64 == 0 and st32 == st64
+    assert torch.equal(p32, p64) or (torch.isnan(p32) == torch.isnan(p64)).all()
+    # singular and indefinite systems: `singular` from both
+    for Gbad in (torch.zeros(N, N), -torch.eye(N)):
+        parts, stride = _parts_from([Gbad], [torch.ones(N)])
+        assert _solve_fast(parts, stride, 0)[1] == optx.RESULTS.singular
+        assert _solve_fast(parts, stride, 1)[1] == optx.RESULTS.singular
+
+
+@pytest.mark.parametrize("m", [4096, 65536, 9472 * 64 + 20])
+def test_device_loop_equals_host_loop(m):
+    """b200opt_gn_iterate (loop on the device, reduction folded into the Gram kernel) against the step-by-step host loop
+    (separate reduction kernel, torch arithmetic for the carry): with the fp64 solver the two are the same arithmetic in the
+    same order - bit-identical iterates, step counts and result codes.  The fp32 + refinement solver agrees to tolerance."""
+    from optimistix_b200._gn_large import gauss_newton_large
+
+    m = m - m % 4
+    w = synthetic.linear_lsq_rows(m, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y0 = torch.zeros(N, dtype=torch.float32, device=DEV)
+    sv = optx.GaussNewton(1e-4, 1e-4)
+    host = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=False)
+    for check_every in (1, 4):
+        dev64 = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=True, linear_solver=1, check_every=check_every)
+        assert dev64.result == host.result == optx.RESULTS.successful
+        assert dev64.stats["num_steps"] == host.stats["num_steps"]
+        assert torch.equal(dev64.value, host.value)
+        assert abs(dev64.stats["loss"] - host.stats["loss"]) <= 1e-6 * abs(host.stats["loss"])
+    dev32 = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=True, linear_solver=0)
+    assert dev32.result == optx.RESULTS.successful and dev32.stats["fp64_fallbacks"] == 0
+    assert abs(dev32.stats["num_steps"] - host.stats["num_steps"]) <= 1
+    scaled = ((dev32.value - host.value).abs() / (1e-4 + 1e-4 * host.value.abs())).max().item()
+    print(f"[device loop m={m}] steps host {host.stats['num_steps']} dev64 {dev64.stats['num_steps']} dev32 {dev32.stats['num_steps']}, "
+          f"fp32-solver vs host scaled diff {scaled:.3g}")
+    assert scaled <= 1.0
+    # max_steps and frozen iterations: running ahead of the device never takes an extra step
+    short = gauss_newton_large(J, d, y0, sv, throw=False, max_steps=2, check_every=8)
+    assert short.result == optx.RESULTS.nonlinear_max_steps_reached and short.stats["num_steps"] == 2
+    host2 = gauss_newton_large(J, d, y0, sv, throw=False, max_steps=2, device_loop=False)
+    dev2 = gauss_newton_large(J, d, y0, sv, throw=False, max_steps=2, linear_solver=1)
+    assert torch.equal(dev2.value, host2.value)
+    # non-finite start: `nonfinite`, zero steps (_iterate.py:214-219)
+    bad = y0.clone()
+    bad[5] = float("nan")
+    nf = gauss_newton_large(J, d, bad, sv, throw=False)
+    assert nf.result == optx.RESULTS.nonfinite and nf.stats["num_steps"] == 0
+
+
+def test_device_loop_repeated_solves_do_not_leak():
+    """every solve used to build (and never close) its helpers; repeated solves must not grow device memory."""
+    w = synthetic.linear_lsq_rows(16384, seed=4)
+    J = torch.as_tensor(w["J"], device=DEV)
+    d = torch.as_tensor(w["d"], device=DEV)
+    y0 = torch.zeros(N, dtype=torch.float32, device=DEV)
+    for _ in range(3):
+        optx.least_squares(optx.models.linear_rows, optx.GaussNewton(1e-4, 1e-4), y0, (J, d), throw=False)
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    for _ in range(10):
+        sol = optx.least_squares(optx.models.linear_rows, optx.GaussNewton(1e-4, 1e-4), y0, (J, d), throw=False)
+    torch.cuda.synchronize()
+    del sol
+    assert torch.cuda.memory_allocated() <= base + (1 << 20)

@@ -23,11 +23,19 @@ w = synthetic.linear_lsq_rows(m, seed=4)
 lo, hi = rank * m // world, (rank + 1) * m // world
 J, d = torch.as_tensor(w["J"][lo:hi], device=dev), torch.as_tensor(w["d"][lo:hi], device=dev)
 y0 = torch.zeros(N, dtype=torch.float32, device=dev)
-a = optx.least_squares(optx.models.linear_rows, optx.GaussNewton(1e-4, 1e-4), y0, (J, d), throw=False)  # default: peer exchange
-b = gauss_newton_large(J, d, y0, optx.GaussNewton(1e-4, 1e-4), throw=False, exchange="nccl")
-assert a.result == b.result == optx.RESULTS.successful, (a.result, b.result)
-assert a.stats["num_steps"] == b.stats["num_steps"]
-assert torch.equal(a.value, b.value), "peer exchange and NCCL all-gather must give the same bits"
+sv = optx.GaussNewton(1e-4, 1e-4)
+a = optx.least_squares(optx.models.linear_rows, sv, y0, (J, d), throw=False)  # default: device loop, peer exchange, fp32 + refinement solver
+assert "peer memory (device loop)" in a.stats["exchange"], a.stats
+a64 = gauss_newton_large(J, d, y0, sv, throw=False, linear_solver=1)           # device loop, fp64 solver
+b = gauss_newton_large(J, d, y0, sv, throw=False, exchange="nccl")             # host loop over the NCCL all-gather (fp64 solver)
+c = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=False)           # host loop over the peer exchange
+assert a.result == a64.result == b.result == c.result == optx.RESULTS.successful, (a.result, a64.result, b.result, c.result)
+assert a64.stats["num_steps"] == b.stats["num_steps"] == c.stats["num_steps"]
+assert torch.equal(a64.value, b.value) and torch.equal(b.value, c.value), "device loop, NCCL all-gather and host-loop peer exchange must give the same bits"
+assert abs(a.stats["num_steps"] - b.stats["num_steps"]) <= 1 and a.stats["fp64_fallbacks"] == 0
+for _ in range(3):  # repeated solves reuse the cached exchange (sequence numbers keep counting)
+    a2 = optx.least_squares(optx.models.linear_rows, sv, y0, (J, d), throw=False)
+    assert torch.equal(a2.value, a.value)
 allv = [torch.empty_like(a.value) for _ in range(world)]
 dist.all_gather(allv, a.value)
 assert all(torch.equal(v, allv[0]) for v in allv), "every rank must hold the same iterate"
