@@ -215,8 +215,9 @@ def bench_gram(args, rank, world, dev, K, W):
     (strong scaling: the total row count is fixed).  A step is one Gauss-Newton iteration.  Timed THROUGH the public API:
     optx.least_squares(models.linear_rows, GaussNewton(rtol=atol=0), ..., max_steps=K) runs exactly K iterations (a zero
     tolerance never terminates), with everything an iteration does (residual, Gram, exchange, solve, y update, Cauchy test,
-    step counter) inside the timed region.  `kernel_only` repeats the round-1 measurement (Gram + reduce + solve enqueued
-    back to back, nothing else) for the same exchange so that the two can be compared."""
+    step counter) inside the timed region.  `kernel_only` repeats the round-1 measurement (Gram + separate reduce kernel + fp64
+    solve enqueued back to back through the step-wise C entry points, nothing else) for the same exchange so that the two can
+    be compared; `solve_kernel_ms` times the two 256 x 256 solvers alone."""
     import torch
     import torch.distributed as dist
 
@@ -324,21 +325,61 @@ def bench_gram(args, rank, world, dev, K, W):
         t_step, t_gram = max_over_ranks([t_step, t_gram])
         return t_step / K, t_gram / K
 
+    def time_solvers():
+        """The 256 x 256 solve alone (b200opt_gn_solve_fast on `world` copies of this rank's block): fp32 + refinement vs fp64."""
+        lib = ops.lib
+        stride = OUT_FLOATS + 2  # a multiple of 4
+        parts = torch.zeros(world * stride, device=dev)
+        for q in range(world):
+            parts[q * stride: q * stride + OUT_FLOATS] = out
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        tms = {}
+        for nm, sid in (("fp32_blocked_cholesky+fp64_refinement", 0), ("fp64_cholesky", 1)):
+            def one():
+                return lib.b200opt_gn_solve_fast(parts.data_ptr(), world, stride, N, 0.0, sid, p.data_ptr(), status.data_ptr(), summary.data_ptr(),
+                                                 info.data_ptr(), ops.ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            for _ in range(3):
+                one()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            tms[nm] = e0.elapsed_time(e1) / 20
+        tms["fp32_path_accepted"] = None
+        lib.b200opt_gn_solve_fast(parts.data_ptr(), world, stride, N, 0.0, 0, p.data_ptr(), status.data_ptr(), summary.data_ptr(), info.data_ptr(),
+                                  ops.ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        tms["fp32_path_accepted"] = bool(int(info.item()))
+        return tms
+
     sampler = ClockSampler(dev.index)
     sampler.start()
     res = {}
     exchanges = ["peer", "nccl"] if world > 1 else ["local"]
-    for ex in exchanges:
-        ms_api, wall_api, sol = time_api(ex if world > 1 else "peer", 0)
-        entry = {"api_ms_per_iteration": ms_api, "api_wall_ms_per_iteration": wall_api, "fp64_fallbacks": sol.stats.get("fp64_fallbacks")}
-        if ex != "nccl":
-            ms64, _, _ = time_api(ex if world > 1 else "peer", 1)
-            entry["api_ms_per_iteration_fp64_solver"] = ms64
-        ms_k, ms_g = time_kernels(ex)
-        entry["kernel_only_ms_per_iteration"] = ms_k
-        entry["kernel_only_breakdown_ms"] = {"gram+reduce(+publish)": ms_g, "exchange_wait+solve": ms_k - ms_g}
-        entry["api_over_kernel_only"] = ms_api / ms_k
-        res[ex] = entry
+    # every configuration is timed twice, interleaved with the others (A B C A B C), and the faster pass is kept: under
+    # a power cap the SM clock drifts over seconds, which would otherwise be read as a difference between configurations
+    for rep_i in range(2):
+        for ex in exchanges:
+            entry = res.setdefault(ex, {})
+
+            def keep(key, val):
+                entry[key] = min(entry.get(key, float("inf")), val)
+
+            ms_api, wall_api, sol = time_api(ex if world > 1 else "peer", 0)
+            keep("api_ms_per_iteration", ms_api)
+            keep("api_wall_ms_per_iteration", wall_api)
+            entry["fp64_fallbacks"] = sol.stats.get("fp64_fallbacks")
+            entry["api_path"] = sol.stats.get("exchange")
+            if ex != "nccl":
+                keep("api_ms_per_iteration_fp64_solver", time_api(ex if world > 1 else "peer", 1)[0])
+            ms_k, ms_g = time_kernels(ex)
+            if ms_k < entry.get("kernel_only_ms_per_iteration", float("inf")):
+                entry["kernel_only_ms_per_iteration"] = ms_k
+                entry["kernel_only_breakdown_ms"] = {"gram+reduce(+publish)": ms_g, "exchange_wait+solve": ms_k - ms_g}
+    for entry in res.values():
+        entry["api_over_kernel_only"] = entry["api_ms_per_iteration"] / entry["kernel_only_ms_per_iteration"]
+    solve_ms = time_solvers()
     clocks = sampler.stop()
     best = min(res, key=lambda k: res[k]["api_ms_per_iteration"])
     ms = res[best]["api_ms_per_iteration"]
@@ -378,7 +419,7 @@ def bench_gram(args, rank, world, dev, K, W):
                                       "buffer by the Gram kernel itself (P2P over NVLink, flag-signalled) and summed in rank order inside the solve kernel"
                                       if world > 1 else "single GPU",
                        "l2": "J shard (>= 8 GB) exceeds the 126 MB L2"},
-            "exchanges": res,
+            "exchanges": res, "solve_kernel_ms": solve_ms,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_gram / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (ms_gram / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "kernel": "gram_kernel (fused residual + Gram pass)", "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes // m_local,

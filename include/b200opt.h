@@ -98,7 +98,17 @@ typedef struct b200opt_options {
   int32_t cauchy_termination; /* Newton/Chord only: 1 (default) or 0 = Hairer-Wanner test, newton_chord.py:179-192 */
   int32_t root_near_zero;     /* 1 = also require norm(f) < atol (root_find through LM/BFGS, _root_find.py:45-80) */
   double kappa;               /* Newton/Chord non-Cauchy mode, default 1e-2 */
+  int32_t linear_solver;      /* least squares only: B200OPT_LINSOLVE_* (the `linear_solver=` field of LevenbergMarquardt /
+                               * GaussNewton, levenberg_marquardt.py:286, gauss_newton.py:387) */
+  int32_t reserved;           /* 0 */
 } b200opt_options_t;
+
+/* Linear solve of the LM / GN descent.  NORMAL_CHOLESKY (default; BASELINE north_star): Cholesky of J^T J + lambda I, J never
+ * materialised.  QR: the reference's own operations - Householder QR of the augmented system [J; sqrt(lambda) I] p = [r; 0]
+ * (levenberg_marquardt.py:66-75) and the predicted reduction from J d + r (trust_region.py:182-186); J of the accepted
+ * point is rebuilt in shared memory every step.  Use it when kappa(J)^2 eps is not small. */
+#define B200OPT_LINSOLVE_NORMAL_CHOLESKY 0
+#define B200OPT_LINSOLVE_QR 1
 
 /* Residual-model plugin registry: the compiled-in model families (device residual/Jacobian functions). */
 typedef struct b200opt_model_info {

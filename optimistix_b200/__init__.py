@@ -39,6 +39,7 @@ from ._solvers import (
     LU,
     Newton,
     NewtonDescent,
+    NormalCholesky,
     QR,
     RecursiveCheckpointAdjoint,
     max_norm,

@@ -92,6 +92,15 @@ class _Buf:
         return x.ctypes.data
 
 
+def _np_ndim(x):
+    return x.ndim if hasattr(x, "ndim") else np.asarray(x).ndim
+
+
+def _as_cuda(x):
+    t = _torch()
+    return x if (_is_torch(x) and x.is_cuda) else t.as_tensor(x).cuda()
+
+
 def _host_empty(shape, dtype):
     """Host output / staging array.  Page-locked through torch's caching host allocator when a CUDA device is present:
     the D2H copies of the C host pipeline then land directly in it (no bounce buffer, no first-touch page faults on a
@@ -254,6 +263,16 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     _check_defaults(solver)
     if max_steps is None:
         max_steps = _UNBOUNDED
+    if isinstance(fn, RegisteredModel) and getattr(solver, "verbose", None) is not None and fn.name != "linear_rows":
+        # a verbose solve reports every step to the host: it runs through the per-iteration step kernel, with the family's
+        # torch evaluator standing in for the device functions
+        if fn.torch_fn is None:
+            raise NotImplementedError(f"verbose: model family {fn.name} has no torch evaluator")
+        tfn, names, nshared = fn.torch_fn, fn.arg_names, fn.n_shared
+        a0 = fn.split_args(args)
+        in_dims = {k: (None if i < nshared else 0) for i, k in enumerate(names)} if _np_ndim(y0) == 2 else None
+        return least_squares(lambda y, ad: tfn(y, ad), solver, y0, {k: _as_cuda(a0[k]) for k in names}, options, max_steps=max_steps,
+                             adjoint=adjoint, throw=throw, _root_near_zero=_root_near_zero, args_in_dims=in_dims)
     if not isinstance(fn, RegisteredModel):
         from ._generic import least_squares_generic
 
@@ -282,7 +301,8 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     if prob.ndim != 2 or prob.shape[0] != B or prob.shape[1] != m:
         raise ValueError(f"{fn.name}: per-problem data must have shape [{B}, {m}], got {tuple(prob.shape)}")
     solver_id = _lib.SOLVER_LM if isinstance(solver, LevenbergMarquardt) else _lib.SOLVER_GN
-    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=_root_near_zero)
+    opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=_root_near_zero,
+                             linear_solver=solver.descent.linear_solver)
     y_out = buf.empty((B, n), y0)
     steps = buf.empty_i32((B,), y0)
     res = buf.empty_i32((B,), y0)

@@ -258,6 +258,9 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
 
     if getattr(solver.norm, "norm_name", "max") != "max":
         raise NotImplementedError("the large Gauss-Newton path implements max_norm termination")
+    if _lib.linear_solver_id(getattr(getattr(solver, "descent", None), "linear_solver", None)) != _lib.LINSOLVE_NORMAL_CHOLESKY:
+        raise NotImplementedError("linear_rows (m x 256 with m ~ 6.7e7): the row-sharded path forms the normal equations on the tensor "
+                                  "cores; a tall-skinny QR across ranks is not implemented - use linear_solver=NormalCholesky()")
     distributed = dist.is_available() and dist.is_initialized() and (group is not None or dist.get_world_size() > 1)
     dev = J.device
     if ops is None:

@@ -27,6 +27,8 @@ class Options(C.Structure):
         ("cauchy_termination", C.c_int32),
         ("root_near_zero", C.c_int32),
         ("kappa", C.c_double),
+        ("linear_solver", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -128,9 +130,29 @@ def check(code: int, what: str):
         raise B200OptError(f"{what} failed ({code}): {msg}")
 
 
-def make_options(rtol, atol, norm="max", max_steps=256, cauchy_termination=True, root_near_zero=False, kappa=1e-2):
+LINSOLVE_NORMAL_CHOLESKY, LINSOLVE_QR = 0, 1
+
+
+def linear_solver_id(linear_solver) -> int:
+    """Map the `linear_solver=` field of LevenbergMarquardt / GaussNewton to the kernels' two solvers.  Anything the kernels
+    do not implement raises: the argument is never silently ignored."""
+    if linear_solver is None:
+        return LINSOLVE_NORMAL_CHOLESKY
+    name = type(linear_solver).__name__
+    if name in ("NormalCholesky", "Cholesky"):
+        return LINSOLVE_NORMAL_CHOLESKY
+    if name == "QR":
+        return LINSOLVE_QR
+    if name == "AutoLinearSolver" and getattr(linear_solver, "well_posed", None) is None:
+        return LINSOLVE_NORMAL_CHOLESKY  # GaussNewton's default token (gauss_newton.py:387): see _solvers.py
+    raise NotImplementedError(f"linear_solver={linear_solver!r}: the CUDA least-squares kernels implement NormalCholesky() (Cholesky of "
+                              "J^T J + lambda I, the default) and QR() (Householder QR of the augmented system)")
+
+
+def make_options(rtol, atol, norm="max", max_steps=256, cauchy_termination=True, root_near_zero=False, kappa=1e-2, linear_solver=None):
     if isinstance(norm, str):
         norm_id = NORM_IDS[norm]
     else:
         norm_id = NORM_IDS[getattr(norm, "norm_name")]
-    return Options(float(rtol), float(atol), norm_id, int(max_steps), int(bool(cauchy_termination)), int(bool(root_near_zero)), float(kappa))
+    return Options(float(rtol), float(atol), norm_id, int(max_steps), int(bool(cauchy_termination)), int(bool(root_near_zero)), float(kappa),
+                   linear_solver_id(linear_solver), 0)

@@ -52,7 +52,14 @@ def rms_norm(x):
 # ---- lineax stand-ins (only used as tokens; see DESIGN.md "linear solves") -----------------------------------------
 @dataclasses.dataclass(frozen=True)
 class QR:
-    pass
+    """`lx.QR()`: selects the kernels' Householder-QR descent (B200OPT_LINSOLVE_QR) when given to LevenbergMarquardt / GaussNewton."""
+
+
+@dataclasses.dataclass(frozen=True)
+class NormalCholesky:
+    """Cholesky of J^T J + lambda I with J never materialised (BASELINE north_star; `lx.NormalCholesky` is the nearest lineax
+    name): the default linear solve of the CUDA least-squares kernels.  The reference's default for LevenbergMarquardt is
+    `lx.QR()` (levenberg_marquardt.py:286): pass `linear_solver=QR()` to get the reference's own operations."""
 
 
 @dataclasses.dataclass(frozen=True)
@@ -111,6 +118,35 @@ class NewtonDescent(AbstractDescent):
 
 
 # ---- solver hierarchy -----------------------------------------------------------------------------------------
+def _session(kind):
+    from . import _protocol
+
+    return {"lstsq": _protocol.LsqSession, "root": _protocol.RootSession, "min": _protocol.MinSession}[kind]
+
+
+class _ProtocolBase:
+    """`init / step / terminate / postprocess` with the reference's signatures (optimistix/_iterate.py:33-184), backed by the
+    per-iteration CUDA step kernels: see `_protocol.py`."""
+
+    _kind = ""
+
+    def init(self, fn, y, args, options, f_struct=None, aux_struct=None, tags=frozenset()):
+        from . import _protocol
+
+        return _protocol.protocol_init(self, _session(self._kind), fn, y, args, options)
+
+    def step(self, fn, y, args, options, state, tags=frozenset()):
+        from . import _protocol
+
+        return _protocol.protocol_step(state, args)
+
+    def terminate(self, fn, y, args, options, state, tags=frozenset()):
+        return state.done, state.result
+
+    def postprocess(self, fn, y, aux, args, options, state, tags=frozenset(), result=None):
+        return y, aux, {}
+
+
 class AbstractIterativeSolver:
     pass
 
@@ -131,12 +167,12 @@ class AbstractFixedPointSolver(AbstractIterativeSolver):
     pass
 
 
-class AbstractGaussNewton(AbstractLeastSquaresSolver):
-    pass
+class AbstractGaussNewton(AbstractLeastSquaresSolver, _ProtocolBase):
+    _kind = "lstsq"
 
 
-class AbstractQuasiNewton(AbstractMinimiser):
-    pass
+class AbstractQuasiNewton(AbstractMinimiser, _ProtocolBase):
+    _kind = "min"
 
 
 class AbstractBFGS(AbstractQuasiNewton):
@@ -147,32 +183,51 @@ class AbstractDFP(AbstractQuasiNewton):
     pass
 
 
+def _default_verbose(**kwargs):
+    """`verbose=True` (optimistix/_misc.py:385-393): one line per step, every field."""
+    pieces = []
+    for name, value in kwargs.values():
+        if hasattr(value, "detach"):
+            value = value.detach().cpu()
+            value = value.item() if value.ndim == 0 else value.tolist()
+        pieces.append(f"{name}: {value}")
+    if pieces:
+        print(", ".join(pieces))
+
+
 def _check_verbose(verbose):
-    if verbose not in (False, None):
-        raise NotImplementedError("verbose=... printing is not available from inside the persistent CUDA kernel")
+    """`verbose: bool | Callable[..., None]` as in the reference (gauss_newton.py:300-312, quasi_newton.py:273-283).  Returns
+    None (silent) or the callable that receives `name=(label, value)` keyword arguments once per step.  A verbose solve runs
+    through the per-iteration step kernels (the host sees every step); the persistent kernels never print."""
+    if verbose in (False, None):
+        return None
+    if verbose is True:
+        return _default_verbose
+    if callable(verbose):
+        return verbose
+    raise TypeError("verbose must be a bool or a callable `**kwargs -> None`")
 
 
 class LevenbergMarquardt(AbstractGaussNewton):
-    def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, linear_solver: Any = QR(), verbose=False):
-        _check_verbose(verbose)
+    def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, linear_solver: Any = NormalCholesky(), verbose=False):
+        self.verbose = _check_verbose(verbose)
         self.rtol, self.atol, self.norm = rtol, atol, norm
         self.descent = DampedNewtonDescent(linear_solver=linear_solver)
         self.search = ClassicalTrustRegion()
-        self.verbose = verbose
 
 
 class GaussNewton(AbstractGaussNewton):
     def __init__(self, rtol: float, atol: float, norm: Callable = max_norm,
-                 linear_solver: Any = AutoLinearSolver(well_posed=None), verbose=False):
-        _check_verbose(verbose)
+                 linear_solver: Any = NormalCholesky(), verbose=False):
+        self.verbose = _check_verbose(verbose)
         self.rtol, self.atol, self.norm = rtol, atol, norm
         self.descent = NewtonDescent(linear_solver=linear_solver)
         self.search = LearningRate(1.0)
-        self.verbose = verbose
 
 
-class _AbstractNewtonChord(AbstractRootFinder):
+class _AbstractNewtonChord(AbstractRootFinder, _ProtocolBase):
     _is_newton: bool
+    _kind = "root"
 
     def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, kappa: float = 1e-2,
                  linear_solver: Any = AutoLinearSolver(well_posed=None), cauchy_termination: bool = True):
@@ -195,11 +250,10 @@ class BFGS(AbstractBFGS):
     _update = "bfgs"
 
     def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, use_inverse: bool = True, verbose=False):
-        _check_verbose(verbose)
+        self.verbose = _check_verbose(verbose)
         self.rtol, self.atol, self.norm, self.use_inverse = rtol, atol, norm, use_inverse
         self.descent = NewtonDescent(linear_solver=Cholesky())
         self.search = BacktrackingArmijo()
-        self.verbose = verbose
 
 
 class DFP(AbstractDFP):
@@ -208,11 +262,10 @@ class DFP(AbstractDFP):
     _update = "dfp"
 
     def __init__(self, rtol: float, atol: float, norm: Callable = max_norm, use_inverse: bool = True, verbose=False):
-        _check_verbose(verbose)
+        self.verbose = _check_verbose(verbose)
         self.rtol, self.atol, self.norm, self.use_inverse = rtol, atol, norm, use_inverse
         self.descent = NewtonDescent(linear_solver=Cholesky())
         self.search = BacktrackingArmijo()
-        self.verbose = verbose
 
 
 # ---- adjoints (names kept; differentiating through the CUDA solve is SURVEY 8f.2) ---------------------------------

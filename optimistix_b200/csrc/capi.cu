@@ -78,6 +78,10 @@ static int validate_common(const char* who, int dtype, int64_t batch, const b200
     set_error("%s: max_steps must be >= 0", who);
     return B200OPT_EINVAL;
   }
+  if (opts->linear_solver != B200OPT_LINSOLVE_NORMAL_CHOLESKY && opts->linear_solver != B200OPT_LINSOLVE_QR) {
+    set_error("%s: unknown linear_solver %d", who, opts->linear_solver);
+    return B200OPT_EINVAL;
+  }
   return 0;
 }
 
@@ -268,6 +272,8 @@ void b200opt_default_options(b200opt_options_t* o) {
   o->cauchy_termination = 1;
   o->root_near_zero = 0;
   o->kappa = 1e-2;
+  o->linear_solver = B200OPT_LINSOLVE_NORMAL_CHOLESKY;
+  o->reserved = 0;
 }
 
 int32_t b200opt_least_squares(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, int32_t m,

@@ -163,6 +163,10 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
     set_error("least_squares: model %s expects n=%d parameters, got n=%d", fam.name, fam.n, a.n);
     return B200OPT_EINVAL;
   }
+  if (a.opts->linear_solver != B200OPT_LINSOLVE_NORMAL_CHOLESKY) {
+    set_error("least_squares: run-time compiled families run the normal-equation kernel (linear_solver = QR is compiled for the built-in families)");
+    return B200OPT_EINVAL;
+  }
   const bool f64 = a.dtype == B200OPT_F64;
   const size_t es = f64 ? 8 : 4;
   const int m_pad = (a.m + 31) / 32 * 32;

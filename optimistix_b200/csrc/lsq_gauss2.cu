@@ -22,7 +22,7 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
 
 int lsq_launch_gauss2(const LsqArgs& a) {
   const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
-  if (a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
+  if (a.opts->linear_solver == B200OPT_LINSOLVE_NORMAL_CHOLESKY && a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
       !a.opts->root_near_zero) {
     LsqParams<float> p;
     p.y0 = static_cast<const float*>(a.y0);

@@ -49,6 +49,15 @@ template <typename T> struct LsqParams {
   int vec_ok;              // data rows 16-byte aligned and m a multiple of the vector width
 };
 
+// QR mode (B200OPT_LINSOLVE_QR): the reference's own operations instead of the normal equations.  The Jacobian of the
+// accepted point is kept in shared memory (column-major, one row per lane and slot: conflict free), the predicted reduction
+// is 0.5 (|J d + r|^2 - |r|^2) from the rows themselves (trust_region.py:182-186), and the descent is the Householder QR of the
+// augmented system [J; sqrt(lambda) I] p = [r; 0] (levenberg_marquardt.py:66-75; lx.QR = geqrf + Q^T b + triangular solve) on
+// a work copy: rows 0..m-1 are J, rows m_pad..m_pad+N-1 (an extra group of 32 rows, lane a holds row a) are sqrt(lambda) I.
+// kappa(J) enters once (not squared as in G = J^T J); the price is 2 N (m_pad + 32) more shared-memory elements per warp and a
+// few times the arithmetic per step.
+__host__ __device__ inline int lsq_qr_rows(int m_pad) { return m_pad + 32; }
+
 constexpr int kLsqWarpsPerBlock = 4;
 
 // ---- warp all-reduce of K per-lane partial sums through shared memory, 128-bit accesses ---------------------------
@@ -126,16 +135,16 @@ template <typename T, int K> __device__ __forceinline__ void warp_allreduce_arra
 template <class Model, typename T> __host__ __device__ constexpr int lsq_scratch_elems() {
   return WarpReduceLayout<T, Tri<Model::N>::size + Model::N>::elems;
 }
-template <class Model, typename T> __host__ __device__ inline size_t lsq_smem_bytes(int m_pad) {
-  const size_t per_warp = lsq_scratch_elems<Model, T>() + (size_t)(3 + Model::NAUX) * m_pad;
+template <class Model, typename T> __host__ __device__ inline size_t lsq_smem_bytes(int m_pad, bool qr = false) {
+  const size_t per_warp = lsq_scratch_elems<Model, T>() + (size_t)(3 + Model::NAUX) * m_pad + (qr ? (size_t)2 * Model::N * lsq_qr_rows(m_pad) : 0);
   return sizeof(T) * ((size_t)m_pad /* shared abscissa grid */ + kLsqWarpsPerBlock * per_warp);
 }
 
 #ifndef LSQ_MINBLOCKS_F64
 #define LSQ_MINBLOCKS_F64 2
 #endif
-template <class Model, typename T, bool TRUST>
-__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : LSQ_MINBLOCKS_F64)) lsq_solve_kernel(const LsqParams<T> p) {
+template <class Model, typename T, bool TRUST, bool QRMODE = false>
+__global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (QRMODE ? 1 : (sizeof(T) == 4 ? 4 : LSQ_MINBLOCKS_F64))) lsq_solve_kernel(const LsqParams<T> p) {
   constexpr int N = Model::N;
   constexpr int NG = Tri<N>::size;
   constexpr int NAUX = Model::NAUX;
@@ -144,12 +153,15 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
   const int wib = threadIdx.x >> 5;
   const int m = p.m, mp = p.m_pad;
   T* xs = reinterpret_cast<T*>(smem_raw);
-  T* wbase = xs + mp + (size_t)wib * (lsq_scratch_elems<Model, T>() + (size_t)(3 + NAUX) * mp);
+  const int ma = lsq_qr_rows(mp);  // QR mode: rows of the augmented work matrix
+  T* wbase = xs + mp + (size_t)wib * (lsq_scratch_elems<Model, T>() + (size_t)(3 + NAUX) * mp + (QRMODE ? (size_t)2 * N * ma : 0));
   T* scratch = wbase;
   T* ds = wbase + lsq_scratch_elems<Model, T>();
   T* racc = ds + mp;       // residuals at the last accepted point
   T* rtry = racc + mp;     // residuals at the trial point
   T* auxs = rtry + mp;     // NAUX arrays of m_pad
+  T* Jacc = auxs + (size_t)NAUX * mp;  // QR mode: Jacobian at the accepted point, [N][ma] column-major
+  T* Wq = Jacc + (size_t)N * ma;       // QR mode: work copy of the augmented matrix
   const int64_t warp0 = (int64_t)blockIdx.x * kLsqWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kLsqWarpsPerBlock;
   const T rtol = p.rtol, atol = p.atol;
@@ -173,6 +185,8 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
       for (int i = lane; i < m; i += 32) ds[i] = __ldg(drow + i);
     }
     for (int i = lane; i < mp; i += 32) racc[i] = T(0);
+    if (QRMODE)
+      for (int i = lane; i < N * ma; i += 32) Jacc[i] = T(0);  // gauss_newton.py:229-230: zero-filled f_info
     __syncwarp();
 
     // ---------------- init (gauss_newton.py:229-241, trust_region.py:75, _iterate.py:214-219)
@@ -217,16 +231,29 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
       // ---- search (trust_region.py:86-104 with constants :125-128 / learning_rate.py:24-35)
       bool accept = true;
       if (TRUST) {
-        T lin = T(0), quad = T(0);
+        T pred;
+        if (QRMODE) {
+          T sj = T(0);
+          for (int i = lane; i < m; i += 32) {
+            T s = T(0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          T gd = T(0);
+            for (int a = 0; a < N; ++a) s += Jacc[a * ma + i] * d[a];
+            s += racc[i];
+            sj += s * s;
+          }
+          pred = T(0.5) * (warp_sum(sj) - rr);  // the reference's expression, term by term
+        } else {
+          T lin = T(0), quad = T(0);
 #pragma unroll
-          for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
-          quad += d[i] * gd;
-          lin += d[i] * g[i];
+          for (int i = 0; i < N; ++i) {
+            T gd = T(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) gd += G[Tri<N>::at(i, j)] * d[j];
+            quad += d[i] * gd;
+            lin += d[i] * g[i];
+          }
+          pred = predicted_reduction(lin, quad, rr);  // 0.5(|J d + r|^2 - |r|^2), trust_region.py:182-186
         }
-        const T pred = predicted_reduction(lin, quad, rr);  // 0.5(|J d + r|^2 - |r|^2), trust_region.py:182-186
         const T df = T(0.5) * rre - T(0.5) * rr;
         accept = (df <= T(0.01) * pred) || first;
         const bool good = (df < T(0.99) * pred) && (pred < T(0)) && !first;
@@ -268,22 +295,29 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
           for (int q = 0; q < NAUX; ++q) aux[q] = auxs[q * mp + i];
           const T re = rtry[i], ro = racc[i];
           Model::jac_row(y, pre, CurveRow<T>{xs[i], T(0)}, aux, j);
+          if (QRMODE) {
 #pragma unroll
-          for (int a = 0; a < N; ++a) {
+            for (int a = 0; a < N; ++a) Jacc[a * ma + i] = j[a];
+          } else {
 #pragma unroll
-            for (int b = 0; b <= a; ++b) acc[Tri<N>::at(a, b)] += j[a] * j[b];
-            acc[NG + a] += j[a] * re;
+            for (int a = 0; a < N; ++a) {
+#pragma unroll
+              for (int b = 0; b <= a; ++b) acc[Tri<N>::at(a, b)] += j[a] * j[b];
+              acc[NG + a] += j[a] * re;
+            }
           }
           const T fs = atol + rtol * t_abs(re);
           if (maxnorm) fconv = fconv && (t_abs(re - ro) < fs);
           else fn.add(t_abs(re - ro) / fs);
           if (p.root_near_zero) zn.add(t_abs(first ? re : ro));
         }
-        warp_allreduce_array<T, NG + N>(acc, scratch, lane);
+        if (!QRMODE) {
+          warp_allreduce_array<T, NG + N>(acc, scratch, lane);
 #pragma unroll
-        for (int a = 0; a < NG; ++a) G[a] = acc[a];
+          for (int a = 0; a < NG; ++a) G[a] = acc[a];
 #pragma unroll
-        for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
+          for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
+        }
         if (maxnorm) {
           fconv = __all_sync(kFull, fconv);
         } else {
@@ -307,7 +341,64 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (sizeof(T) == 4 ? 4 : 
       T lam = T(0);
       if (TRUST) lam = (delta > Num<T>::eps()) ? T(1) / delta : Num<T>::max();
       T pstep[N];
-      spd_solve<T, N>(G, lam, g, pstep);
+      if (QRMODE) {
+        __syncwarp();
+        T* bq = rtry;  // free until the next trial evaluation: right-hand side [r; 0] of the augmented system
+        const T sq = t_sqrt(lam);
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+          for (int i = lane; i < ma; i += 32) Wq[a * ma + i] = (i < m) ? Jacc[a * ma + i] : ((i - mp == a) ? sq : T(0));
+        for (int i = lane; i < mp; i += 32) bq[i] = (i < m) ? racc[i] : T(0);
+        __syncwarp();
+        // Householder reflections, column by column; the rows at or below the diagonal are all rows except 0..k-1.  The
+        // right-hand side of the 32 augmented rows is zero before the first reflection and is kept in a register (baug).
+        T baug = T(0);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          T sig = T(0);
+          for (int i = lane; i < ma; i += 32)
+            if (i >= k) sig += Wq[k * ma + i] * Wq[k * ma + i];
+          sig = warp_sum(sig);
+          const T xk = Wq[k * ma + k];
+          const T alpha = (xk > T(0)) ? -t_sqrt(sig) : t_sqrt(sig);
+          const T inv = T(1) / (sig - alpha * xk);  // 2 / v^T v; a zero column gives 0/0 -> non-finite step -> `singular`
+          T dots[N + 1];
+#pragma unroll
+          for (int j = 0; j <= N; ++j) dots[j] = T(0);
+          for (int i = lane; i < ma; i += 32) {
+            if (i >= k) {
+              const T vi = (i == k) ? xk - alpha : Wq[k * ma + i];
+#pragma unroll
+              for (int j = k + 1; j < N; ++j) dots[j] += vi * Wq[j * ma + i];
+              dots[N] += vi * (i < mp ? bq[i] : baug);
+            }
+          }
+#pragma unroll
+          for (int j = k + 1; j <= N; ++j) dots[j] = warp_sum(dots[j]) * inv;
+          for (int i = lane; i < ma; i += 32) {
+            if (i >= k) {
+              const T vi = (i == k) ? xk - alpha : Wq[k * ma + i];
+#pragma unroll
+              for (int j = k + 1; j < N; ++j) Wq[j * ma + i] -= vi * dots[j];
+              if (i < mp) bq[i] -= vi * dots[N];
+              else baug -= vi * dots[N];
+            }
+          }
+          if (lane == k) Wq[k * ma + k] = alpha;  // R_kk (row k is slot 0 of lane k)
+          __syncwarp();
+        }
+        // back substitution R p = (Q^T b)[0..N): R sits in rows 0..N-1
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+          T s = bq[i];
+#pragma unroll
+          for (int j = i + 1; j < N; ++j) s -= Wq[j * ma + i] * pstep[j];
+          pstep[i] = s / Wq[i * ma + i];
+        }
+        __syncwarp();
+      } else {
+        spd_solve<T, N>(G, lam, g, pstep);
+      }
       bool pfin = true;
 #pragma unroll
       for (int j = 0; j < N; ++j) {

@@ -20,9 +20,9 @@ struct LsqArgs {
 
 int device_sm_count();
 
-template <class Model, typename T, bool TRUST> int lsq_launch_one(const LsqParams<T>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel<Model, T, TRUST>;
-  const size_t smem = lsq_smem_bytes<Model, T>(p.m_pad);
+template <class Model, typename T, bool TRUST, bool QRMODE = false> int lsq_launch_one(const LsqParams<T>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel<Model, T, TRUST, QRMODE>;
+  const size_t smem = lsq_smem_bytes<Model, T>(p.m_pad, QRMODE);
   if (smem > 227 * 1024) {
     set_error("least_squares: m=%d needs %zu bytes of shared memory per block (limit 227 KB)", p.m, smem);
     return B200OPT_EINVAL;
@@ -67,7 +67,10 @@ template <template <typename> class ModelT, typename T> int lsq_launch_typed(con
   p.root_near_zero = a.opts->root_near_zero;
   constexpr int V = Num<T>::kVec;
   p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
-  if (a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT) return lsq_launch_rpl<Model, T, true>(p, a.stream);
+  const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
+  if (a.opts->linear_solver == B200OPT_LINSOLVE_QR)  // the reference's own linear algebra (see lsq_kernel.cuh, QR mode)
+    return lm ? lsq_launch_one<Model, T, true, true>(p, a.stream) : lsq_launch_one<Model, T, false, true>(p, a.stream);
+  if (lm) return lsq_launch_rpl<Model, T, true>(p, a.stream);
   return lsq_launch_rpl<Model, T, false>(p, a.stream);
 }
 

@@ -502,6 +502,11 @@ int32_t b200opt_lsq_step(int32_t solver, int32_t dtype, int64_t batch, int32_t n
     set_error("lsq_step: bad options");
     return B200OPT_EINVAL;
   }
+  if (opts->linear_solver != B200OPT_LINSOLVE_NORMAL_CHOLESKY) {
+    set_error("lsq_step: the per-iteration step kernel carries (G, g) and solves the normal equations; linear_solver = QR is available "
+              "in the persistent kernels of the registered families (b200opt_least_squares)");
+    return B200OPT_EINVAL;
+  }
   if (solver != B200OPT_SOLVER_LEVENBERG_MARQUARDT && solver != B200OPT_SOLVER_GAUSS_NEWTON) {
     set_error("lsq_step: solver %d is not a least-squares solver", solver);
     return B200OPT_EINVAL;

@@ -286,3 +286,64 @@ def test_gauss2_fp32_residual_counts(m, solver_cls, oracle):
     else:
         assert s["within_2tol_ok"] >= 0.99 and s["both_ok"] >= 0.85
     assert abs(s["mean_steps"][0] - s["mean_steps"][1]) / s["mean_steps"][1] <= 0.06
+
+
+# ---- linear_solver=QR(): the reference's own linear algebra (levenberg_marquardt.py:66-75, trust_region.py:182-186) -------
+def _illcond_exp_decay(B=256, bscale=1e-4, seed=5):
+    """Exponential decays with a rate so small that exp(-b t) is nearly the constant column: kappa(J) ~ 1e9 at bscale=1e-4."""
+    rng = np.random.default_rng(seed)
+    t = np.linspace(0, 4, 64)
+    a, b, c = rng.uniform(1, 3, B), rng.uniform(0.5, 2, B) * bscale, rng.uniform(-0.5, 0.5, B)
+    truth = np.stack([a, b, c], 1)
+    d = a[:, None] * np.exp(-b[:, None] * t) + c[:, None] + 1e-9 * rng.standard_normal((B, 64))
+    y0 = truth * (1 + 0.01 * rng.uniform(-1, 1, (B, 3)))
+    return dict(t=t, d=d, y0=y0)
+
+
+def test_qr_mode_solves_what_the_normal_equations_cannot():
+    """GaussNewton on kappa(J) ~ 1e9: J^T J is numerically singular in fp64 (kappa^2 eps >> 1), the Cholesky of the normal
+    equations breaks down and the default path reports `singular` - as its restatement in the oracle does.  With
+    linear_solver=QR() the kernel runs the reference's operations (Householder QR of J, kappa enters once) and reproduces the
+    QR oracle: successful everywhere, same iteration counts, values to tolerance."""
+    w = _illcond_exp_decay()
+    args = dict(t=w["t"], d=w["d"])
+    o_qr = S.gauss_newton(M.exp_decay, w["y0"], args, rtol=1e-8, atol=1e-8, linsolve="qr")
+    o_gram = S.gauss_newton(M.exp_decay, w["y0"], args, rtol=1e-8, atol=1e-8, linsolve="gram")
+    assert (o_qr["result"] == optx.RESULTS.successful).all() and (o_gram["result"] == optx.RESULTS.singular).mean() > 0.9
+    g_qr = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8, linear_solver=optx.QR()))
+    g_gram = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8))
+    s = compare(g_qr, o_qr, 1e-8, 1e-8, "GN exp_decay kappa~1e9, QR mode vs oracle[qr]")
+    assert s["result_match"] == 1.0 and s["within_tol"] >= 0.99 and s["steps_match"] >= 0.9
+    assert (to_np(g_gram.result) == optx.RESULTS.singular).mean() > 0.9   # the normal equations fail here, loudly
+    # moderately ill-conditioned (kappa ~ 1e7): both converge, the normal equations need more steps (kappa^2 eps ~ 1e-2)
+    w = _illcond_exp_decay(bscale=1e-3)
+    g_qr = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8, linear_solver=optx.QR()))
+    g_gram = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8))
+    assert (to_np(g_qr.result) == 0).all() and (to_np(g_gram.result) == 0).all()
+    assert to_np(g_qr.stats["num_steps"]).mean() <= to_np(g_gram.stats["num_steps"]).mean()
+
+
+@pytest.mark.parametrize("name", ["exp_decay", "gauss2"])
+def test_qr_mode_vs_oracle(name):
+    """LevenbergMarquardt(linear_solver=QR()) on the two LM configs against the QR oracle: same operations as the reference,
+    so the distribution of iteration counts is the oracle's (|bias| of the mean <= 1 %), values to tolerance."""
+    if name == "exp_decay":
+        w = synthetic.exp_decay_batch(4096)
+        tol, model, omodel, args, targs = 1e-8, optx.models.exp_decay, M.exp_decay, dict(t=w["t"], d=w["d"]), (_cuda(w["t"]), _cuda(w["d"]))
+    else:
+        w = synthetic.gauss2_batch(2048)
+        tol, model, omodel, args, targs = 1e-4, optx.models.gauss2, M.gauss2, dict(x=w["x"], d=w["d"]), (_cuda(w["x"]), _cuda(w["d"]))
+    sol = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol, linear_solver=optx.QR()), _cuda(w["y0"]), targs, throw=False)
+    dflt = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol), _cuda(w["y0"]), targs, throw=False)
+    qr = S.levenberg_marquardt(omodel, w["y0"], args, rtol=tol, atol=tol, linsolve="qr")
+    s = compare(sol, qr, tol, tol, f"{name} QR mode vs oracle[qr]")
+    sd = compare(dflt, qr, tol, tol, f"{name} default mode vs oracle[qr]")
+    assert s["result_match"] >= 0.999 and s["within_tol"] >= 0.99
+    bias = s["mean_steps"][0] / s["mean_steps"][1] - 1.0
+    print(f"[qr mode {name}] steps_match {s['steps_match']:.3f} (default mode {sd['steps_match']:.3f}), mean-step bias {100 * bias:+.2f}%")
+    assert abs(bias) <= 0.01
+    assert s["steps_match"] >= 0.55
+    # host entry point, same kernel
+    hs = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol, linear_solver=optx.QR()), w["y0"],
+                            tuple(np.asarray(args[k]) for k in args), throw=False)
+    assert np.array_equal(hs.value, to_np(sol.value))

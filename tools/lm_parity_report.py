@@ -39,11 +39,22 @@ def main():
         modes = {m: c_oracle.levenberg_marquardt(name, w["y0"], w[xk], w["d"], rtol=tol, atol=tol, linsolve=m)
                  for m in ("qr", "gram", "kernel", "kernel_exact_pred")}
         r = {"batch": a.batch, "gpu_mean_steps": float(gs.mean())}
+        # the kernels' QR mode (linear_solver=QR(): the reference's operations) against the same oracle modes
+        solq = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol, linear_solver=optx.QR()), torch.as_tensor(w["y0"], device=dev),
+                                  (torch.as_tensor(w[xk], device=dev), torch.as_tensor(w["d"], device=dev)), throw=False)
+        qv, qs, qr_ = solq.value.cpu().numpy(), solq.stats["num_steps"].cpu().numpy(), solq.result.cpu().numpy()
+        r["gpu_qr_mode_mean_steps"] = float(qs.mean())
         for m, o in modes.items():
             scaled = np.max(np.abs(gv - o["value"]) / (tol + tol * np.abs(o["value"])), axis=1)
             r[f"gpu_vs_{m}"] = {"steps_match": float((gs == o["num_steps"]).mean()), "mean_steps_oracle": float(o["num_steps"].mean()),
                                 "bias_pct": float(100 * (gs.mean() / o["num_steps"].mean() - 1)), "result_match": float((gr == o["result"]).mean()),
                                 "within_tol": float((scaled <= 1).mean()), "within_2tol": float((scaled <= 2).mean())}
+        for m in ("qr", "gram", "kernel"):
+            o = modes[m]
+            scaled = np.max(np.abs(qv - o["value"]) / (tol + tol * np.abs(o["value"])), axis=1)
+            r[f"gpu_qr_mode_vs_{m}"] = {"steps_match": float((qs == o["num_steps"]).mean()), "bias_pct": float(100 * (qs.mean() / o["num_steps"].mean() - 1)),
+                                        "result_match": float((qr_ == o["result"]).mean()), "within_tol": float((scaled <= 1).mean())}
+        r["gpu_qr_mode_vs_gpu_default"] = {"steps_match": float((qs == gs).mean()), "bias_pct": float(100 * (qs.mean() / gs.mean() - 1))}
         for m in ("gram", "kernel", "kernel_exact_pred"):
             o, q = modes[m], modes["qr"]
             scaled = np.max(np.abs(o["value"] - q["value"]) / (tol + tol * np.abs(q["value"])), axis=1)
