@@ -265,6 +265,8 @@ class RootSession(_Session):
         self._common(solver, y0, args, args_in_dims, max_steps)
         t, lib = self.t, self.lib
         n, dev = self.n, self.dev
+        if n > 32:
+            raise NotImplementedError("generic Newton/Chord step kernel supports n <= 32 unknowns (row-per-lane LU)")
         self.empty = self.B == 0
         if self.empty:
             return
@@ -467,16 +469,28 @@ def protocol_step(state, args):
 
 
 def _aux_at(state, y, args):
+    """The auxiliary output of `fn` at `y` (`None` when the function has none), batched like `y`."""
     t = _torch()
     aux_of = getattr(state, "_aux_of", None)
-    if aux_of is None:
+    if aux_of is None or getattr(state, "_aux_is_none", False):
         return None
     with t.no_grad():
         if y.ndim == 1:
             return aux_of(y, args)
-        probe = aux_of(y[0], args) if state._in_dims is None else None
-        if probe is None and state._in_dims is None:
-            return None
+        saw_none = []
+
+        def tensor_aux(v, a):  # vmap wants tensors out: a function without auxiliary output returns a placeholder
+            out = aux_of(v, a)
+            if out is None:
+                saw_none.append(True)
+                return v.new_zeros(())
+            return out
+
         if state._in_dims is None:
-            return t.func.vmap(lambda v: aux_of(v, args))(y)
-        return t.func.vmap(aux_of, in_dims=(0, state._in_dims))(y, args)
+            out = t.func.vmap(lambda v: tensor_aux(v, args))(y)
+        else:
+            out = t.func.vmap(tensor_aux, in_dims=(0, state._in_dims))(y, args)
+        if saw_none:
+            state._aux_is_none = True  # decided once: later steps skip the evaluation
+            return None
+        return out

@@ -9,7 +9,9 @@ import numpy as np
 
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
 _SO = os.path.join(_DIR, "liboracle.so")
+_SO_FMA = os.path.join(_DIR, "liboracle_fma.so")  # same sources, a*b+c contracted to fma (what nvcc does by default)
 _lib = None
+_lib_fma = None
 MODELS = {"exp_decay": 0, "gauss2": 1}
 
 
@@ -18,23 +20,57 @@ def build():
     return _SO
 
 
+def _nb_sig(lib):
+    lib.oracle_newton_implicit_euler.restype = C.c_int
+    lib.oracle_newton_implicit_euler.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.oracle_bfgs_rosenbrock.restype = C.c_int
+    lib.oracle_bfgs_rosenbrock.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int]
+
+
+def _lm_sig(lib):
+    _nb_sig(lib)
+    lib.oracle_lm_solve.restype = C.c_int
+    lib.oracle_lm_solve.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int]
+
+
+def fma_available() -> bool:
+    """The contracted build exists and this CPU can run it (x86 FMA3)."""
+    if not os.path.exists(_SO_FMA):
+        try:
+            build()
+        except Exception:  # noqa: BLE001
+            return False
+    if not os.path.exists(_SO_FMA):
+        return False
+    try:
+        with open("/proc/cpuinfo") as fh:
+            return " fma " in fh.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def load_fma():
+    global _lib_fma
+    if _lib_fma is None:
+        if not fma_available():
+            raise RuntimeError("liboracle_fma.so is not available on this machine")
+        _lib_fma = C.CDLL(_SO_FMA)
+        _lm_sig(_lib_fma)
+    return _lib_fma
+
+
 def load():
     global _lib
     if _lib is None:
         if not os.path.exists(_SO):
             build()
         _lib = C.CDLL(_SO)
-        _lib.oracle_lm_solve.restype = C.c_int
-        _lib.oracle_lm_solve.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_int]
+        _lm_sig(_lib)
         _lib.oracle_max_threads.restype = C.c_int
-        _lib.oracle_newton_implicit_euler.restype = C.c_int
-        _lib.oracle_newton_implicit_euler.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        _lib.oracle_bfgs_rosenbrock.restype = C.c_int
-        _lib.oracle_bfgs_rosenbrock.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
-                                                C.c_void_p, C.c_int]
     return _lib
 
 
@@ -42,8 +78,9 @@ def max_threads() -> int:
     return load().oracle_max_threads()
 
 
-def levenberg_marquardt(model: str, y0, x, d, *, rtol, atol, max_steps=256, linsolve="qr", nthreads=0):
-    lib = load()
+def levenberg_marquardt(model: str, y0, x, d, *, rtol, atol, max_steps=256, linsolve="qr", nthreads=0, fma=False):
+    """linsolve: "qr" | "gram" | "kernel" | "kernel_exact_pred" (oracle/c/lm_oracle.c); fma=True: the contracted build."""
+    lib = load_fma() if fma else load()
     y0 = np.ascontiguousarray(y0)
     dt = y0.dtype
     x = np.ascontiguousarray(x, dtype=dt)
@@ -76,9 +113,9 @@ def newton_implicit_euler(y0, A, B, y_prev, dt, *, rtol, atol, max_steps=256, ch
     return dict(value=y, num_steps=steps, result=res)
 
 
-def bfgs_rosenbrock(y0, *, rtol, atol, max_steps=256, nthreads=0):
+def bfgs_rosenbrock(y0, *, rtol, atol, max_steps=256, nthreads=0, fma=False):
     """BFGS (inverse update, backtracking Armijo) on the chained Rosenbrock function (fp64, max_norm), C + OpenMP."""
-    lib = load()
+    lib = load_fma() if fma else load()
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     Bn, n = y0.shape
     y = np.empty_like(y0)

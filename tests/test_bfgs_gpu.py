@@ -42,6 +42,26 @@ def test_bfgs_rosenbrock_vs_oracle():
     assert np.allclose(to_np(sol.state["f"]), f_gpu, rtol=1e-9, atol=1e-14)
 
 
+def test_bfgs_final_state_vs_c_oracle_at_the_solver_tolerance():
+    """Final values at the SOLVER's tolerance (1e-8), on 4096 problems, against the C restatement.  Measured: 94.5 % of the
+    minimisers agree to one tolerance unit, 100 % to ten, identical counts on 36 %, mean count equal to 0.01 %.  That is the
+    level at which two builds of the same C oracle agree when only a*b+c -> fma changes (94.8 % / 100 % / 35 %,
+    tests/test_oracle_pred_modes.py::test_bfgs_moves_with_the_rounding_alone): ~760 quasi-Newton steps amplify one rounding
+    into a different (equally valid) stopping iterate."""
+    from oracle import c_oracle
+
+    w = synthetic.rosenbrock_batch(4096)
+    sol = _solve(w["y0"], max_steps=4096)
+    ref = c_oracle.bfgs_rosenbrock(w["y0"], rtol=1e-8, atol=1e-8, max_steps=4096)
+    s = compare(sol, ref, 1e-8, 1e-8, "bfgs rosenbrock n=64 x4096 vs C oracle")
+    scaled = np.max(np.abs(to_np(sol.value) - ref["value"]) / (1e-8 + 1e-8 * np.abs(ref["value"])), axis=1)
+    print(f"[bfgs final] within 1 tol {np.mean(scaled <= 1):.4f}, within 10 tol {np.mean(scaled <= 10):.4f}, max {scaled.max():.3g} tolerance units")
+    assert s["result_match"] == 1.0
+    assert np.mean(scaled <= 1.0) >= 0.93 and np.mean(scaled <= 10.0) >= 0.999
+    assert s["steps_match"] >= 0.3
+    assert abs(s["mean_steps"][0] / s["mean_steps"][1] - 1.0) <= 0.002
+
+
 def test_bfgs_prefix_state_parity():
     """First k steps: identical accept/reject sequence and iterates to rounding (before chaos sets in)."""
     w = synthetic.rosenbrock_batch(128)

@@ -44,8 +44,13 @@ def test_lm_exp_decay_fp64_vs_oracle():
     # accept/reject decisions inside rounding noise (see test_lm_prefix_state_parity), so two restatements of the
     # same algorithm already disagree (NumPy-vs-C oracle: 74%, QR-vs-Gram: 89%).  What is comparable: the
     # distribution (mean within 3%) and, step by step, the state machine (prefix test below).
-    assert abs(sg["mean_steps"][0] - sg["mean_steps"][1]) / sg["mean_steps"][1] <= 0.03
-    assert sg["steps_match"] >= 0.5
+    # Measured (profiles/lm_parity_r2*.json, 32,768 problems): count match 0.61 against every oracle mode - exactly the level
+    # at which two builds of the SAME C oracle differ when only a*b+c -> fma changes (0.63, tests/test_oracle_pred_modes.py) -
+    # and mean-step bias -1.1 % against the QR oracle (round 1: +1.0 ... +2.4 % from the exactly evaluated predicted
+    # reduction; the contracted C build alone is at -0.4 %).
+    for s in (sg, sq):
+        assert abs(s["mean_steps"][0] / s["mean_steps"][1] - 1.0) <= 0.015
+        assert s["steps_match"] >= 0.58
 
 
 def test_lm_gauss2_fp32_vs_oracle():
@@ -63,7 +68,9 @@ def test_lm_gauss2_fp32_vs_oracle():
     for s in (sg, sq):
         assert s["result_match"] >= 0.999
         assert s["within_tol"] >= 0.99             # north_star: 1e-4 fp32 on solution values
-    assert abs(sg["mean_steps"][0] - sg["mean_steps"][1]) / sg["mean_steps"][1] <= 0.05
+    for s in (sg, sq):  # measured: count match 0.58-0.59, bias -0.3 ... -0.8 % (fma-vs-plain C oracle: 0.77, +-0.2 %)
+        assert abs(s["mean_steps"][0] / s["mean_steps"][1] - 1.0) <= 0.012
+        assert s["steps_match"] >= 0.55
     # the fit itself is right: residual norm at the solution matches the oracle's
     r = optx.models.gauss2(sol.value, (_cuda(w["x"]), _cuda(w["d"])))
     r_ref, _ = M.gauss2(qr["value"], args)
@@ -313,7 +320,11 @@ def test_qr_mode_solves_what_the_normal_equations_cannot():
     g_qr = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8, linear_solver=optx.QR()))
     g_gram = _solve_exp(w, optx.GaussNewton(1e-8, 1e-8))
     s = compare(g_qr, o_qr, 1e-8, 1e-8, "GN exp_decay kappa~1e9, QR mode vs oracle[qr]")
-    assert s["result_match"] == 1.0 and s["within_tol"] >= 0.99 and s["steps_match"] >= 0.9
+    # kappa eps ~ 1e-7: the minimiser itself is only defined to ~10 tolerance units along the flat direction
+    assert s["result_match"] == 1.0 and s["within_2tol_ok"] >= 0.99 and s["steps_match"] >= 0.85
+    r_g, _ = M.exp_decay(to_np(g_qr.value), args)
+    r_o, _ = M.exp_decay(o_qr["value"], args)
+    assert np.allclose((r_g * r_g).sum(1), (r_o * r_o).sum(1), rtol=1e-6, atol=1e-20)
     assert (to_np(g_gram.result) == optx.RESULTS.singular).mean() > 0.9   # the normal equations fail here, loudly
     # moderately ill-conditioned (kappa ~ 1e7): both converge, the normal equations need more steps (kappa^2 eps ~ 1e-2)
     w = _illcond_exp_decay(bscale=1e-3)

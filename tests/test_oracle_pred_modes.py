@@ -69,3 +69,43 @@ def test_pred_modes_numpy_oracle_agree_with_c():
     scaled = np.abs(k_np["value"] - k_c["value"]) / (1e-8 + 1e-8 * np.abs(k_c["value"]))
     assert scaled.max() <= 1.0
     assert abs(k_np["num_steps"].mean() / k_c["num_steps"].mean() - 1.0) <= 0.01
+
+
+@pytest.mark.skipif(not c_oracle.fma_available(), reason="needs an x86 CPU with FMA3 for the contracted build of the C oracle")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_iteration_counts_move_with_the_rounding_alone(name):
+    """The yardstick for final-iteration-count parity.  liboracle_fma.so is liboracle.so compiled with a*b+c -> fma (what nvcc
+    does to the CUDA kernels by default): the same algorithm, the same operation order, only the roundings differ.  Already
+    that changes the final count on 20-40 % of the problems and lowers the mean by a few tenths of a per cent - every problem
+    of these workloads ends on accept / reject decisions inside the rounding noise of |r|^2, and fewer roundings mean more
+    exact ties `df == 0`, which the reference's test accepts.  The CUDA kernels against the oracle sit at exactly this level
+    (count match 0.58-0.64, bias -0.2 ... -1.1 %: profiles/lm_parity_r2*.json), so problem-by-problem count equality with ANY
+    independent implementation - XLA's included - is not a property the reference algorithm has on these workloads."""
+    make, xk, tol = CASES[name]
+    w = make(8192)
+    for mode in ("qr", "kernel"):
+        a = c_oracle.levenberg_marquardt(name, w["y0"], w[xk], w["d"], rtol=tol, atol=tol, linsolve=mode)
+        b = c_oracle.levenberg_marquardt(name, w["y0"], w[xk], w["d"], rtol=tol, atol=tol, linsolve=mode, fma=True)
+        match = float((a["num_steps"] == b["num_steps"]).mean())
+        bias = b["num_steps"].mean() / a["num_steps"].mean() - 1.0
+        scaled = np.abs(a["value"] - b["value"]) / (tol + tol * np.abs(a["value"]))
+        print(f"[fma yardstick {name} {mode}] count match {match:.3f}, mean-step bias of the contracted build {100 * bias:+.2f}%, "
+              f"values within tol {(scaled.max(1) <= 1).mean():.4f}")
+        assert (a["result"] == b["result"]).mean() >= 0.999
+        assert (scaled.max(1) <= 1.0).mean() >= 0.99
+        assert match <= 0.9          # far from identical although nothing but the rounding changed
+        assert abs(bias) <= 0.012
+
+
+@pytest.mark.skipif(not c_oracle.fma_available(), reason="needs an x86 CPU with FMA3 for the contracted build of the C oracle")
+def test_bfgs_moves_with_the_rounding_alone():
+    """The same yardstick for BFGS on the chained Rosenbrock function (configs[3]): plain against contracted build of the same
+    C code - about a third of the counts equal, ~95 % of the minimisers within one tolerance unit, all within ten."""
+    w = synthetic.rosenbrock_batch(2048)
+    a = c_oracle.bfgs_rosenbrock(w["y0"], rtol=1e-8, atol=1e-8, max_steps=4096)
+    b = c_oracle.bfgs_rosenbrock(w["y0"], rtol=1e-8, atol=1e-8, max_steps=4096, fma=True)
+    scaled = np.max(np.abs(a["value"] - b["value"]) / (1e-8 + 1e-8 * np.abs(a["value"])), axis=1)
+    match = float((a["num_steps"] == b["num_steps"]).mean())
+    print(f"[fma yardstick bfgs] count match {match:.3f}, within 1 tol {np.mean(scaled <= 1):.4f}, within 10 tol {np.mean(scaled <= 10):.4f}")
+    assert (a["result"] == b["result"]).all()
+    assert match <= 0.6 and 0.9 <= np.mean(scaled <= 1.0) <= 0.99 and np.mean(scaled <= 10.0) >= 0.999

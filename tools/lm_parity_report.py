@@ -38,6 +38,9 @@ def main():
         gv, gs, gr = sol.value.cpu().numpy(), sol.stats["num_steps"].cpu().numpy(), sol.result.cpu().numpy()
         modes = {m: c_oracle.levenberg_marquardt(name, w["y0"], w[xk], w["d"], rtol=tol, atol=tol, linsolve=m)
                  for m in ("qr", "gram", "kernel", "kernel_exact_pred")}
+        if c_oracle.fma_available():  # the same C sources with a*b+c contracted to fma, as nvcc compiles the kernels
+            for m in ("qr", "kernel"):
+                modes[m + "_fma"] = c_oracle.levenberg_marquardt(name, w["y0"], w[xk], w["d"], rtol=tol, atol=tol, linsolve=m, fma=True)
         r = {"batch": a.batch, "gpu_mean_steps": float(gs.mean())}
         # the kernels' QR mode (linear_solver=QR(): the reference's operations) against the same oracle modes
         solq = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol, linear_solver=optx.QR()), torch.as_tensor(w["y0"], device=dev),
@@ -49,13 +52,13 @@ def main():
             r[f"gpu_vs_{m}"] = {"steps_match": float((gs == o["num_steps"]).mean()), "mean_steps_oracle": float(o["num_steps"].mean()),
                                 "bias_pct": float(100 * (gs.mean() / o["num_steps"].mean() - 1)), "result_match": float((gr == o["result"]).mean()),
                                 "within_tol": float((scaled <= 1).mean()), "within_2tol": float((scaled <= 2).mean())}
-        for m in ("qr", "gram", "kernel"):
+        for m in [k for k in ("qr", "gram", "kernel", "qr_fma", "kernel_fma") if k in modes]:
             o = modes[m]
             scaled = np.max(np.abs(qv - o["value"]) / (tol + tol * np.abs(o["value"])), axis=1)
             r[f"gpu_qr_mode_vs_{m}"] = {"steps_match": float((qs == o["num_steps"]).mean()), "bias_pct": float(100 * (qs.mean() / o["num_steps"].mean() - 1)),
                                         "result_match": float((qr_ == o["result"]).mean()), "within_tol": float((scaled <= 1).mean())}
         r["gpu_qr_mode_vs_gpu_default"] = {"steps_match": float((qs == gs).mean()), "bias_pct": float(100 * (qs.mean() / gs.mean() - 1))}
-        for m in ("gram", "kernel", "kernel_exact_pred"):
+        for m in [k for k in ("gram", "kernel", "kernel_exact_pred", "qr_fma", "kernel_fma") if k in modes]:
             o, q = modes[m], modes["qr"]
             scaled = np.max(np.abs(o["value"] - q["value"]) / (tol + tol * np.abs(q["value"])), axis=1)
             r[f"{m}_vs_qr"] = {"steps_match": float((o["num_steps"] == q["num_steps"]).mean()),
