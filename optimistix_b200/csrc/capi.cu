@@ -103,7 +103,9 @@ struct HostCache {
   size_t shared_bytes = 0;
   void release() {
     if (device < 0) return;
-    cudaSetDevice(device);
+    int current = -1;
+    cudaGetDevice(&current);
+    cudaSetDevice(device);  // the staging buffers are freed on the device that owns them ...
     for (int s = 0; s < kStreams; ++s) {
       if (st[s]) cudaStreamDestroy(st[s]);
       if (done[s]) cudaEventDestroy(done[s]);
@@ -115,6 +117,7 @@ struct HostCache {
     shared = nullptr;
     dev_bytes = pin_bytes = shared_bytes = 0;
     device = -1;
+    if (current >= 0) cudaSetDevice(current);  // ... and the caller's current device is left as it was
   }
   ~HostCache() { /* process teardown: the CUDA context may already be gone; leak rather than crash */ }
 };
@@ -144,10 +147,18 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 template <class Launch>
 static int host_pipeline(const char* who, int device, int64_t batch, int64_t chunk, const void* shared_h, size_t shared_bytes,
                          const std::vector<HostIn>& ins, const std::vector<HostOut>& outs, Launch launch) {
+  struct DeviceGuard {  // the host entry points work on `device` and leave the caller's current device untouched
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() {
+      if (prev >= 0) cudaSetDevice(prev);
+    }
+  } guard;
   if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return B200OPT_ECUDA;
   HostCache& hc = g_host;
   if (hc.device != device) {
     hc.release();
+    if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return B200OPT_ECUDA;  // streams and buffers below belong to `device`
     hc.device = device;
     for (int s = 0; s < kStreams; ++s) {
       if (check_cuda(cudaStreamCreateWithFlags(&hc.st[s], cudaStreamNonBlocking), "stream create")) return B200OPT_ECUDA;

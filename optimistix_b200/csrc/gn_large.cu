@@ -549,7 +549,9 @@ __device__ int solve32(const float* gram_out, int nparts, int64_t part_stride, d
     float dm = 0.f, pm = 0.f;
     for (int w = 0; w < 8; ++w) dm = fmaxf(dm, fs.red[w]), pm = fmaxf(pm, fs.red[32 + w]);
     step_ratio = dm / fmaxf(pm, 1e-37f);
-    if (pass > 0 && step_ratio <= 1e-6f) break;        // converged to the fp32 resolution of p_out
+    // a refinement step of relative size s leaves an error of about s^2 (the factor's relative accuracy is s): s <= 1e-4
+    // is below the resolution of the fp32 output
+    if (pass > 0 && step_ratio <= 1e-4f) break;
     if (pass == 2) break;
     // rho = g - A p in fp64 (A full symmetric, row-major in global memory / L2): warp w takes rows w, w + 32, ...
     for (int i = warp; i < n; i += 32) {

@@ -444,10 +444,20 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
             const int a = idx / N, c = idx % N;
             if (a >= 128 && c < 128) src = c * N + a;  // lower-left block: the transposed entry of the upper-right block
           }
+          // the partials are added in CTA order (the order of gram_reduce_kernel); 16 loads are in flight per thread - with
+          // 8 warps per SM the reduction is bound by memory-level parallelism, not by the adds
           sv = 0.f;
           const float* w = p.ws + src;
-#pragma unroll 4
-          for (int c = 0; c < (int)gridDim.x; ++c) sv += __ldcg(w + (size_t)c * WS_STRIDE);
+          const int parts = (int)gridDim.x;
+          int c = 0;
+          for (; c + 16 <= parts; c += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldcg(w + (size_t)(c + u) * WS_STRIDE);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) sv += v[u];
+          }
+          for (; c < parts; ++c) sv += __ldcg(w + (size_t)c * WS_STRIDE);
           p.out[idx] = sv;
         } else {
           sv = __ldcg(p.out + idx);  // the f-statistic (atomicMax target of every CTA; complete after the grid-wide meeting)
