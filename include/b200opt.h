@@ -316,10 +316,12 @@ int32_t b200opt_gn_solve_xchg(const void* xchg_local, int32_t world, int32_t par
  *                       counters in `workspace`.  solver: 0 = equilibrated fp32 blocked Cholesky + fp64 refinement with an
  *                       fp64 fallback when the refinement step is not small, 1 = fp64 Cholesky only.  timeout_ms bounds the
  *                       in-kernel wait for the peers (<= 0: 30 s).
- *   b200opt_gn_iterate  enqueues ONE iteration = two kernels: (1) the fused residual + tcgen05 Gram pass at state.y_eval
+ *   b200opt_gn_iterate  enqueues ONE iteration = two (three) kernels: (1) the fused residual + tcgen05 Gram pass at state.y_eval
  *                       (J read once), the cross-CTA reduction and - when xchg_bases_dev / xchg_local are given - the
- *                       publication of this rank's [G | g | r^T r | f-statistic] into every peer's exchange buffer, all in
- *                       one cooperative launch; (2) one CTA that waits for every rank's flag, sums the blocks in rank order
+ *                       publication of this rank's [G | g | r^T r | f-statistic] into every peer's exchange buffer
+ *                       (fold_reduce != 0: all in one cooperative launch, the CTAs meet at a grid-wide counter;
+ *                       fold_reduce == 0: a small reduction kernel follows the pass - measured equally fast, the default of the
+ *                       Python layer); (2) one CTA that waits for every rank's flag, sums the blocks in rank order
  *                       in fp64, solves (G + lambda I) p = g, applies the Cauchy test on y and f (_misc.py:291-310), and
  *                       advances the carry (y <- y_eval, y_eval <- y_eval - p, num_steps + 1, result).
  *                       Once state.terminate is set, state.result != successful or num_steps == max_steps, both kernels
@@ -339,7 +341,7 @@ int32_t b200opt_gn_init(void* state, const float* y0, int32_t n, double rtol, do
                         int32_t timeout_ms, float* r_old0, int64_t m_local, float* out, void* workspace, void* stream);
 int32_t b200opt_gn_iterate(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, void* state,
                            float* out, void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world,
-                           int32_t rank, double rtol, double atol, double lambda, void* stream);
+                           int32_t rank, double rtol, double atol, double lambda, int32_t fold_reduce, void* stream);
 /* r = J y - d for the "linear_rows" family (one coalesced pass over the row shard). If r_old is not NULL the
  * f-space half of cauchy_termination (optimistix/_misc.py:306-309) is fused in: *fmax_bits (device, caller-zeroed)
  * receives, as an IEEE bit pattern, max_i |r_i - r_old_i| / (atol + rtol |r_i|) over this shard. r may alias r_old. */

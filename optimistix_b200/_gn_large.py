@@ -99,14 +99,15 @@ class CudaOps:
                                             self._stream()), "b200opt_gn_init")
         self.launches += 2
 
-    def iterate(self, J, d, r0, r1, state, out, xchg, rtol, atol, lam=0.0):
+    def iterate(self, J, d, r0, r1, state, out, xchg, rtol, atol, lam=0.0, fold=False):
         bases = xchg.bases.data_ptr() if xchg is not None else None
         local = xchg.local if xchg is not None else None
         _lib.check(self.lib.b200opt_gn_iterate(J.data_ptr(), d.data_ptr(), r0.data_ptr(), r1.data_ptr(), J.shape[0], N, state.data_ptr(),
                                                out.data_ptr(), self.ws.data_ptr(), bases, local, xchg.world if xchg is not None else 1,
-                                               xchg.rank if xchg is not None else 0, float(rtol), float(atol), float(lam), self._stream()),
+                                               xchg.rank if xchg is not None else 0, float(rtol), float(atol), float(lam), int(bool(fold)),
+                                               self._stream()),
                    "b200opt_gn_iterate")
-        self.launches += 2
+        self.launches += 2 if fold else 3
 
     def solve_parts(self, parts, nparts, stride, lam, p, status, summary):
         """parts: the all-gathered [G | g | rr | f-stat] blocks of every rank (or this rank's own block, nparts = 1)."""
@@ -199,7 +200,7 @@ class PeerExchange:
 STATE_TAIL_INTS = 12  # int32 words after y[256], y_eval[256] in the device state (include/b200opt.h)
 
 
-def _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, check_every, linear_solver, timeout_ms):
+def _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, check_every, linear_solver, timeout_ms, fold_reduce=False):
     """The loop of _iterate.py:194-268 on the device: enqueue `check_every` iterations, read the 48-byte tail of the state."""
     import torch
 
@@ -226,7 +227,7 @@ def _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, check_every, line
             break
         k = min(check_every, max_steps - steps)
         for _ in range(k):
-            ops.iterate(J, d, r0, r1, state, out, xchg, rtol, atol)
+            ops.iterate(J, d, r0, r1, state, out, xchg, rtol, atol, fold=fold_reduce)
         enq += k
     if result < 0:
         raise _lib.B200OptError("peer exchange timed out: a rank never published its block of the normal equations")
@@ -243,7 +244,7 @@ def _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, check_every, line
 
 
 def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=None, ops=None, fused=True, exchange="peer",
-                       device_loop=True, check_every=4, linear_solver=0, timeout_ms=0):
+                       device_loop=True, check_every=4, linear_solver=0, timeout_ms=0, fold_reduce=False):
     """Solve min_y |J y - d|^2 with this rank's row shard (J [m_local, 256] fp32, d [m_local]); returns a Solution.
 
     `group`: a torch.distributed process group (None = the default group if initialised, else single rank).
@@ -252,7 +253,9 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     "nccl" = one all_gather_into_tensor per iteration when CUDA IPC is not available or `ops` has no kernels for it).
     `device_loop`: run the loop on the device (b200opt_gn_iterate; single rank or peer exchange), the host reading the
     state every `check_every` iterations; False = the step-by-step host loop (one host read per iteration).
-    `linear_solver`: 0 = equilibrated fp32 blocked Cholesky + fp64 refinement (fp64 fallback), 1 = fp64 Cholesky."""
+    `linear_solver`: 0 = equilibrated fp32 blocked Cholesky + fp64 refinement (fp64 fallback), 1 = fp64 Cholesky.
+    `fold_reduce`: reduce and publish inside the Gram kernel (one cooperative launch) instead of a separate small kernel;
+    same bits either way."""
     import torch
     import torch.distributed as dist
 
@@ -302,7 +305,8 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
             xchg = None
     if device_loop and fused and hasattr(ops, "iterate") and (not distributed or xchg is not None):
         with torch.cuda.device(dev):
-            return _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, max(1, int(check_every)), int(linear_solver), int(timeout_ms))
+            return _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, max(1, int(check_every)), int(linear_solver), int(timeout_ms),
+                                bool(fold_reduce))
     try:
         gathered = torch.empty(world * OUT_FLOATS, dtype=torch.float32, device=dev) if (distributed and xchg is None) else out
         summary = torch.zeros(2, dtype=torch.float32, device=dev)  # total r^T r, max f-stat

@@ -100,7 +100,7 @@ _SIGNATURES = {
     "b200opt_gn_solve_fast": (_i32, [_vp, _i32, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_gn_state_size": (_i64, []),
     "b200opt_gn_init": (_i32, [_vp, _vp, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
-    "b200opt_gn_iterate": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _vp]),
+    "b200opt_gn_iterate": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp]),
     "b200opt_linear_residual": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, C.c_float, C.c_float, _vp, _vp]),
 }
 

@@ -27,6 +27,12 @@ static int min_launch(int64_t batch, int n, const void* y0, const b200opt_option
   if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
   const int grid = (int)(batch < cap ? batch : cap);
+  QueueCounter qc;
+  p.queue = nullptr;
+  if (batch > cap) {  // dynamic problem queue after the first resident wave (common.cuh)
+    qc.acquire(stream);
+    p.queue = qc.ptr;
+  }
   kern<<<grid, kBfgsThreads, 0, stream>>>(p);
   return check_cuda(cudaGetLastError(), "bfgs_solve_kernel launch");
 }

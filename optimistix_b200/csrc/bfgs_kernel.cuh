@@ -44,7 +44,17 @@ template <typename T> struct MinParams {
   T rtol, atol;
   int norm;
   int max_steps;
+  unsigned long long* queue;  // ticket counter of the dynamic problem queue (common.cuh), or NULL: static grid-stride
 };
+
+// next problem of a CTA (block-uniform): static stride, or a ticket from the global counter broadcast through shared memory
+__device__ __forceinline__ int64_t next_problem_cta(unsigned long long* queue, int64_t prev, long long* slot) {
+  if (queue == nullptr) return prev + gridDim.x;
+  __syncthreads();  // every thread is done with the previous problem (and with its read of *slot)
+  if (threadIdx.x == 0) *slot = (long long)gridDim.x + (long long)atomicAdd(queue, 1ull);
+  __syncthreads();
+  return *slot;
+}
 
 constexpr int kBfgsN = 64;       // padded dimension
 constexpr int kBfgsThreads = 128;
@@ -116,7 +126,8 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
   const int e0 = lane, e1 = lane + 32;
   const T rtol = p.rtol, atol = p.atol;
 
-  for (int64_t prob = blockIdx.x; prob < p.batch; prob += gridDim.x) {
+  __shared__ long long next_slot;
+  for (int64_t prob = blockIdx.x; prob < p.batch; prob = next_problem_cta(p.queue, prob, &next_slot)) {
     // ---- init (quasi_newton.py:176-202, :334-340)
     T h[32];
 #pragma unroll

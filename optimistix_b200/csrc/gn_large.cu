@@ -11,7 +11,7 @@ size_t gn_workspace_solve_offset();
 size_t gn_workspace_sync_offset();
 int32_t gn_iterate_gram(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, const void* state, float* out,
                         void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world, int32_t rank, float rtol,
-                        float atol, void* stream);
+                        float atol, int32_t fold_reduce, void* stream);
 
 // Blocked right-looking Cholesky + both triangular solves on ONE CTA (the whole problem is 5.6 Mflop; what matters is
 // the number of block-wide barriers on the critical path, not the flop rate):
@@ -817,7 +817,7 @@ int32_t b200opt_gn_init(void* state, const float* y0, int32_t n, double rtol, do
 
 int32_t b200opt_gn_iterate(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, void* state, float* out,
                            void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world, int32_t rank,
-                           double rtol, double atol, double lambda, void* stream) {
+                           double rtol, double atol, double lambda, int32_t fold_reduce, void* stream) {
   if (!J || !d || !r0 || !r1 || !state || !out || !workspace || n != 256 || m_local < 4) {
     set_error("gn_iterate: need n == 256, m_local >= 4 and non-NULL buffers");
     return B200OPT_EINVAL;
@@ -831,7 +831,7 @@ int32_t b200opt_gn_iterate(const float* J, const float* d, float* r0, float* r1,
     return B200OPT_EINVAL;
   }
   if (int32_t e = gn_iterate_gram(J, d, r0, r1, m_local, n, state, out, workspace, xchg_bases_dev, xchg_local, world, rank, (float)rtol,
-                                  (float)atol, stream))
+                                  (float)atol, fold_reduce, stream))
     return e;
   double* A = reinterpret_cast<double*>(static_cast<char*>(workspace) + gn_workspace_solve_offset());
   const size_t smem = FAST_SMEM > SOLVE_SMEM ? FAST_SMEM : SOLVE_SMEM;

@@ -421,8 +421,17 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (b == 0) {
+        // one poller per CTA, with back-off: 148 threads hammering one L2 line slow down the CTAs that are still streaming J
+        // (measured: +170 us per pass with a 64 ns poll interval)
         atomicAdd(p.sync, 1u);
-        while (*reinterpret_cast<volatile unsigned*>(p.sync) < gridDim.x) __nanosleep(64);
+        unsigned ns = 256;
+        for (;;) {
+          unsigned seen;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync) : "memory");
+          if (seen >= gridDim.x) break;
+          __nanosleep(ns);
+          if (ns < 4096) ns *= 2;
+        }
         __threadfence();
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -499,7 +508,12 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
 // straight into the slot of this rank in every peer's exchange buffer (P2P stores over NVLink / NVSwitch), and the last CTA to
 // finish raises this rank's flag on every peer.  The collective is therefore part of the reduction kernel; the consumer
 // (gn_solve_kernel) waits on the flags.  No NCCL call, no extra launch, no host involvement.
-__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out, PeerXchg x) {
+__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out, PeerXchg x, const GnState* state) {
+  if (state && gn_frozen(state)) return;  // state-driven iteration: the solve has ended, nothing was computed, nothing is published
+  if (x.bases && x.seq_counter) {
+    x.seq = *x.seq_counter + 1u;
+    x.parity = (int)(x.seq & 1u);
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = N * N + N + 1;
   float s = 0.f;
@@ -569,6 +583,7 @@ int64_t b200opt_gn_gram_workspace_size(int32_t n) {
 struct GnFold {
   const GnState* state;
   float *rbuf0, *rbuf1;
+  bool fold;  // true: reduction + publication inside gram_kernel (cooperative launch); false: gram_reduce_kernel follows
 };
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
                             float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream,
@@ -653,7 +668,7 @@ namespace b200opt {
 // publication folded into the kernel
 int32_t gn_iterate_gram(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, const void* state, float* out,
                         void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world, int32_t rank, float rtol,
-                        float atol, void* stream) {
+                        float atol, int32_t fold_reduce, void* stream) {
   gram::PeerXchg x{nullptr, 0, 0, 0, 0, nullptr};
   if (xchg_bases_dev) {
     x.bases = reinterpret_cast<unsigned char* const*>(const_cast<void* const*>(xchg_bases_dev));
@@ -661,7 +676,7 @@ int32_t gn_iterate_gram(const float* J, const float* d, float* r0, float* r1, in
     x.rank = rank;
     x.seq_counter = reinterpret_cast<const unsigned*>(static_cast<const unsigned char*>(xchg_local) + gram::xchg_flags_offset(world)) + 2 * world + 1;
   }
-  GnFold fold{static_cast<const GnState*>(state), r0, r1};
+  GnFold fold{static_cast<const GnState*>(state), r0, r1, fold_reduce != 0};
   uint32_t* fmax_bits = reinterpret_cast<uint32_t*>(out + gram::N * gram::N + gram::N + 1);
   // y / r_old / r_out are taken from the state inside the kernel; `r0` stands in so that the argument checks see buffers
   return gn_gram_impl(J, d, static_cast<const GnState*>(state)->y_eval, r1, r0, fmax_bits, rtol, atol, m_local, n, out, workspace, stream, x, &fold);
@@ -724,10 +739,12 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, nullptr, nullptr, nullptr, nullptr, nullptr,
                  gram::PeerXchg{nullptr, 0, 0, 0, 0, nullptr}, debug};
   if (fold) {
-    // grid-wide meeting inside the kernel: cooperative launch guarantees that all CTAs are resident at the same time
     p.state = fold->state;
     p.rbuf0 = fold->rbuf0;
     p.rbuf1 = fold->rbuf1;
+  }
+  if (fold && fold->fold) {
+    // grid-wide meeting inside the kernel: cooperative launch guarantees that all CTAs are resident at the same time
     p.out = out;
     p.sync = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + gn_workspace_sync_offset());
     p.x = x;
@@ -739,7 +756,7 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;
-  gram::gram_reduce_kernel<<<(total + 1 + 255) / 256, 256, 0, st>>>(ws, grid, grid, out, x);
+  gram::gram_reduce_kernel<<<(total + 1 + 255) / 256, 256, 0, st>>>(ws, grid, grid, out, x, fold ? fold->state : nullptr);
   return check_cuda(cudaGetLastError(), "gram_reduce_kernel launch");
 }
 

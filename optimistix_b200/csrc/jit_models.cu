@@ -207,6 +207,12 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
     p.root_near_zero = a.opts->root_near_zero;
     constexpr int V = Num<T>::kVec;
     p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
+    QueueCounter qc;
+    p.queue = nullptr;
+    if (need > cap) {
+      qc.acquire(a.stream);
+      p.queue = qc.ptr;
+    }
     void* params[] = {&p};
     return check_cu(g_drv.LaunchKernel(fn, grid, 1, 1, kLsqWarpsPerBlock * 32, 1, 1, (unsigned)smem, a.stream, params, nullptr),
                     "cuLaunchKernel(run-time family)");

@@ -16,7 +16,14 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
   const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
   const int grid = (int)(need < cap ? need : cap);
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
+  QueueCounter qc;
+  LsqParams<float> pq = p;
+  pq.queue = nullptr;
+  if (need > cap) {  // dynamic problem queue after the first resident wave (common.cuh)
+    qc.acquire(stream);
+    pq.queue = qc.ptr;
+  }
+  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
   return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
 }
 

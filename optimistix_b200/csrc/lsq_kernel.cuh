@@ -47,6 +47,7 @@ template <typename T> struct LsqParams {
   int max_steps;
   int root_near_zero;
   int vec_ok;              // data rows 16-byte aligned and m a multiple of the vector width
+  unsigned long long* queue;  // ticket counter of the dynamic problem queue (common.cuh), or NULL: static grid-stride
 };
 
 // QR mode (B200OPT_LINSOLVE_QR): the reference's own operations instead of the normal equations.  The Jacobian of the
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (QRMODE ? 1 : (sizeof(
   for (int i = threadIdx.x; i < mp; i += blockDim.x) xs[i] = p.shared[i < m ? i : m - 1];
   __syncthreads();
 
-  for (int64_t prob = warp0; prob < p.batch; prob += nwarps) {
+  for (int64_t prob = warp0; prob < p.batch; prob = next_problem_warp(p.queue, prob, nwarps, lane)) {
     // ---------------- load: y0 (broadcast) and the data row (coalesced; 128-bit when aligned) into shared memory
     T y[N], ye[N];
 #pragma unroll

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
   const float2* xs2 = reinterpret_cast<const float2*>(xs);
   const float2* ds2 = reinterpret_cast<const float2*>(ds);
 
-  for (int64_t prob = warp0; prob < p.batch; prob += nwarps) {
+  for (int64_t prob = warp0; prob < p.batch; prob = next_problem_warp(p.queue, prob, nwarps, lane)) {
     T y[N], ye[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);

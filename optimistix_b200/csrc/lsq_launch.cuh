@@ -31,9 +31,16 @@ template <class Model, typename T, bool TRUST, bool QRMODE = false> int lsq_laun
   const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
   if (blocks_per_sm < 0) return B200OPT_ECUDA;
   const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;  // persistent: one resident wave, grid-stride
+  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;  // persistent: one resident wave, then the problem queue
   const int grid = (int)(need < cap ? need : cap);
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(p);
+  QueueCounter qc;
+  LsqParams<T> pq = p;
+  pq.queue = nullptr;
+  if (need > cap) {  // more problems than resident warps: later problems are handed out dynamically
+    qc.acquire(stream);
+    pq.queue = qc.ptr;
+  }
+  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
   return check_cuda(cudaGetLastError(), "lsq_solve_kernel launch");
 }
 
