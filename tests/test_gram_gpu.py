@@ -342,6 +342,8 @@ def test_device_loop_equals_host_loop(m):
         assert dev64.stats["num_steps"] == host.stats["num_steps"]
         assert torch.equal(dev64.value, host.value)
         assert abs(dev64.stats["loss"] - host.stats["loss"]) <= 1e-6 * abs(host.stats["loss"])
+    folded = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=True, linear_solver=1, fold_reduce=True)
+    assert torch.equal(folded.value, host.value) and folded.stats["num_steps"] == host.stats["num_steps"]  # same order of additions
     dev32 = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=True, linear_solver=0)
     assert dev32.result == optx.RESULTS.successful and dev32.stats["fp64_fallbacks"] == 0
     assert abs(dev32.stats["num_steps"] - host.stats["num_steps"]) <= 1

@@ -27,6 +27,8 @@ sv = optx.GaussNewton(1e-4, 1e-4)
 a = optx.least_squares(optx.models.linear_rows, sv, y0, (J, d), throw=False)  # default: device loop, peer exchange, fp32 + refinement solver
 assert "peer memory (device loop)" in a.stats["exchange"], a.stats
 a64 = gauss_newton_large(J, d, y0, sv, throw=False, linear_solver=1)           # device loop, fp64 solver
+af = gauss_newton_large(J, d, y0, sv, throw=False, linear_solver=1, fold_reduce=True)  # reduction + publication folded into the Gram kernel
+assert torch.equal(af.value, a64.value) and af.stats["num_steps"] == a64.stats["num_steps"]
 b = gauss_newton_large(J, d, y0, sv, throw=False, exchange="nccl")             # host loop over the NCCL all-gather (fp64 solver)
 c = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=False)           # host loop over the peer exchange
 assert a.result == a64.result == b.result == c.result == optx.RESULTS.successful, (a.result, a64.result, b.result, c.result)

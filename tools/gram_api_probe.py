@@ -60,8 +60,8 @@ def gram_only():
         ops.residual_gram(J, y, d, r, r_old, 1e-4, 1e-4, fmax, out)
 
 
-def api(solver):
-    return lambda: gauss_newton_large(J, d, y0, never, max_steps=a.iters, throw=False, linear_solver=solver, check_every=a.iters)
+def api(solver, fold=False):
+    return lambda: gauss_newton_large(J, d, y0, never, max_steps=a.iters, throw=False, linear_solver=solver, check_every=a.iters, fold_reduce=fold)
 
 
 def kernels_split():
@@ -82,7 +82,8 @@ def kernels_split():
 
 
 cfgs = {"gram+reduce kernels only": gram_only, "kernel-only loop (gram, reduce, fp64 solve)": kernels,
-        "device loop, fp32+refinement solver": api(0), "device loop, fp64 solver": api(1)}
+        "device loop, fp32+refinement solver": api(0), "device loop, fp64 solver": api(1),
+        "device loop, fp32+refinement solver, reduction folded into the Gram kernel": api(0, True)}
 for f in cfgs.values():
     f()
 res = {k: [] for k in cfgs}
