@@ -100,8 +100,17 @@ typedef struct b200opt_options {
   double kappa;               /* Newton/Chord non-Cauchy mode, default 1e-2 */
   int32_t linear_solver;      /* least squares only: B200OPT_LINSOLVE_* (the `linear_solver=` field of LevenbergMarquardt /
                                * GaussNewton, levenberg_marquardt.py:286, gauss_newton.py:387) */
-  int32_t reserved;           /* 0 */
+  int32_t data_dtype;         /* least squares only: B200OPT_DATA_* - storage type of the per-problem data rows */
 } b200opt_options_t;
+
+/* Storage type of `problem_args` of b200opt_least_squares(_host).  AS_COMPUTE: the compute dtype (the default).  F16 / U16 /
+ * I16: 16-bit values, `problem_args_stride` counted in 16-bit elements; every value is converted exactly to the compute dtype
+ * when the row is loaded, so the result equals the solve of the converted array bit for bit.  Halves the bytes per problem
+ * over PCIe and HBM (measured curves usually ARE 16-bit detector counts). */
+#define B200OPT_DATA_AS_COMPUTE 0
+#define B200OPT_DATA_F16 1
+#define B200OPT_DATA_U16 2
+#define B200OPT_DATA_I16 3
 
 /* Linear solve of the LM / GN descent.  NORMAL_CHOLESKY (default; BASELINE north_star): Cholesky of J^T J + lambda I, J never
  * materialised.  QR: the reference's own operations - Householder QR of the augmented system [J; sqrt(lambda) I] p = [r; 0]

@@ -92,6 +92,13 @@ class _Buf:
         return x.ctypes.data
 
 
+def _data16_kind(x):
+    """16-bit per-problem data (float16 / uint16 / int16) is handed to the kernels as it is (B200OPT_DATA_*): half the bytes per
+    problem; every value is converted exactly to the compute dtype when the row is loaded."""
+    name = str(getattr(x, "dtype", "")).replace("torch.", "")
+    return {"float16": _lib.DATA_F16, "uint16": _lib.DATA_U16, "int16": _lib.DATA_I16}.get(name, _lib.DATA_AS_COMPUTE)
+
+
 def _np_ndim(x):
     return x.ndim if hasattr(x, "ndim") else np.asarray(x).ndim
 
@@ -294,7 +301,16 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     a = fn.split_args(args)
     dev = y0.device if buf.device else None
     shared = buf.arr(a[fn.arg_names[0]], dev).reshape(-1)
-    prob = buf.arr(a[fn.arg_names[1]], dev)
+    data_kind = _data16_kind(a[fn.arg_names[1]])
+    if data_kind != _lib.DATA_AS_COMPUTE:
+        prob = a[fn.arg_names[1]]
+        if buf.device:
+            t = _torch()
+            prob = (prob if _is_torch(prob) else t.as_tensor(prob)).to(dev).contiguous()
+        else:
+            prob = np.ascontiguousarray(prob.detach().cpu().numpy() if _is_torch(prob) else prob)
+    else:
+        prob = buf.arr(a[fn.arg_names[1]], dev)
     if single and prob.ndim == 1:
         prob = prob[None]
     m = int(shared.shape[0])
@@ -302,7 +318,7 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
         raise ValueError(f"{fn.name}: per-problem data must have shape [{B}, {m}], got {tuple(prob.shape)}")
     solver_id = _lib.SOLVER_LM if isinstance(solver, LevenbergMarquardt) else _lib.SOLVER_GN
     opts = _lib.make_options(solver.rtol, solver.atol, solver.norm, max_steps, root_near_zero=_root_near_zero,
-                             linear_solver=solver.descent.linear_solver)
+                             linear_solver=solver.descent.linear_solver, data_dtype=data_kind)
     y_out = buf.empty((B, n), y0)
     steps = buf.empty_i32((B,), y0)
     res = buf.empty_i32((B,), y0)

@@ -28,7 +28,7 @@ class Options(C.Structure):
         ("root_near_zero", C.c_int32),
         ("kappa", C.c_double),
         ("linear_solver", C.c_int32),
-        ("reserved", C.c_int32),
+        ("data_dtype", C.c_int32),
     ]
 
 
@@ -131,6 +131,7 @@ def check(code: int, what: str):
 
 
 LINSOLVE_NORMAL_CHOLESKY, LINSOLVE_QR = 0, 1
+DATA_AS_COMPUTE, DATA_F16, DATA_U16, DATA_I16 = 0, 1, 2, 3
 
 
 def linear_solver_id(linear_solver) -> int:
@@ -149,10 +150,11 @@ def linear_solver_id(linear_solver) -> int:
                               "J^T J + lambda I, the default) and QR() (Householder QR of the augmented system)")
 
 
-def make_options(rtol, atol, norm="max", max_steps=256, cauchy_termination=True, root_near_zero=False, kappa=1e-2, linear_solver=None):
+def make_options(rtol, atol, norm="max", max_steps=256, cauchy_termination=True, root_near_zero=False, kappa=1e-2, linear_solver=None,
+                 data_dtype=0):
     if isinstance(norm, str):
         norm_id = NORM_IDS[norm]
     else:
         norm_id = NORM_IDS[getattr(norm, "norm_name")]
     return Options(float(rtol), float(atol), norm_id, int(max_steps), int(bool(cauchy_termination)), int(bool(root_near_zero)), float(kappa),
-                   linear_solver_id(linear_solver), 0)
+                   linear_solver_id(linear_solver), int(data_dtype))

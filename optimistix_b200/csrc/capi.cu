@@ -82,6 +82,10 @@ static int validate_common(const char* who, int dtype, int64_t batch, const b200
     set_error("%s: unknown linear_solver %d", who, opts->linear_solver);
     return B200OPT_EINVAL;
   }
+  if (opts->data_dtype < B200OPT_DATA_AS_COMPUTE || opts->data_dtype > B200OPT_DATA_I16) {
+    set_error("%s: unknown data_dtype %d", who, opts->data_dtype);
+    return B200OPT_EINVAL;
+  }
   return 0;
 }
 
@@ -284,7 +288,7 @@ void b200opt_default_options(b200opt_options_t* o) {
   o->root_near_zero = 0;
   o->kappa = 1e-2;
   o->linear_solver = B200OPT_LINSOLVE_NORMAL_CHOLESKY;
-  o->reserved = 0;
+  o->data_dtype = B200OPT_DATA_AS_COMPUTE;
 }
 
 int32_t b200opt_least_squares(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, int32_t m,
@@ -330,9 +334,10 @@ int32_t b200opt_least_squares_host(int32_t device, int32_t solver, int32_t model
     return B200OPT_EINVAL;
   }
   const size_t es = dtype == B200OPT_F32 ? 4 : 8;
+  const size_t ds = opts->data_dtype == B200OPT_DATA_AS_COMPUTE ? es : 2;  // 16-bit data rows: half (a quarter) of the bytes per problem
   return host_pipeline(
       "least_squares_host", device, batch, chunk, shared_args, es * shared_args_count,
-      {{y0, es * n}, {problem_args, es * (size_t)problem_args_stride}}, {{y_out, es * n}, {num_steps, 4}, {result, 4}},
+      {{y0, es * n}, {problem_args, ds * (size_t)problem_args_stride}}, {{y_out, es * n}, {num_steps, 4}, {result, 4}},
       [&](int64_t nb, const void* d_shared, const void** d_in, void** d_out, cudaStream_t st) {
         return b200opt_least_squares(solver, model_id, dtype, nb, n, m, d_in[0], d_shared, d_in[1], problem_args_stride, opts,
                                      d_out[0], static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), nullptr,

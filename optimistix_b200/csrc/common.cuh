@@ -108,6 +108,40 @@ __device__ __forceinline__ double predicted_reduction(double lin, double quad, d
   return 0.5 * __dsub_rn(jt, rr);
 }
 
+// ---- 16-bit per-problem data (b200opt_options_t.data_dtype) -------------------------------------------------------------
+// Detector counts and half-precision samples are what measured curves usually are; shipping them as 16-bit values halves the
+// bytes every problem moves over PCIe and HBM.  Each value is converted EXACTLY to the compute type on load (every uint16 /
+// int16 / float16 is representable in fp32), so the solve is the solve of the converted array, bit for bit.
+template <typename T> __device__ __forceinline__ T data16_to(unsigned short raw, int kind) {
+  if (kind == B200OPT_DATA_U16) return (T)raw;
+  if (kind == B200OPT_DATA_I16) return (T)(short)raw;
+  // IEEE binary16 -> fp32 by hand (no cuda_fp16.h under NVRTC): exact, subnormals and inf / NaN included
+  const unsigned sign = (unsigned)(raw & 0x8000u) << 16, ex = (raw >> 10) & 0x1fu, man = raw & 0x3ffu;
+  float f;
+  if (ex == 0) f = __uint_as_float(sign) + (sign ? -1.f : 1.f) * (float)man * 5.9604644775390625e-08f;  // man * 2^-24
+  else if (ex == 31) f = __uint_as_float(sign | 0x7f800000u | (man << 13));
+  else f = __uint_as_float(sign | ((ex + 112u) << 23) | (man << 13));
+  return (T)f;
+}
+// one data row of m 16-bit values -> m values of T in shared memory (128-bit loads when `vec`: row 16-byte aligned, m % 8 == 0)
+template <typename T> __device__ __forceinline__ void load_row16(const void* rows, int64_t row_index, int64_t stride, int m, int kind, bool vec,
+                                                                 T* dst, int lane) {
+  const unsigned short* src = static_cast<const unsigned short*>(rows) + row_index * stride;
+  if (vec) {
+    for (int i = lane; i < m / 8; i += 32) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dst[8 * i + 2 * e] = data16_to<T>((unsigned short)(v[e] & 0xffffu), kind);
+        dst[8 * i + 2 * e + 1] = data16_to<T>((unsigned short)(v[e] >> 16), kind);
+      }
+    }
+  } else {
+    for (int i = lane; i < m; i += 32) dst[i] = data16_to<T>(__ldg(src + i), kind);
+  }
+}
+
 // ---- dynamic problem queue of the persistent kernels -------------------------------------------------------------------
 // A worker (warp or CTA) takes problem `worker index` first; every further problem is a ticket from a global counter
 // (zero at launch).  Iteration counts vary a lot between problems (LM gauss2: mean 10, a few at max_steps = 256), so a static

@@ -207,6 +207,8 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
     p.root_near_zero = a.opts->root_near_zero;
     constexpr int V = Num<T>::kVec;
     p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
+    p.data_kind = a.opts->data_dtype;
+    p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
     QueueCounter qc;
     p.queue = nullptr;
     if (need > cap) {

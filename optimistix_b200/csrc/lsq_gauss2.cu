@@ -28,7 +28,8 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
 }
 
 int lsq_launch_gauss2(const LsqArgs& a) {
-  const bool aligned = (a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
+  const bool d16 = a.opts->data_dtype != B200OPT_DATA_AS_COMPUTE;  // 16-bit rows: any alignment (the loader has a scalar path)
+  const bool aligned = d16 || ((a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0));
   if (a.opts->linear_solver == B200OPT_LINSOLVE_NORMAL_CHOLESKY && a.dtype == B200OPT_F32 && a.n == Gauss2P2::N && a.m % 64 == 0 && aligned && a.opts->norm == B200OPT_NORM_MAX &&
       !a.opts->root_near_zero) {
     LsqParams<float> p;
@@ -50,6 +51,8 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.max_steps = a.opts->max_steps;
     p.root_near_zero = 0;
     p.vec_ok = 1;
+    p.data_kind = a.opts->data_dtype;
+    p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
     int rc;
     if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]

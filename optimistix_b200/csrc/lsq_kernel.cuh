@@ -48,6 +48,8 @@ template <typename T> struct LsqParams {
   int root_near_zero;
   int vec_ok;              // data rows 16-byte aligned and m a multiple of the vector width
   unsigned long long* queue;  // ticket counter of the dynamic problem queue (common.cuh), or NULL: static grid-stride
+  int data_kind;           // B200OPT_DATA_*: 0 = `prob` holds T; otherwise 16-bit values (prob_stride in 16-bit elements)
+  int data_vec;            // 16-bit rows: 16-byte aligned and m % 8 == 0
 };
 
 // QR mode (B200OPT_LINSOLVE_QR): the reference's own operations instead of the normal equations.  The Jacobian of the
@@ -177,7 +179,9 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, (QRMODE ? 1 : (sizeof(
 #pragma unroll
     for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);
     const T* drow = p.prob + prob * p.prob_stride;
-    if (p.vec_ok) {
+    if (p.data_kind != B200OPT_DATA_AS_COMPUTE) {
+      load_row16<T>(p.prob, prob, p.prob_stride, m, p.data_kind, p.data_vec != 0, ds, lane);
+    } else if (p.vec_ok) {
       using Vec = typename Num<T>::Vec;
       constexpr int V = Num<T>::kVec;
       for (int i = lane; i < m / V; i += 32)

@@ -237,8 +237,12 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
     T y[N], ye[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) y[j] = ye[j] = __ldg(p.y0 + prob * N + j);
-    const T* drow = p.prob + prob * p.prob_stride;
-    for (int i = lane; i < m / 4; i += 32) reinterpret_cast<float4*>(ds)[i] = __ldg(reinterpret_cast<const float4*>(drow) + i);
+    if (p.data_kind != B200OPT_DATA_AS_COMPUTE) {
+      load_row16<T>(p.prob, prob, p.prob_stride, m, p.data_kind, p.data_vec != 0, ds, lane);
+    } else {
+      const T* drow = p.prob + prob * p.prob_stride;
+      for (int i = lane; i < m / 4; i += 32) reinterpret_cast<float4*>(ds)[i] = __ldg(reinterpret_cast<const float4*>(drow) + i);
+    }
     for (int i = lane; i < mp; i += 32) racc[i] = T(0);
     __syncwarp();
 

@@ -74,6 +74,8 @@ template <template <typename> class ModelT, typename T> int lsq_launch_typed(con
   p.root_near_zero = a.opts->root_near_zero;
   constexpr int V = Num<T>::kVec;
   p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
+  p.data_kind = a.opts->data_dtype;
+  p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
   const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
   if (a.opts->linear_solver == B200OPT_LINSOLVE_QR)  // the reference's own linear algebra (see lsq_kernel.cuh, QR mode)
     return lm ? lsq_launch_one<Model, T, true, true>(p, a.stream) : lsq_launch_one<Model, T, false, true>(p, a.stream);

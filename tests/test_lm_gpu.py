@@ -359,3 +359,73 @@ def test_qr_mode_vs_oracle(name):
     hs = optx.least_squares(model, optx.LevenbergMarquardt(tol, tol, linear_solver=optx.QR()), w["y0"],
                             tuple(np.asarray(args[k]) for k in args), throw=False)
     assert np.array_equal(hs.value, to_np(sol.value))
+
+
+# ---- 16-bit per-problem data (B200OPT_DATA_F16 / U16 / I16) ----------------------------------------------------------------
+def _counts(w, kind):
+    """gauss2 data as 16-bit detector counts (offset 8192, 16384 counts per unit) and the matching start values."""
+    d = np.rint(w["d"].astype(np.float64) * 16384.0 + 8192.0)
+    y0 = w["y0"].astype(np.float64).copy()
+    y0[:, [0, 3, 7]] *= 16384.0
+    y0[:, 6] = y0[:, 6] * 16384.0 + 8192.0
+    if kind == "uint16":
+        return d.astype(np.uint16), y0.astype(np.float32)
+    if kind == "int16":
+        y0[:, 6] -= 16384.0
+        return (d - 16384.0).astype(np.int16), y0.astype(np.float32)
+    return w["d"].astype(np.float16), w["y0"]
+
+
+@pytest.mark.parametrize("kind", ["uint16", "int16", "float16"])
+@pytest.mark.parametrize("m", [256, 200])
+def test_sixteen_bit_data_is_the_solve_of_the_converted_array(kind, m):
+    """Data rows stored as 16-bit values are converted exactly on load: the result is bit-identical to passing the same values as
+    float32, on the device-pointer and on the host entry point (which then moves half the bytes), packed and scalar kernel."""
+    w = synthetic.gauss2_batch(2048, m=m, seed=31)
+    d16, y0 = _counts(w, kind)
+    d32 = d16.astype(np.float32)
+    sv = optx.LevenbergMarquardt(1e-4, 1e-4)
+    td16 = torch.as_tensor(d16.view(np.int16) if kind == "uint16" else d16, device=DEV)
+    if kind == "uint16":
+        td16 = td16.view(torch.uint16)
+    a = optx.least_squares(optx.models.gauss2, sv, _cuda(y0), (_cuda(w["x"]), td16), throw=False)
+    b = optx.least_squares(optx.models.gauss2, sv, _cuda(y0), (_cuda(w["x"]), _cuda(d32)), throw=False)
+    assert torch.equal(a.value, b.value) and torch.equal(a.stats["num_steps"], b.stats["num_steps"]) and torch.equal(a.result, b.result)
+    assert (to_np(a.result) == optx.RESULTS.successful).mean() > 0.99
+    h = optx.least_squares(optx.models.gauss2, sv, y0, (w["x"], d16), throw=False)
+    assert np.array_equal(h.value, to_np(a.value)) and np.array_equal(h.stats["num_steps"], to_np(a.stats["num_steps"]))
+    # ... and it is the oracle's solve of the converted array
+    ref = S.levenberg_marquardt(M.gauss2, y0, dict(x=w["x"], d=d32), rtol=1e-4, atol=1e-4, linsolve="qr")
+    s = compare(a, ref, 1e-4, 1e-4, f"gauss2 {kind} data m={m} vs oracle[qr] on the converted array")
+    assert s["result_match"] >= 0.995 and s["within_tol"] >= 0.985
+
+
+def test_sixteen_bit_data_fp64_and_ragged_alignment():
+    """fp64 compute with int16 data (exp_decay), a row pitch that is not a multiple of 8 (scalar 16-bit loads)."""
+    w = synthetic.exp_decay_batch(512)
+    d16 = np.rint(w["d"] * 8192.0).astype(np.int16)
+    y0 = w["y0"].copy()
+    y0[:, [0, 2]] *= 8192.0
+    pitch = 67
+    dp = np.zeros((512, pitch), np.int16)
+    dp[:, :64] = d16
+    sv = optx.LevenbergMarquardt(1e-8, 1e-8)
+    ref = optx.least_squares(optx.models.exp_decay, sv, _cuda(y0), (_cuda(w["t"]), _cuda(d16.astype(np.float64))), throw=False)
+    a = optx.least_squares(optx.models.exp_decay, sv, _cuda(y0), (_cuda(w["t"]), torch.as_tensor(d16, device=DEV)), throw=False)
+    assert torch.equal(a.value, ref.value) and torch.equal(a.stats["num_steps"], ref.stats["num_steps"])
+    # pitched rows through the C ABI directly
+    import ctypes as C
+
+    from optimistix_b200 import _lib
+
+    lib = _lib.load()
+    opts = _lib.make_options(1e-8, 1e-8, "max", 256, data_dtype=_lib.DATA_I16)
+    ty0, tt, tdp = _cuda(y0), _cuda(w["t"]), torch.as_tensor(dp, device=DEV)
+    y = torch.empty_like(ty0)
+    steps = torch.empty(512, dtype=torch.int32, device=DEV)
+    res = torch.empty(512, dtype=torch.int32, device=DEV)
+    _lib.check(lib.b200opt_least_squares(_lib.SOLVER_LM, optx.models.exp_decay.model_id, _lib.F64, 512, 3, 64, ty0.data_ptr(), tt.data_ptr(),
+                                         tdp.data_ptr(), pitch, C.byref(opts), y.data_ptr(), steps.data_ptr(), res.data_ptr(), None, None,
+                                         torch.cuda.current_stream().cuda_stream), "least_squares int16 pitched")
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref.value) and torch.equal(steps, ref.stats["num_steps"])
