@@ -574,14 +574,10 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
         launches += (kp + 1) * ((batch + args.chunk - 1) // args.chunk)
         del inp_host, inp_page
         if name == "gauss2":
-            # the same fits with the data as 16-bit detector counts (8192 + 16384 d, amplitudes and baseline in counts): what a
-            # measured spectrum usually is.  Half the H2D bytes per problem; rows are converted exactly to fp32 on load.
-            d16 = np.rint(inp["prob"].astype(np.float64) * 16384.0 + 8192.0).astype(np.uint16)
-            y16 = inp["y0"].astype(np.float64).copy()
-            y16[:, [0, 3, 7]] *= 16384.0
-            y16[:, 6] = y16[:, 6] * 16384.0 + 8192.0
-            h16 = {"y0": torch.as_tensor(y16.astype(np.float32)).pin_memory().numpy(), "shared": inp["shared"],
-                   "prob": torch.as_tensor(d16.view(np.int16)).pin_memory().numpy().view(np.uint16)}
+            # the same fits with the data rows stored as float16 (2^-11 relative quantisation, 20x below the noise of the data):
+            # half the H2D bytes per problem; rows are converted exactly to fp32 on load (uint16 / int16 counts work the same way)
+            d16 = inp["prob"].astype(np.float16)
+            h16 = {"y0": torch.as_tensor(inp["y0"]).pin_memory().numpy(), "shared": inp["shared"], "prob": torch.as_tensor(d16).pin_memory().numpy()}
             for _ in range(2):
                 hs16 = run_host(name, h16, args.chunk)
             barrier()
@@ -591,7 +587,7 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
             torch.cuda.synchronize()
             ms16 = max_over_ranks(1e3 * (time.perf_counter() - t0)) / K
             dv16 = {"y0": torch.as_tensor(h16["y0"], device=dev), "shared": torch.as_tensor(inp["shared"], device=dev),
-                    "prob": torch.as_tensor(d16.view(np.int16), device=dev).view(torch.uint16)}
+                    "prob": torch.as_tensor(d16, device=dev)}
             for _ in range(2):
                 s16 = run_device(name, dv16)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -601,11 +597,11 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
             ev1.record()
             torch.cuda.synchronize()
             dms16 = max_over_ranks(ev0.elapsed_time(ev1)) / K
-            e2e["uint16_data"] = {"value": batch * world / (ms16 / 1e3), "ms_per_step": ms16, "h2d_bytes_per_step": int(h16["y0"].nbytes + h16["prob"].nbytes + inp["shared"].nbytes),
+            e2e["float16_data"] = {"value": batch * world / (ms16 / 1e3), "ms_per_step": ms16, "h2d_bytes_per_step": int(h16["y0"].nbytes + h16["prob"].nbytes + inp["shared"].nbytes),
                                   "device_resident_ms_per_step": dms16, "device_resident_value": batch * world / (dms16 / 1e3),
                                   "successful_frac": float((s16.result == 0).float().mean().item()), "mean_num_steps": float(s16.stats["num_steps"].float().mean().item()),
                                   "e2e_bitwise_equal_device_path": bool(np.array_equal(hs16.value, s16.value.cpu().numpy())),
-                                  "note": "same curves, data stored as uint16 counts (8192 + 16384 d); NOT the headline configuration (fp32 data)"}
+                                  "note": "same curves, data rows stored as float16; NOT the headline configuration (fp32 data)"}
             launches += (K + 2) * ((batch + args.chunk - 1) // args.chunk) + K + 2
             del h16, dv16, d16
 

@@ -10,6 +10,7 @@
 namespace b200opt {
 
 static thread_local char g_err[512] = "";
+thread_local unsigned long long* g_queue_scratch = nullptr;  // see QueueCounter (common.cuh)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -176,6 +177,8 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   std::vector<bool> out_pinned(outs.size());
   size_t dev_need = 0, pin_need = 0;
   for (size_t i = 0; i < ins.size(); ++i) in_off[i] = dev_need, dev_need += align256(ins[i].bytes_per_problem * chunk);
+  const size_t queue_off = dev_need;  // 8 bytes per stream for the ticket counter of the dynamic problem queue
+  dev_need += 256;
   for (size_t i = 0; i < outs.size(); ++i) {
     out_off[i] = dev_need, dev_need += align256(outs[i].bytes_per_problem * chunk);
     out_pinned[i] = is_pinned(outs[i].h);
@@ -237,7 +240,10 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
                         ins[i].bytes_per_problem * nb, cudaMemcpyHostToDevice, hc.st[s]);
     }
     for (size_t i = 0; i < outs.size(); ++i) d_out[i] = base + out_off[i];
-    if (int e = launch(nb, hc.shared, d_in.data(), d_out.data(), hc.st[s])) return e;
+    g_queue_scratch = reinterpret_cast<unsigned long long*>(base + queue_off);
+    const int launch_rc = launch(nb, hc.shared, d_in.data(), d_out.data(), hc.st[s]);
+    g_queue_scratch = nullptr;
+    if (launch_rc) return launch_rc;
     for (size_t i = 0; i < outs.size(); ++i) {
       void* dst = out_pinned[i] ? static_cast<void*>(static_cast<char*>(outs[i].h) + outs[i].bytes_per_problem * off)
                                 : static_cast<void*>(static_cast<char*>(hc.pin[s]) + bounce_off[i]);

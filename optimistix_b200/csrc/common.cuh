@@ -234,11 +234,22 @@ namespace b200opt {
 // Ticket counter of the dynamic problem queue (next_problem_warp): allocated, zeroed and freed in stream order on the caller's
 // stream - nothing persists between calls and nothing is shared between launches.  If the stream-ordered allocator is not
 // available the kernels run their static schedule (ptr stays NULL).
+// The chunked host pipeline (capi.cu) launches on four streams; a block freed in stream order on one stream cannot be handed to
+// another without a dependency, so per-chunk cudaMallocAsync serialised the pipeline (measured: e2e 28 ms instead of 21 ms per
+// 1 Mi fits).  The pipeline therefore lends each launch 8 bytes of its own per-stream staging slab through this thread-local.
+extern thread_local unsigned long long* g_queue_scratch;
 struct QueueCounter {
   unsigned long long* ptr = nullptr;
   cudaStream_t stream = nullptr;
+  bool owned = false;
   void acquire(cudaStream_t s) {
     stream = s;
+    if (g_queue_scratch != nullptr) {  // caller-owned scratch: zero it in stream order, nothing to free
+      if (cudaMemsetAsync(g_queue_scratch, 0, sizeof(unsigned long long), s) == cudaSuccess) ptr = g_queue_scratch;
+      else cudaGetLastError();
+      return;
+    }
+    owned = true;
     void* q = nullptr;
     if (cudaMallocAsync(&q, sizeof(unsigned long long), s) != cudaSuccess) {
       cudaGetLastError();
@@ -252,7 +263,7 @@ struct QueueCounter {
     ptr = static_cast<unsigned long long*>(q);
   }
   ~QueueCounter() {
-    if (ptr) cudaFreeAsync(ptr, stream);
+    if (ptr && owned) cudaFreeAsync(ptr, stream);
   }
 };
 
