@@ -29,7 +29,7 @@ static int min_launch(int64_t batch, int n, const void* y0, const b200opt_option
   const int grid = (int)(batch < cap ? batch : cap);
   QueueCounter qc;
   p.queue = nullptr;
-  if (batch > cap) {  // dynamic problem queue after the first resident wave (common.cuh)
+  if (batch > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh)
     qc.acquire(stream);
     p.queue = qc.ptr;
   }

@@ -211,7 +211,7 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
     p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
     QueueCounter qc;
     p.queue = nullptr;
-    if (need > cap) {
+    if (need > 4 * cap) {
       qc.acquire(a.stream);
       p.queue = qc.ptr;
     }

@@ -19,7 +19,7 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   QueueCounter qc;
   LsqParams<float> pq = p;
   pq.queue = nullptr;
-  if (need > cap) {  // dynamic problem queue after the first resident wave (common.cuh)
+  if (need > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh); not worth its set-up for a wave or two
     qc.acquire(stream);
     pq.queue = qc.ptr;
   }

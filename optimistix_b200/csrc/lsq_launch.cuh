@@ -36,7 +36,8 @@ template <class Model, typename T, bool TRUST, bool QRMODE = false> int lsq_laun
   QueueCounter qc;
   LsqParams<T> pq = p;
   pq.queue = nullptr;
-  if (need > cap) {  // more problems than resident warps: later problems are handed out dynamically
+  if (need > 4 * cap) {  // several waves of problems: later ones are handed out dynamically (a launch of a wave or two runs
+                         // ~0.1 ms: the stream-ordered counter allocation would cost more than the balance gains)
     qc.acquire(stream);
     pq.queue = qc.ptr;
   }
