@@ -27,12 +27,14 @@ static b200opt_options_t options(double rtol, double atol, int32_t norm, int32_t
 
 // ---- optx.least_squares(registered family, LevenbergMarquardt | GaussNewton): one persistent kernel for the batch
 static ffi::Error LeastSquaresImpl(cudaStream_t stream, int32_t solver, int32_t model_id, double rtol, double atol, int32_t norm,
-                                   int32_t max_steps, ffi::AnyBuffer y0 /*[B,n]*/, ffi::AnyBuffer shared /*[m]*/,
+                                   int32_t max_steps, int32_t linear_solver /*B200OPT_LINSOLVE_*: the solver's linear_solver= field*/,
+                                   int32_t data_dtype /*B200OPT_DATA_*: 16-bit data rows*/, ffi::AnyBuffer y0 /*[B,n]*/, ffi::AnyBuffer shared /*[m]*/,
                                    ffi::AnyBuffer prob /*[B,m]*/, ffi::Result<ffi::AnyBuffer> y /*[B,n]*/,
                                    ffi::Result<ffi::Buffer<ffi::S32>> num_steps, ffi::Result<ffi::Buffer<ffi::S32>> result) {
   const int64_t B = y0.dimensions()[0];
   const int32_t n = (int32_t)y0.dimensions()[1], m = (int32_t)prob.dimensions()[1];
-  const b200opt_options_t o = options(rtol, atol, norm, max_steps);
+  b200opt_options_t o = options(rtol, atol, norm, max_steps);
+  o.linear_solver = linear_solver, o.data_dtype = data_dtype;
   return status(b200opt_least_squares(solver, model_id, dtype_of(y0.element_type()), B, n, m, y0.untyped_data(), shared.untyped_data(),
                                       prob.untyped_data(), m, &o, y->untyped_data(), num_steps->typed_data(), result->typed_data(),
                                       nullptr, nullptr, stream));
@@ -46,6 +48,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(B200optLeastSquares, LeastSquaresImpl,
                                   .Attr<double>("atol")
                                   .Attr<int32_t>("norm")
                                   .Attr<int32_t>("max_steps")
+                                  .Attr<int32_t>("linear_solver")
+                                  .Attr<int32_t>("data_dtype")
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::AnyBuffer>()

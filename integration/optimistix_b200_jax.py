@@ -29,4 +29,8 @@ def least_squares_registered(model_id, solver, y0, shared, prob, *, max_steps=25
     out = (jax.ShapeDtypeStruct((B, n), y0.dtype), jax.ShapeDtypeStruct((B,), jnp.int32), jax.ShapeDtypeStruct((B,), jnp.int32))
     return jax.ffi.ffi_call("b200opt_least_squares", out, vmap_method="broadcast_all")(
         y0, shared, prob, solver=SOLVER_GN if gauss_newton else SOLVER_LM, model_id=model_id, rtol=float(solver.rtol),
-        atol=float(solver.atol), norm=NORM_MAX, max_steps=int(max_steps))
+        atol=float(solver.atol), norm=NORM_MAX, max_steps=int(max_steps),
+        # the solver's `linear_solver=` field: lx.QR() (the reference's default for LevenbergMarquardt) -> B200OPT_LINSOLVE_QR = 1,
+        # the normal equations of the north_star -> 0; 16-bit data rows are handed over as they are (B200OPT_DATA_F16/U16/I16)
+        linear_solver=1 if type(solver.descent.linear_solver).__name__ == "QR" and getattr(solver, "b200_reference_linear_algebra", False) else 0,
+        data_dtype={"float16": 1, "uint16": 2, "int16": 3}.get(str(prob.dtype), 0))
