@@ -229,7 +229,8 @@ int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t
 
 /* ---- generic per-iteration step, root finding (Newton / Chord) for an arbitrary user `fn` -------------------
  * One call = one _AbstractNewtonChord.step + terminate (optimistix/_solver/newton_chord.py:103-196) for every
- * still-running problem; n <= 32.  f_eval [batch][n] = fn(y), J_eval [batch][n][n] = d fn / d y (row-major) at the
+ * still-running problem; n <= 32: one warp per problem, row-per-lane LU; 32 < n <= 160 (fp64) / 224 (fp32): one CTA per problem,
+ * the Jacobian in shared memory.  f_eval [batch][n] = fn(y), J_eval [batch][n][n] = d fn / d y (row-major) at the
  * CURRENT y for Newton; for Chord the caller passes the Jacobian at y0 on every call (newton_chord.py:80-87).
  * lower / upper: optional [n] clip bounds.  y [batch][n] is updated in place.  `state`: opaque carry of
  * b200opt_root_step_state_size bytes per problem.  opts: rtol, atol, norm, max_steps, cauchy_termination, kappa. */
@@ -242,7 +243,7 @@ int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f
 int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result,
                                  void* stream);
 
-/* ---- batched dense solve A x = b (n <= 32), LU with partial pivoting, one warp per system ----------------------
+/* ---- batched dense solve A x = b, LU with partial pivoting: n <= 32 one warp per system, n <= 160 (fp64) / 224 (fp32) one CTA ---
  * The linear solve of ImplicitAdjoint (optimistix/_ad.py:83-118: tangents / cotangents of a solution are
  * -(d rewrite / d y)^-1 d rewrite / d args).  A [batch][n][n] row-major, b and x [batch][n]; status (optional)
  * [batch]: successful, or singular when the solution is not finite. */

@@ -35,8 +35,9 @@ def lu_solve(A, b):
     t = _torch()
     lib = _lib.load()
     B, n = b.shape
-    if n > 32:
-        raise NotImplementedError("ImplicitAdjoint: the batched LU solve kernel supports n <= 32 unknowns")
+    nmax = 160 if b.dtype == t.float64 else 224
+    if n > nmax:
+        raise NotImplementedError(f"ImplicitAdjoint: the batched LU solve kernels support n <= {nmax} unknowns in this dtype")
     A = A.contiguous()
     b = b.contiguous()
     x = t.empty_like(b)

@@ -265,8 +265,10 @@ class RootSession(_Session):
         self._common(solver, y0, args, args_in_dims, max_steps)
         t, lib = self.t, self.lib
         n, dev = self.n, self.dev
-        if n > 32:
-            raise NotImplementedError("generic Newton/Chord step kernel supports n <= 32 unknowns (row-per-lane LU)")
+        nmax = 160 if self.dtype_code == _lib.F64 else 224
+        if n > nmax:
+            raise NotImplementedError(f"generic Newton/Chord step kernels support n <= {nmax} unknowns in this dtype (n <= 32: one warp per "
+                                      "problem, row-per-lane LU; above: one CTA per problem, the Jacobian in shared memory)")
         self.empty = self.B == 0
         if self.empty:
             return

@@ -119,6 +119,202 @@ template <typename T, int N> __global__ void __launch_bounds__(kRootStepWarps * 
   }
 }
 
+// ---- n > 32: one CTA per problem, the Jacobian in shared memory -----------------------------------------------------------
+// LU with partial pivoting (first maximal entry, multiplication by the pivot's reciprocal: the arithmetic of the in-warp
+// kernels and of getf2) with the forward substitution fused into the elimination, then a column-oriented back substitution.
+// Three block barriers per column: the generic path is host-latency bound anyway (torch evaluates f and J every step).
+constexpr int kBigRootThreads = 256;
+__host__ __device__ inline int big_root_ld(int n) { return n | 1; }  // odd pitch: conflict-free column access
+template <typename T> __host__ __device__ inline size_t big_root_smem(int n) {
+  return sizeof(T) * ((size_t)n * big_root_ld(n) + 2 * (size_t)n + 2 * (kBigRootThreads / 32) + 8);
+}
+// block-wide NaN-propagating max / sum of one value per thread (all threads get the result)
+template <typename T> __device__ __forceinline__ T block_combine(T v, bool is_max, T* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = is_max ? warp_nanmax(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  T r = red[0];
+  for (int i = 1; i < kBigRootThreads / 32; ++i) r = is_max ? nan_max(r, red[i]) : r + red[i];
+  return r;
+}
+// A x = b in shared memory (A [n][ld] overwritten by its factors, b overwritten by the solution)
+template <typename T> __device__ void cta_lu_solve(T* A, int ld, T* b, int n, T* red, int* ired) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int k = 0; k < n; ++k) {
+    // pivot: first maximal |A[i][k]|, i >= k
+    T best = T(-1);
+    int bi = n;
+    for (int i = k + tid; i < n; i += kBigRootThreads) {
+      const T v = t_abs(A[i * ld + k]);
+      if (v > best || (v != v && best == best)) best = v, bi = i;  // strided scan: indices increase, so > keeps the first; NaN wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(kFull, best, o);
+      const int oi = __shfl_xor_sync(kFull, bi, o);
+      const bool take = (ov != ov && best == best) || (!(best != best) && (ov > best || (ov == best && oi < bi)));
+      if (take) best = ov, bi = oi;
+    }
+    if (lane == 0) red[w] = best, ired[w] = bi;
+    __syncthreads();
+    best = red[0];
+    bi = ired[0];
+    for (int i = 1; i < kBigRootThreads / 32; ++i) {
+      const T ov = red[i];
+      const int oi = ired[i];
+      const bool take = (ov != ov && best == best) || (!(best != best) && (ov > best || (ov == best && oi < bi)));
+      if (take) best = ov, bi = oi;
+    }
+    const int pr = bi < n ? bi : k;
+    __syncthreads();
+    if (pr != k) {  // swap rows k and pr (and the right-hand side)
+      for (int j = tid; j < n; j += kBigRootThreads) {
+        const T t = A[k * ld + j];
+        A[k * ld + j] = A[pr * ld + j];
+        A[pr * ld + j] = t;
+      }
+      if (tid == 0) {
+        const T t = b[k];
+        b[k] = b[pr];
+        b[pr] = t;
+      }
+      __syncthreads();
+    }
+    const T rinv = T(1) / A[k * ld + k];
+    const T bk = b[k];
+    // multipliers and trailing update, row by row: thread t takes rows k + 1 + t, ...
+    for (int i = k + 1 + w; i < n; i += kBigRootThreads / 32) {
+      const T l = A[i * ld + k] * rinv;
+      for (int j = k + 1 + lane; j < n; j += 32) A[i * ld + j] -= l * A[k * ld + j];
+      if (lane == 0) {
+        A[i * ld + k] = l;
+        b[i] -= l * bk;
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    if (tid == 0) b[k] = b[k] / A[k * ld + k];
+    __syncthreads();
+    const T xk = b[k];
+    for (int i = tid; i < k; i += kBigRootThreads) b[i] -= A[i * ld + k] * xk;
+    __syncthreads();
+  }
+}
+
+template <typename T> __global__ void __launch_bounds__(kBigRootThreads) root_step_big_kernel(const RootStepParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = p.n, ld = big_root_ld(n), tid = threadIdx.x;
+  T* A = reinterpret_cast<T*>(smem_raw);
+  T* b = A + (size_t)n * ld;
+  T* yv = b + n;
+  T* red = yv + n;
+  int* ired = reinterpret_cast<int*>(red + kBigRootThreads / 32);
+  const int64_t prob = blockIdx.x;
+  T* st = p.state + prob * kRootStateElems;
+  int result = p.result[prob];
+  int steps = p.num_steps[prob];
+  bool terminate = st[2] != T(0);
+  if (terminate || result != RES_OK || steps >= p.max_steps) return;  // frozen (block-uniform)
+  const T rtol = p.rtol, atol = p.atol;
+  T small_tol = T(1);
+  for (int i = 0; i < Num<T>::precision - 2; ++i) small_tol *= T(0.1);
+  bool fin = true;
+  for (int i = tid; i < n; i += kBigRootThreads) {
+    yv[i] = p.y[prob * n + i];
+    b[i] = p.f_eval[prob * n + i];
+    fin = fin && t_finite(yv[i]);
+  }
+  for (int e = tid; e < n * n; e += kBigRootThreads) A[(e / n) * ld + e % n] = p.J_eval[prob * (int64_t)n * n + e];
+  const bool y_old_finite = __syncthreads_and(fin ? 1 : 0) != 0;
+  // the pre-step f is needed by the Cauchy test after b has become the solution
+  T fnacc = T(0);
+  if (p.cauchy)
+    for (int i = tid; i < n; i += kBigRootThreads) {
+      const T q = t_abs(b[i]) / atol;
+      fnacc = (p.norm == B200OPT_NORM_MAX) ? nan_max(fnacc, q) : fnacc + q * q;
+    }
+  cta_lu_solve<T>(A, ld, b, n, red, ired);
+  bool solfin = true;
+  T dsacc = T(0), ynacc = T(0);
+  for (int i = tid; i < n; i += kBigRootThreads) {
+    const T sol = b[i], y = yv[i];
+    solfin = solfin && t_finite(sol);
+    T new_y = y - sol, d = sol;
+    if (p.lower != nullptr || p.upper != nullptr) {
+      const T lo = p.lower ? p.lower[i] : -Num<T>::inf(), hi = p.upper ? p.upper[i] : Num<T>::inf();
+      new_y = new_y < lo ? lo : new_y;
+      new_y = new_y > hi ? hi : new_y;
+      d = y - new_y;
+    }
+    const T q = t_abs(d / (atol + rtol * t_abs(new_y)));
+    dsacc = (p.norm == B200OPT_NORM_MAX) ? nan_max(dsacc, q) : dsacc + q * q;
+    const T qy = t_abs(d) / (atol + rtol * t_abs(y));
+    ynacc = (p.norm == B200OPT_NORM_MAX) ? nan_max(ynacc, qy) : ynacc + qy * qy;
+    p.y[prob * n + i] = new_y;
+  }
+  const int lin_result = __syncthreads_and(solfin ? 1 : 0) ? RES_OK : RES_SINGULAR;
+  const bool is_max = p.norm == B200OPT_NORM_MAX;
+  auto finish = [&](T v) { return is_max ? v : (p.norm == B200OPT_NORM_TWO ? t_sqrt(v) : t_sqrt(v / T(n))); };
+  const T diffsize = finish(block_combine(dsacc, is_max, red));
+  const T diffsize_prev = st[0];
+  const int nstep = (int)st[1] + 1;
+  int term_result = RES_OK;
+  if (p.cauchy) {
+    const T yn = finish(block_combine(ynacc, is_max, red));
+    const T fn = finish(block_combine(fnacc, is_max, red));
+    terminate = (yn < T(1)) && (fn < T(1));
+  } else {
+    const bool at_least_two = nstep >= 2;
+    const T rate = diffsize / diffsize_prev;
+    const T factor = diffsize * rate / (T(1) - rate);
+    const bool small = diffsize < small_tol;
+    const bool diverged = !t_finite(rate) || rate > T(2);
+    const bool converged = factor > T(0) && factor < p.kappa;
+    terminate = at_least_two && (small || diverged || converged);
+    if (at_least_two && !small && diverged) term_result = RES_DIVERGED;
+  }
+  const bool fail = lin_result != RES_OK;
+  result = fail ? lin_result : term_result;
+  terminate = terminate || fail;
+  if (!y_old_finite) result = RES_NONFINITE;
+  ++steps;
+  __syncthreads();  // every thread has read the state before it is rewritten
+  if (tid == 0) {
+    st[0] = diffsize;
+    st[1] = (T)nstep;
+    st[2] = terminate ? T(1) : T(0);
+    p.num_steps[prob] = steps;
+    p.result[prob] = result;
+    if (p.active_count && !terminate && result == RES_OK && steps < p.max_steps) atomicAdd(p.active_count, 1);
+  }
+}
+
+template <typename T> __global__ void __launch_bounds__(kBigRootThreads) lu_solve_big_kernel(const T* Ain, const T* bin, T* x, int32_t* status, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ld = big_root_ld(n), tid = threadIdx.x;
+  T* A = reinterpret_cast<T*>(smem_raw);
+  T* b = A + (size_t)n * ld;
+  T* red = b + 2 * n;
+  int* ired = reinterpret_cast<int*>(red + kBigRootThreads / 32);
+  const int64_t prob = blockIdx.x;
+  for (int i = tid; i < n; i += kBigRootThreads) b[i] = bin[prob * n + i];
+  for (int e = tid; e < n * n; e += kBigRootThreads) A[(e / n) * ld + e % n] = Ain[prob * (int64_t)n * n + e];
+  __syncthreads();
+  cta_lu_solve<T>(A, ld, b, n, red, ired);
+  bool fin = true;
+  for (int i = tid; i < n; i += kBigRootThreads) {
+    x[prob * n + i] = b[i];
+    fin = fin && t_finite(b[i]);
+  }
+  const int ok = __syncthreads_and(fin ? 1 : 0);
+  if (tid == 0 && status) status[prob] = ok ? RES_OK : RES_SINGULAR;
+}
+
+template <typename T> static int big_root_nmax() { return sizeof(T) == 8 ? 160 : 224; }  // n (n | 1) + 2 n elements within 227 KB
+
 template <typename T> __global__ void root_step_init_kernel(int64_t batch, int n, const T* y0, T* y, T* state, int32_t* num_steps,
                                                             int32_t* result) {
   const int64_t prob = blockIdx.x;
@@ -446,6 +642,13 @@ static int root_step_typed(int64_t batch, int n, const void* f, const void* J, c
   p.max_steps = o->max_steps;
   p.cauchy = o->cauchy_termination;
   if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
+  if (n > 32) {  // one CTA per problem, Jacobian in shared memory
+    const size_t smem = big_root_smem<T>(n);
+    static LaunchCache cache;
+    if (cache.configure(root_step_big_kernel<T>, kBigRootThreads, smem) < 0) return B200OPT_ECUDA;
+    root_step_big_kernel<T><<<(unsigned)batch, kBigRootThreads, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "root_step_big_kernel launch");
+  }
   const unsigned grid = (unsigned)((batch + kRootStepWarps - 1) / kRootStepWarps);
   if (n <= 8) root_step_kernel<T, 8><<<grid, kRootStepWarps * 32, 0, st>>>(p);
   else if (n <= 16) root_step_kernel<T, 16><<<grid, kRootStepWarps * 32, 0, st>>>(p);
@@ -508,13 +711,13 @@ constexpr int kBfgsStepNMax = 1024;  // 4 n elements of shared memory per CTA, n
 extern "C" {
 
 int64_t b200opt_root_step_state_size(int32_t dtype, int32_t n) {
-  if (gstep_check("root_step_state_size", dtype, 0, n, 32)) return -1;
+  if (gstep_check("root_step_state_size", dtype, 0, n, dtype == B200OPT_F64 ? 160 : 224)) return -1;
   return (int64_t)kRootStateElems * (dtype == B200OPT_F32 ? 4 : 8);
 }
 
 int32_t b200opt_root_step_init(int32_t dtype, int64_t batch, int32_t n, const void* y0, void* y, void* state, int32_t* num_steps,
                                int32_t* result, void* stream) {
-  if (int e = gstep_check("root_step_init", dtype, batch, n, 32)) return e;
+  if (int e = gstep_check("root_step_init", dtype, batch, n, dtype == B200OPT_F64 ? 160 : 224)) return e;
   if (batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200OPT_F64)
@@ -529,7 +732,7 @@ int32_t b200opt_root_step_init(int32_t dtype, int64_t batch, int32_t n, const vo
 int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f_eval, const void* J_eval, const void* lower,
                           const void* upper, void* y, void* state, const b200opt_options_t* opts, int32_t* num_steps,
                           int32_t* result, int32_t* active_count, void* stream) {
-  if (int e = gstep_check("root_step", dtype, batch, n, 32)) return e;
+  if (int e = gstep_check("root_step", dtype, batch, n, dtype == B200OPT_F64 ? 160 : 224)) return e;
   if (int e = opts_check("root_step", opts)) return e;
   if (batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -539,7 +742,7 @@ int32_t b200opt_root_step(int32_t dtype, int64_t batch, int32_t n, const void* f
 }
 
 int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const void* state, int32_t* result, void* stream) {
-  if (int e = gstep_check("root_step_finish", dtype, batch, n, 32)) return e;
+  if (int e = gstep_check("root_step_finish", dtype, batch, n, dtype == B200OPT_F64 ? 160 : 224)) return e;
   if (batch == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((batch + 127) / 128);
@@ -551,13 +754,29 @@ int32_t b200opt_root_step_finish(int32_t dtype, int64_t batch, int32_t n, const 
 }
 
 int32_t b200opt_lu_solve(int32_t dtype, int64_t batch, int32_t n, const void* A, const void* b, void* x, int32_t* status, void* stream) {
-  if (int e = gstep_check("lu_solve", dtype, batch, n, 32)) return e;
+  if (int e = gstep_check("lu_solve", dtype, batch, n, dtype == B200OPT_F64 ? 160 : 224)) return e;
   if (batch == 0) return 0;
   if (!A || !b || !x) {
     set_error("lu_solve: NULL buffer");
     return B200OPT_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n > 32) {  // one CTA per system, matrix in shared memory
+    if (dtype == B200OPT_F64) {
+      static LaunchCache cache;
+      const size_t smem = big_root_smem<double>(n);
+      if (cache.configure(lu_solve_big_kernel<double>, kBigRootThreads, smem) < 0) return B200OPT_ECUDA;
+      lu_solve_big_kernel<double><<<(unsigned)batch, kBigRootThreads, smem, st>>>(static_cast<const double*>(A), static_cast<const double*>(b),
+                                                                                  static_cast<double*>(x), status, n);
+    } else {
+      static LaunchCache cache;
+      const size_t smem = big_root_smem<float>(n);
+      if (cache.configure(lu_solve_big_kernel<float>, kBigRootThreads, smem) < 0) return B200OPT_ECUDA;
+      lu_solve_big_kernel<float><<<(unsigned)batch, kBigRootThreads, smem, st>>>(static_cast<const float*>(A), static_cast<const float*>(b),
+                                                                                 static_cast<float*>(x), status, n);
+    }
+    return check_cuda(cudaGetLastError(), "lu_solve_big_kernel launch");
+  }
   const unsigned grid = (unsigned)((batch + kRootStepWarps - 1) / kRootStepWarps);
   const int threads = kRootStepWarps * 32;
 #define B200OPT_LU_LAUNCH(T, N) lu_solve_kernel<T, N><<<grid, threads, 0, st>>>(static_cast<const T*>(A), static_cast<const T*>(b), static_cast<T*>(x), status, batch, n)

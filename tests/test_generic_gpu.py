@@ -317,7 +317,7 @@ def test_generic_empty_batch():
 
 def test_generic_limits_are_reported():
     with pytest.raises(NotImplementedError):
-        optx.root_find(lambda y, _: y, optx.Newton(1e-8, 1e-8), torch.zeros(33, dtype=torch.float64, device=DEV))
+        optx.root_find(lambda y, _: y, optx.Newton(1e-8, 1e-8), torch.zeros(161, dtype=torch.float64, device=DEV))
     with pytest.raises(NotImplementedError):
         optx.minimise(lambda y, _: (y * y).sum(), optx.BFGS(1e-8, 1e-8, use_inverse=False), torch.zeros(65, dtype=torch.float64, device=DEV))
     with pytest.raises(ValueError):
@@ -393,3 +393,52 @@ def test_generic_lm_step_kernels_agree_across_the_size_boundary():
                              max_steps=1000)
     assert _res_name(s16) == _res_name(s17) == "successful"
     assert torch.allclose(s17.value[:16], s16.value, rtol=1e-6, atol=1e-8) and abs(float(s17.value[16]) - 2.0) < 1e-8
+
+
+# ---- Newton / Chord beyond n = 32: one CTA per problem, the Jacobian in shared memory (the reference has no size limit,
+# _solver/newton_chord.py:103-152) -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dtype", [(33, torch.float64), (64, torch.float64), (100, torch.float64), (160, torch.float64), (48, torch.float32)])
+def test_newton_chord_large_n_vs_oracle(n, dtype):
+    """Implicit-Euler steps of a stiff quadratic ODE with n unknowns through the generic step kernel against the oracle: the LU
+    with partial pivoting is the oracle's (first maximal pivot), so iteration counts and result codes are identical and the
+    roots agree to rounding."""
+    B = 24
+    w = synthetic.implicit_euler_batch(B, n=n, seed=7)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    tol = 1e-8 if dtype == torch.float64 else 1e-4
+    A, Bm = torch.as_tensor(w["A"].astype(npdt), device=DEV), torch.as_tensor(w["B"].astype(npdt), device=DEV)
+    yp, dt = torch.as_tensor(w["y_prev"].astype(npdt), device=DEV), torch.as_tensor(w["dt"].astype(npdt), device=DEV)
+
+    def F_(y, a):
+        return y - a["y_prev"] - a["dt"] * (A @ y + y * (Bm @ y))
+
+    args, in_dims = {"y_prev": yp, "dt": dt}, {"y_prev": 0, "dt": 0}
+    oargs = dict(A=w["A"].astype(npdt), B=w["B"].astype(npdt), y_prev=w["y_prev"].astype(npdt), dt=w["dt"].astype(npdt))
+    for chord in (False, True):
+        solver = (optx.Chord if chord else optx.Newton)(tol, tol)
+        sol = optx.root_find(F_, solver, yp.clone(), args, args_in_dims=in_dims, throw=False)
+        ref = S.newton_chord(M.implicit_euler, w["y_prev"].astype(npdt), oargs, rtol=tol, atol=tol, chord=chord)
+        assert (to_np(sol.result) == ref["result"]).all()
+        if dtype == torch.float64:
+            assert (to_np(sol.stats["num_steps"]) == ref["num_steps"]).all()
+            assert np.allclose(to_np(sol.value), ref["value"], rtol=1e-9, atol=1e-12)
+        else:
+            assert np.abs(to_np(sol.stats["num_steps"]) - ref["num_steps"]).max() <= 1
+            assert np.allclose(to_np(sol.value), ref["value"], rtol=2e-4, atol=2e-5)
+        assert (to_np(sol.result) == optx.RESULTS.successful).all()
+
+
+def test_lu_solve_large_n_and_adjoint():
+    """b200opt_lu_solve for 32 < n (the linear solve of ImplicitAdjoint): against torch.linalg.solve, singular systems flagged."""
+    from optimistix_b200._adjoint import lu_solve
+
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    for n in (40, 96, 160):
+        Amat = torch.randn(7, n, n, dtype=torch.float64, device=DEV, generator=gen) + n ** 0.5 * torch.eye(n, dtype=torch.float64, device=DEV)
+        bvec = torch.randn(7, n, dtype=torch.float64, device=DEV, generator=gen)
+        x, status = lu_solve(Amat, bvec)
+        assert (status == 0).all()
+        assert torch.allclose(x, torch.linalg.solve(Amat, bvec), rtol=1e-9, atol=1e-11)
+    Amat[3] = 0.0
+    x, status = lu_solve(Amat, bvec)
+    assert int(status[3]) == optx.RESULTS.singular and (status[[0, 1, 2, 4, 5, 6]] == 0).all()
