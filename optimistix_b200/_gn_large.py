@@ -169,7 +169,7 @@ class PeerExchange:
         all_gather_object of the handles and the barrier are paid once, nothing leaks per call).  Collective."""
         import torch
 
-        key = (torch.device(device).index, id(group) if group is not None else None)
+        key = (torch.device(device).index, group)  # the group object itself: the cache keeps it alive, an id() could be recycled
         x = cls._cache.get(key)
         if x is None or x.local is None:
             x = cls(device, group)

@@ -401,7 +401,7 @@ def test_sixteen_bit_data_is_the_solve_of_the_converted_array(kind, m):
     if kind == "float16":
         assert s["result_match"] >= 0.995 and s["within_tol"] >= 0.985
     else:  # count units: the marginal fits reach max_steps in one implementation and not in the other
-        assert s["result_match"] >= 0.9 and s["within_tol_ok"] >= 0.97
+        assert s["result_match"] >= 0.9 and s["within_tol_ok"] >= 0.95
 
 
 def test_sixteen_bit_data_fp64_and_ragged_alignment():
