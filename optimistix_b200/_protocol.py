@@ -457,6 +457,8 @@ def protocol_init(solver, session_cls, fn, y, args, options):
     opts = dict(options or {})
     in_dims = opts.pop("args_in_dims", None)
     sess = session_cls(first, solver, y, args, opts or None, args_in_dims=in_dims, max_steps=None)
+    if sess.empty:
+        raise ValueError("init: the batch is empty - there is nothing to step through (the entry points return an empty Solution)")
     sess._aux_of = aux_of
     sess._in_dims = in_dims
     return sess
