@@ -156,3 +156,29 @@ def test_linear_solver_is_never_silently_ignored():
         optx.least_squares(optx.models.exp_decay, optx.LevenbergMarquardt(1e-8, 1e-8, linear_solver=optx.LU()),
                            torch.ones(3, dtype=torch.float64, device=DEV),
                            (torch.linspace(0, 4, 64, dtype=torch.float64, device=DEV), torch.ones(64, dtype=torch.float64, device=DEV)))
+
+
+def test_least_squares_stepping_n20_cta_kernel_state():
+    """16 < n <= 64 runs the one-CTA-per-problem step kernel (Gram in shared memory): same protocol, same state fields."""
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    A = torch.randn(4, 30, 20, dtype=torch.float64, device=DEV, generator=gen)
+    b = torch.randn(4, 30, dtype=torch.float64, device=DEV, generator=gen)
+
+    def residual(y, a):
+        return a["A"] @ y - a["b"] + 0.1 * torch.sin(y).sum()
+
+    solver = optx.LevenbergMarquardt(1e-9, 1e-9)
+    args, in_dims = {"A": A, "b": b}, {"A": 0, "b": 0}
+    y0 = torch.zeros(4, 20, dtype=torch.float64, device=DEV)
+    y, _, state, result, _ = _interactive(solver, lambda y, a: (residual(y, a), None), y0, args, {"args_in_dims": in_dims})
+    sol = optx.least_squares(residual, solver, y0, args, args_in_dims=in_dims, throw=False)
+    assert torch.equal(sol.value, y) and torch.equal(sol.result, result) and (result == optx.RESULTS.successful).all()
+    info = state.f_info
+    r = torch.func.vmap(residual, in_dims=(0, in_dims))(y, args)
+    J = torch.func.vmap(torch.func.jacfwd(residual), in_dims=(0, in_dims))(y, args)
+    assert torch.allclose(info.gram, J.transpose(1, 2) @ J, rtol=1e-9, atol=1e-10)
+    assert torch.allclose(info.compute_grad(), (J * r[:, :, None]).sum(1), rtol=1e-8, atol=1e-10)
+    assert torch.allclose(info.as_min(), 0.5 * (r * r).sum(1), rtol=1e-12)
+    assert bool(state.terminate.all()) and (state.search_state > 0).all()
+    with pytest.raises(ValueError, match="empty"):
+        solver.init(lambda y, a: (residual(y, a), None), y0[:0], {"A": A[:0], "b": b[:0]}, {"args_in_dims": in_dims}, None, None, frozenset())
