@@ -272,8 +272,11 @@ int32_t b200opt_bfgs_step_finish(int32_t dtype, int64_t batch, int32_t n, const 
                                  void* stream);
 
 /* ---- large row-sharded Gauss-Newton Gram on tcgen05 tensor cores (TF32 in, FP32 accumulate in TMEM) ----
- * J [m_local][n] row-major fp32 (n == 256 in this build), r [m_local] fp32.
- * out [n*n + n + 1] fp32: G = J^T J (row-major, full symmetric), then g = J^T r, then r^T r.
+ * J [m_local][n] row-major fp32 with 4 <= n <= 256, n % 4 == 0; r [m_local] fp32.  The kernels work on J padded with zero
+ * columns to N = 256 (the padding is never read from memory: whole 32-column groups beyond n are zeroed once in shared memory, a
+ * partial group is zero-filled by the TMA): every n-indexed vector of this family (y, p, the state) has 256 entries, the ones
+ * beyond n are zero, and `out` keeps the 256-wide layout below with a unit diagonal for the padded unknowns.
+ * out [N*N + N + 1] fp32: G = J^T J (row-major, full symmetric), then g = J^T r, then r^T r.
  * The caller all-reduces `out` across ranks (NCCL sum) and calls b200opt_gn_solve. `workspace` must hold
  * b200opt_gn_gram_workspace_size(n) bytes. */
 int64_t b200opt_gn_gram_workspace_size(int32_t n);

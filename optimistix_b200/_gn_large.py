@@ -50,13 +50,13 @@ class CudaOps:
 
     def residual(self, J, y, d, r_out, r_old, rtol, atol, fmax):
         fmax.zero_()
-        _lib.check(self.lib.b200opt_linear_residual(J.data_ptr(), y.data_ptr(), d.data_ptr(), J.shape[0], N, r_out.data_ptr(),
+        _lib.check(self.lib.b200opt_linear_residual(J.data_ptr(), y.data_ptr(), d.data_ptr(), J.shape[0], J.shape[1], r_out.data_ptr(),
                                                     r_old.data_ptr() if r_old is not None else None, rtol, atol,
                                                     fmax.data_ptr(), self._stream()), "b200opt_linear_residual")
         self.launches += 1
 
     def gram(self, J, r, out):
-        _lib.check(self.lib.b200opt_gn_gram(J.data_ptr(), r.data_ptr(), J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+        _lib.check(self.lib.b200opt_gn_gram(J.data_ptr(), r.data_ptr(), J.shape[0], J.shape[1], out.data_ptr(), self.ws.data_ptr(),
                                             self._stream()), "b200opt_gn_gram")
         self.launches += 2
 
@@ -65,7 +65,7 @@ class CudaOps:
         fmax.zero_()
         _lib.check(self.lib.b200opt_gn_gram_linear(J.data_ptr(), y.data_ptr(), d.data_ptr(),
                                                    r_old.data_ptr() if r_old is not None else None, r_out.data_ptr(),
-                                                   fmax.data_ptr(), rtol, atol, J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+                                                   fmax.data_ptr(), rtol, atol, J.shape[0], J.shape[1], out.data_ptr(), self.ws.data_ptr(),
                                                    self._stream()), "b200opt_gn_gram_linear")
         self.launches += 2
 
@@ -74,7 +74,7 @@ class CudaOps:
         fmax.zero_()
         _lib.check(self.lib.b200opt_gn_gram_linear_xchg(J.data_ptr(), y.data_ptr(), d.data_ptr(),
                                                         r_old.data_ptr() if r_old is not None else None, r_out.data_ptr(),
-                                                        fmax.data_ptr(), rtol, atol, J.shape[0], N, out.data_ptr(), self.ws.data_ptr(),
+                                                        fmax.data_ptr(), rtol, atol, J.shape[0], J.shape[1], out.data_ptr(), self.ws.data_ptr(),
                                                         xchg.bases.data_ptr(), xchg.world, xchg.rank, parity, seq, self._stream()),
                    "b200opt_gn_gram_linear_xchg")
         self.launches += 2
@@ -94,7 +94,7 @@ class CudaOps:
         return self.t.empty(self.lib.b200opt_gn_state_size(), dtype=self.t.uint8, device=self.device)
 
     def state_init(self, state, y0, rtol, atol, max_steps, solver, timeout_ms, r_old0, out):
-        _lib.check(self.lib.b200opt_gn_init(state.data_ptr(), y0.data_ptr(), N, float(rtol), float(atol), int(max_steps), int(solver),
+        _lib.check(self.lib.b200opt_gn_init(state.data_ptr(), y0.data_ptr(), int(y0.shape[0]), float(rtol), float(atol), int(max_steps), int(solver),
                                             int(timeout_ms), r_old0.data_ptr(), r_old0.shape[0], out.data_ptr(), self.ws.data_ptr(),
                                             self._stream()), "b200opt_gn_init")
         self.launches += 2
@@ -102,7 +102,7 @@ class CudaOps:
     def iterate(self, J, d, r0, r1, state, out, xchg, rtol, atol, lam=0.0, fold=False):
         bases = xchg.bases.data_ptr() if xchg is not None else None
         local = xchg.local if xchg is not None else None
-        _lib.check(self.lib.b200opt_gn_iterate(J.data_ptr(), d.data_ptr(), r0.data_ptr(), r1.data_ptr(), J.shape[0], N, state.data_ptr(),
+        _lib.check(self.lib.b200opt_gn_iterate(J.data_ptr(), d.data_ptr(), r0.data_ptr(), r1.data_ptr(), J.shape[0], J.shape[1], state.data_ptr(),
                                                out.data_ptr(), self.ws.data_ptr(), bases, local, xchg.world if xchg is not None else 1,
                                                xchg.rank if xchg is not None else 0, float(rtol), float(atol), float(lam), int(bool(fold)),
                                                self._stream()),
@@ -236,7 +236,7 @@ def _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, check_every, line
     if throw and result != RESULTS.successful:
         raise RuntimeError(f"{RESULTS.name(result)}: {RESULTS[result]}")
     fl = tail_host.view(torch.float32)
-    value = state[: N * 4].view(torch.float32).clone()
+    value = state[: N * 4].view(torch.float32)[: J.shape[1]].clone()  # the state is laid out 256 wide; unknowns beyond n are padding
     stats = {"num_steps": steps, "max_steps": max_steps, "loss": 0.5 * float(fl[6]), "gpu_launches": getattr(ops, "launches", None),
              "iterations_enqueued": enq, "fp64_fallbacks": int(tail_host[10]),
              "exchange": "peer memory (device loop)" if xchg is not None else "single rank (device loop)"}
@@ -270,15 +270,21 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
         if not J.is_cuda:
             raise _lib.B200OptError("the large Gauss-Newton path needs CUDA tensors (there is no CPU fallback)")
         ops = CudaOps(dev)
-    if J.dtype != torch.float32 or J.ndim != 2 or J.shape[1] != N or not J.is_contiguous():
-        raise ValueError(f"J must be a contiguous float32 [m_local, {N}] tensor")
+    n = int(J.shape[1]) if J.ndim == 2 else -1
+    if J.dtype != torch.float32 or J.ndim != 2 or not (4 <= n <= N) or n % 4 or not J.is_contiguous():
+        raise ValueError(f"J must be a contiguous float32 [m_local, n] tensor with 4 <= n <= {N} and n % 4 == 0 (the kernels work on the "
+                         f"matrix padded with zero columns to {N}; the padding is never read from memory)")
     m_local = J.shape[0]
     d = d.to(torch.float32).contiguous()
     y = y0.to(device=dev, dtype=torch.float32).contiguous().clone()
-    if y.shape != (N,):
-        raise ValueError(f"y0 must have shape [{N}]")
+    if y.shape != (n,):
+        raise ValueError(f"y0 must have shape [{n}] (the number of columns of J)")
     rtol, atol = float(solver.rtol), float(solver.atol)
     fused = fused and hasattr(ops, "residual_gram")
+    y_unpadded = y
+    if n < N:  # the step-by-step kernels read y 256 wide; the padding stays exactly zero (unit diagonal, zero gradient)
+        y = torch.zeros(N, dtype=torch.float32, device=dev)
+        y[:n] = y_unpadded
     y_eval = y.clone()
     r_old = torch.zeros(m_local, dtype=torch.float32, device=dev)  # gauss_newton.py:229-230: zero-filled f_info
     r_new = torch.empty_like(r_old)
@@ -305,7 +311,7 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
             xchg = None
     if device_loop and fused and hasattr(ops, "iterate") and (not distributed or xchg is not None):
         with torch.cuda.device(dev):
-            return _device_loop(ops, J, d, y, solver, max_steps, throw, xchg, max(1, int(check_every)), int(linear_solver), int(timeout_ms),
+            return _device_loop(ops, J, d, y_unpadded, solver, max_steps, throw, xchg, max(1, int(check_every)), int(linear_solver), int(timeout_ms),
                                 bool(fold_reduce))
     try:
         gathered = torch.empty(world * OUT_FLOATS, dtype=torch.float32, device=dev) if (distributed and xchg is None) else out
@@ -359,4 +365,4 @@ def gauss_newton_large(J, d, y0, solver, *, max_steps=256, throw=True, group=Non
     stats = {"num_steps": steps, "max_steps": max_steps, "loss": 0.5 * float(summary[0].item()),
              "gpu_launches": getattr(ops, "launches", None),
              "exchange": ("peer memory (host loop)" if xchg is not None else "nccl all-gather (host loop)") if distributed else "single rank (host loop)"}
-    return Solution(value=y, result=result, aux=None, stats=stats, state={"gram": out, "residual": r_old})
+    return Solution(value=y[:n], result=result, aux=None, stats=stats, state={"gram": out, "residual": r_old})

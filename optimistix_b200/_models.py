@@ -81,8 +81,8 @@ gauss2 = RegisteredModel("gauss2", 1, KIND_LSQ, 8, ("x", "d"), 1, _gauss2,
 implicit_euler = RegisteredModel("implicit_euler", 2, KIND_ROOT, 32, ("A", "B", "y_prev", "dt"), 2, _implicit_euler,
                                  "F(y) = y - y_prev - dt*(A y + y*(B y))")
 rosenbrock = RegisteredModel("rosenbrock", 3, KIND_MIN, 0, (), 0, _rosenbrock, "standard chained Rosenbrock")
-linear_rows = RegisteredModel("linear_rows", 4, KIND_LSQ, 256, ("J", "d"), 0, None,
-                              "r = J y - d, J materialised row-major in HBM (single large problem)")
+linear_rows = RegisteredModel("linear_rows", 4, KIND_LSQ, 0, ("J", "d"), 0, None,
+                              "r = J y - d, J [m, n] materialised row-major in HBM, 4 <= n <= 256 (single large problem)")
 
 _REGISTRY = {m.name: m for m in (exp_decay, gauss2, implicit_euler, rosenbrock, linear_rows)}
 

@@ -51,7 +51,7 @@ static const b200opt_model_info_t kModels[MODEL_COUNT] = {
      "F(y) = y - y_prev - dt*(A y + y*(B y)), n = 32", "A[n][n] then B[n][n], row-major", "y_prev[n] then dt"},
     {MODEL_ROSENBROCK, B200OPT_KIND_MINIMISE, 0, 64, 0, 0, "rosenbrock",
      "f(y) = sum_i 100 (y_{i+1} - y_i^2)^2 + (1 - y_i)^2 (standard chained Rosenbrock), 2 <= n <= 64", "none", "none"},
-    {MODEL_LINEAR_ROWS, B200OPT_KIND_LEAST_SQUARES, 256, 256, 0, 0, "linear_rows",
+    {MODEL_LINEAR_ROWS, B200OPT_KIND_LEAST_SQUARES, 0, 256, 0, 0, "linear_rows",
      "r = J y - d with J materialised row-major in HBM (single large problem; b200opt_gn_gram path)", "J[m][n]", "d[m]"},
 };
 

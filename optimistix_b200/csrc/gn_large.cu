@@ -672,13 +672,13 @@ __global__ void __launch_bounds__(1024, 1) gn_step_kernel(const float* local_out
   }
 }
 
-__global__ void gn_init_kernel(GnState* state, const float* y0, float rtol, float atol, int max_steps, int timeout_ms, int solver,
+__global__ void gn_init_kernel(GnState* state, const float* y0, int n, float rtol, float atol, int max_steps, int timeout_ms, int solver,
                                float* fstat_slot, unsigned* sync) {
   __shared__ int fin_s;
   const int tid = threadIdx.x;
   if (tid == 0) fin_s = 1;
   __syncthreads();
-  const float v = y0[tid];
+  const float v = tid < n ? y0[tid] : 0.f;  // unknowns beyond n are padding: zero, and they stay zero
   state->y[tid] = v;
   state->y_eval[tid] = v;
   if (!isfinite(v)) fin_s = 0;
@@ -802,15 +802,15 @@ int64_t b200opt_gn_state_size(void) { return (int64_t)sizeof(GnState); }
 
 int32_t b200opt_gn_init(void* state, const float* y0, int32_t n, double rtol, double atol, int32_t max_steps, int32_t solver,
                         int32_t timeout_ms, float* r_old0, int64_t m_local, float* out, void* workspace, void* stream) {
-  if (!state || !y0 || !out || !workspace || !r_old0 || n != 256 || max_steps < 0 || m_local < 0 || (solver != 0 && solver != 1)) {
-    set_error("gn_init: need n == 256, non-NULL buffers, max_steps >= 0 and solver in {0, 1}");
+  if (!state || !y0 || !out || !workspace || !r_old0 || n < 4 || n > 256 || (n & 3) || max_steps < 0 || m_local < 0 || (solver != 0 && solver != 1)) {
+    set_error("gn_init: need 4 <= n <= 256 with n %% 4 == 0, non-NULL buffers, max_steps >= 0 and solver in {0, 1}");
     return B200OPT_EINVAL;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // gauss_newton.py:229-230: the carry starts from a zero-filled f_info, so the first f-space test compares against zeros
   if (m_local && check_cuda(cudaMemsetAsync(r_old0, 0, sizeof(float) * (size_t)m_local, st), "gn_init memset")) return B200OPT_ECUDA;
   unsigned* sync = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + gn_workspace_sync_offset());
-  gn_init_kernel<<<1, 256, 0, st>>>(static_cast<GnState*>(state), y0, (float)rtol, (float)atol, max_steps, timeout_ms, solver,
+  gn_init_kernel<<<1, 256, 0, st>>>(static_cast<GnState*>(state), y0, n, (float)rtol, (float)atol, max_steps, timeout_ms, solver,
                                     out + 256 * 256 + 256 + 1, sync);
   return check_cuda(cudaGetLastError(), "gn_init_kernel launch");
 }
@@ -818,8 +818,8 @@ int32_t b200opt_gn_init(void* state, const float* y0, int32_t n, double rtol, do
 int32_t b200opt_gn_iterate(const float* J, const float* d, float* r0, float* r1, int64_t m_local, int32_t n, void* state, float* out,
                            void* workspace, const void* const* xchg_bases_dev, void* xchg_local, int32_t world, int32_t rank,
                            double rtol, double atol, double lambda, int32_t fold_reduce, void* stream) {
-  if (!J || !d || !r0 || !r1 || !state || !out || !workspace || n != 256 || m_local < 4) {
-    set_error("gn_iterate: need n == 256, m_local >= 4 and non-NULL buffers");
+  if (!J || !d || !r0 || !r1 || !state || !out || !workspace || n < 4 || n > 256 || (n & 3) || m_local < 4) {
+    set_error("gn_iterate: need 4 <= n <= 256 with n %% 4 == 0, m_local >= 4 and non-NULL buffers");
     return B200OPT_EINVAL;
   }
   if ((xchg_bases_dev != nullptr) != (xchg_local != nullptr) || (xchg_bases_dev && (world < 1 || world > 64 || rank < 0 || rank >= world))) {

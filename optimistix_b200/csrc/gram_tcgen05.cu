@@ -165,6 +165,8 @@ struct Params {
   int64_t m;
   float* ws;           // per-CTA partials: [grid][N*N + N + 1] (+ padding to a multiple of 4 floats)
   int num_tiles;
+  int n_cols;            // columns of J that exist (4 <= n_cols <= 256, a multiple of 4); the kernel works on the matrix padded
+                         // with zero columns to 256: column groups beyond n_cols are zeroed once and never loaded
   // ---- state-driven iteration (b200opt_gn_iterate): y_eval, the residual ping-pong parity and the frozen flag come from
   // the device state; the cross-CTA reduction, the mirror of the triangle and the publication to the peers are folded into
   // this kernel (cooperative launch: the CTAs meet at a grid-wide counter before each reduces its slice of the output).
@@ -217,6 +219,17 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // n < 256: the 32-column groups that lie entirely beyond the last column are never loaded; they are zeroed here, once, in
+  // every stage (a partially filled group is zero-filled by the TMA's out-of-bounds handling)
+  const int live_groups = (p.n_cols + BOX_COLS - 1) / BOX_COLS;
+  if (live_groups < GROUPS) {
+    const int dead_words = (GROUPS - live_groups) * GROUP_BYTES / 16;
+    for (int s = 0; s < STAGES; ++s) {
+      uint4* dead = reinterpret_cast<uint4*>(tiles + (size_t)s * TILE_BYTES + (size_t)live_groups * GROUP_BYTES);
+      for (int i = threadIdx.x; i < dead_words; i += THREADS) dead[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros -> visible to the tensor core's async-proxy reads
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,10 +247,11 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
         const int64_t rows_left = p.m - row0;
         const uint32_t r_bytes = (uint32_t)((rows_left < KROWS ? rows_left : KROWS) * 4);
         const bool with_old = y_ptr != nullptr && r_old_ptr != nullptr;
-        mbar_expect_tx(&full[s], TILE_BYTES + r_bytes * (with_old ? 2u : 1u));  // OOB rows are zero-filled and still counted
+        mbar_expect_tx(&full[s], (uint32_t)live_groups * GROUP_BYTES + r_bytes * (with_old ? 2u : 1u));  // OOB rows / columns are zero-filled and still counted
         unsigned char* dst = tiles + (size_t)s * TILE_BYTES;
 #pragma unroll
-        for (int g = 0; g < GROUPS; ++g) tma_load_2d(dst + g * GROUP_BYTES, &tmap, g * BOX_COLS, (int)row0, &full[s]);
+        for (int g = 0; g < GROUPS; ++g)
+          if (g < live_groups) tma_load_2d(dst + g * GROUP_BYTES, &tmap, g * BOX_COLS, (int)row0, &full[s]);
         bulk_load_1d(rs + s * KROWS, p.r + row0, r_bytes, &full[s]);
         if (with_old) bulk_load_1d(ros + s * KROWS, r_old_ptr + row0, r_bytes, &full[s]);
       }
@@ -467,6 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
             for (int u = 0; u < 16; ++u) sv += v[u];
           }
           for (; c < parts; ++c) sv += __ldcg(w + (size_t)c * WS_STRIDE);
+          if (idx < N * N && idx / N == idx % N && idx / N >= p.n_cols) sv = 1.f;  // padded unknowns: unit diagonal, they stay zero
           p.out[idx] = sv;
         } else {
           sv = __ldcg(p.out + idx);  // the f-statistic (atomicMax target of every CTA; complete after the grid-wide meeting)
@@ -508,7 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant_
 // straight into the slot of this rank in every peer's exchange buffer (P2P stores over NVLink / NVSwitch), and the last CTA to
 // finish raises this rank's flag on every peer.  The collective is therefore part of the reduction kernel; the consumer
 // (gn_solve_kernel) waits on the flags.  No NCCL call, no extra launch, no host involvement.
-__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out, PeerXchg x, const GnState* state) {
+__global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, float* out, PeerXchg x, const GnState* state, int n_cols) {
   if (state && gn_frozen(state)) return;  // state-driven iteration: the solve has ended, nothing was computed, nothing is published
   if (x.bases && x.seq_counter) {
     x.seq = *x.seq_counter + 1u;
@@ -526,6 +541,7 @@ __global__ void gram_reduce_kernel(const float* ws, int parts, int live_parts, f
     const bool is_gram = idx < N * N;
     const int count = is_gram ? live_parts : parts;  // CTAs without tiles never wrote their Gram block
     for (int c = 0; c < count; ++c) s += ws[(size_t)c * WS_STRIDE + src];
+    if (is_gram && idx / N == idx % N && idx / N >= n_cols) s = 1.f;  // padded unknowns (n < 256): unit diagonal, they stay zero
     out[idx] = s;
   } else if (idx == total) {
     s = out[idx];  // the f-statistic slot rides along
@@ -574,7 +590,7 @@ using namespace b200opt;
 extern "C" {
 
 int64_t b200opt_gn_gram_workspace_size(int32_t n) {
-  if (n != gram::N) return -1;
+  if (n < 4 || n > gram::N) return -1;  // the workspace does not depend on n: everything is laid out 256 wide
   // per-CTA partials for up to 256 CTAs + an fp64 n x n scratch for the solve kernel + 4 KiB (grid-wide counters)
   return (int64_t)gn_workspace_sync_offset() + 4096;
 }
@@ -608,7 +624,7 @@ int32_t b200opt_gn_gram_linear(const float* J, const float* y, const float* d, c
 }
 
 int64_t b200opt_xchg_bytes(int32_t world, int32_t n) {
-  if (n != gram::N || world < 1 || world > 64) return -1;
+  if (n < 4 || n > gram::N || world < 1 || world > 64) return -1;
   return (int64_t)gram::xchg_bytes(world);
 }
 
@@ -686,8 +702,8 @@ int32_t gn_iterate_gram(const float* J, const float* d, float* r0, float* r1, in
 static int32_t gn_gram_impl(const float* J, const float* r, const float* y, const float* r_old, float* r_out, uint32_t* fmax_bits,
                             float rtol, float atol, int64_t m_local, int32_t n, float* out, void* workspace, void* stream, gram::PeerXchg x,
                             const GnFold* fold) {
-  if (n != gram::N) {
-    set_error("gn_gram: this build supports n = %d parameters only (got %d)", gram::N, n);
+  if (n < 4 || n > gram::N || (n & 3)) {
+    set_error("gn_gram: need 4 <= n <= %d and n %% 4 == 0 (got %d); vectors and `out` keep the %d-wide layout", gram::N, n, gram::N);
     return B200OPT_EINVAL;
   }
   if (m_local < 0 || m_local > ((int64_t)1 << 31) - 64) {
@@ -722,8 +738,8 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
     return B200OPT_ECUDA;
   }
   CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)gram::N, (cuuint64_t)m_local};
-  const cuuint64_t strides[1] = {(cuuint64_t)gram::N * sizeof(float)};
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m_local};
+  const cuuint64_t strides[1] = {(cuuint64_t)n * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)gram::BOX_COLS, (cuuint32_t)gram::KROWS};
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(J), dims, strides, box, estr,
@@ -736,7 +752,7 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   static LaunchCache cache;
   if (cache.configure(gram::gram_kernel, gram::THREADS, gram::SMEM_BYTES) < 0) return B200OPT_ECUDA;
   constexpr int debug = 0;  // ablation switch of profiles/README.md (1: TMA only, 2: TMA + MMA); a build-time constant in release
-  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, nullptr, nullptr, nullptr, nullptr, nullptr,
+  gram::Params p{r, y, r_old, r_out, fmax_bits, rtol, atol, m_local, ws, num_tiles, n, nullptr, nullptr, nullptr, nullptr, nullptr,
                  gram::PeerXchg{nullptr, 0, 0, 0, 0, nullptr}, debug};
   if (fold) {
     p.state = fold->state;
@@ -756,7 +772,7 @@ static int32_t gn_gram_impl(const float* J, const float* r, const float* y, cons
   gram::gram_kernel<<<grid, gram::THREADS, gram::SMEM_BYTES, st>>>(tmap, p);
   if (check_cuda(cudaGetLastError(), "gram_kernel launch")) return B200OPT_ECUDA;
   const int total = gram::N * gram::N + gram::N + 1;
-  gram::gram_reduce_kernel<<<(total + 1 + 255) / 256, 256, 0, st>>>(ws, grid, grid, out, x, fold ? fold->state : nullptr);
+  gram::gram_reduce_kernel<<<(total + 1 + 255) / 256, 256, 0, st>>>(ws, grid, grid, out, x, fold ? fold->state : nullptr, n);
   return check_cuda(cudaGetLastError(), "gram_reduce_kernel launch");
 }
 

@@ -379,3 +379,51 @@ def test_device_loop_repeated_solves_do_not_leak():
     torch.cuda.synchronize()
     del sol
     assert torch.cuda.memory_allocated() <= base + (1 << 20)
+
+
+# ---- fewer than 256 columns: the kernels work on J padded with zero columns (never read from memory) -----------------------
+@pytest.mark.parametrize("n", [4, 36, 64, 100, 128, 200, 252])
+def test_gram_and_gauss_newton_with_fewer_columns(n):
+    """TMA loads only the column groups that exist (a partial group is zero-filled by its out-of-bounds handling, whole groups
+    beyond n are zeroed once in shared memory): G, g, the fused residual and the full Gauss-Newton solve for 4 <= n <= 256."""
+    lib = _lib.load()
+    m = 20000
+    gen = np.random.default_rng(100 + n)
+    scale = np.logspace(0, -1, n)
+    Jn = (gen.standard_normal((m, n)) * scale).astype(np.float32)
+    y_true = gen.standard_normal(n) / scale
+    dn = (Jn.astype(np.float64) @ y_true + 0.01 * gen.standard_normal(m)).astype(np.float32)
+    J, d = torch.as_tensor(Jn, device=DEV), torch.as_tensor(dn, device=DEV)
+    # Gram of a given residual through the C ABI: `out` keeps the 256-wide layout, unit diagonal for the padding
+    st = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(lib.b200opt_gn_gram_workspace_size(n), dtype=torch.uint8, device=DEV)
+    out = torch.full((N * N + N + 1,), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.check(lib.b200opt_gn_gram(J.data_ptr(), d.data_ptr(), m, n, out.data_ptr(), ws.data_ptr(), st), "gn_gram n < 256")
+    torch.cuda.synchronize()
+    G = out[: N * N].view(N, N)
+    Jd = J.double()
+    G_ref = Jd.T @ Jd
+    sc = torch.sqrt(torch.outer(torch.diag(G_ref), torch.diag(G_ref)))
+    assert ((G[:n, :n].double() - G_ref).abs() / sc).max().item() < 2e-3
+    pad = torch.eye(N, device=DEV)[n:, :]
+    assert torch.equal(G[n:, :], pad) and torch.equal(G[:, n:], pad.T)          # zeros, unit diagonal
+    g = out[N * N : N * N + N]
+    assert torch.equal(g[n:], torch.zeros(N - n, device=DEV))
+    gs = Jd.abs().T @ d.double().abs()
+    assert ((g[:n].double() - Jd.T @ d.double()).abs() / gs).max().item() < 1e-5
+    # the whole solve through the public API (device loop, both solvers) and the step-by-step host loop
+    from optimistix_b200._gn_large import gauss_newton_large
+
+    y0 = torch.zeros(n, dtype=torch.float32, device=DEV)
+    sv = optx.GaussNewton(1e-4, 1e-4)
+    sol = optx.least_squares(optx.models.linear_rows, sv, y0, (J, d), throw=False)
+    host = gauss_newton_large(J, d, y0, sv, throw=False, device_loop=False)
+    dev64 = gauss_newton_large(J, d, y0, sv, throw=False, linear_solver=1)
+    assert sol.result == host.result == optx.RESULTS.successful and sol.value.shape == (n,)
+    assert torch.equal(dev64.value, host.value) and dev64.stats["num_steps"] == host.stats["num_steps"]
+    y_ls = np.linalg.lstsq(Jn.astype(np.float64), dn.astype(np.float64), rcond=None)[0]
+    scaled = np.abs(sol.value.cpu().numpy() - y_ls) / (1e-4 + 1e-4 * np.abs(y_ls))
+    print(f"[gram n={n}] steps {sol.stats['num_steps']}, max scaled diff vs fp64 lstsq {scaled.max():.3g}")
+    assert scaled.max() <= 1.0
+    with pytest.raises(ValueError):
+        gauss_newton_large(J[:, : n - 1].contiguous(), d, y0[: n - 1], sv) if n > 4 else gauss_newton_large(J[:, :2].contiguous(), d, y0[:2], sv)
