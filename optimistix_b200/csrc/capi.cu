@@ -3,6 +3,10 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "lsq_launch.cuh"
@@ -96,6 +100,77 @@ static int validate_common(const char* who, int dtype, int64_t batch, const b200
 // buffers so that no D2H ever blocks the enqueueing thread (a blocking copy would serialise the pipeline).
 // The staging buffers are cached per host thread (grow-only) and released by b200opt_host_cache_release().
 constexpr int kStreams = 4;
+
+// Pageable -> page-locked staging copies done by a few helper threads.  cudaMemcpyAsync from pageable memory goes through the
+// driver's own single staging buffer (measured 11 GB/s: 100 ms per 1 Mi gauss2 fits for a caller who did not pin anything);
+// copying each chunk into our page-locked slab with several threads first and letting the copy engine read from there keeps
+// the pipeline at the host-memory rate instead.  One pool per host thread that uses the host entry points, created on first
+// use with pageable inputs, joined by b200opt_host_cache_release().
+class CopyPool {
+ public:
+  explicit CopyPool(int nthreads) : stop_(false), pending_(0), generation_(0) {
+    for (int t = 0; t < nthreads; ++t) workers_.emplace_back([this, t] { run(t); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++generation_;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // dst[0..bytes) = src[0..bytes), split over the pool and the calling thread; returns when every byte has been copied
+  void copy(void* dst, const void* src, size_t bytes) {
+    const int parts = size() + 1;
+    if (bytes < (size_t)1 << 20 || parts == 1) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<char*>(dst), src_ = static_cast<const char*>(src), bytes_ = bytes, per_ = per;
+      pending_ = size();
+      ++generation_;
+    }
+    cv_.notify_all();
+    const size_t off = per * size();  // the caller takes the last slice
+    if (off < bytes) memcpy(dst_ + off, src_ + off, bytes - off);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int t) {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return generation_ != seen; });
+      seen = generation_;
+      if (stop_) return;
+      const size_t off = per_ * t;
+      char* d = dst_;
+      const char* s = src_;
+      const size_t n = off < bytes_ ? (bytes_ - off < per_ ? bytes_ - off : per_) : 0;
+      lk.unlock();
+      if (n) memcpy(d + off, s + off, n);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  bool stop_;
+  int pending_;
+  unsigned long long generation_;
+  char* dst_ = nullptr;
+  const char* src_ = nullptr;
+  size_t bytes_ = 0, per_ = 0;
+};
+
 struct HostCache {
   int device = -1;
   cudaStream_t st[kStreams] = {};
@@ -104,6 +179,10 @@ struct HostCache {
   size_t dev_bytes = 0;
   void* pin[kStreams] = {};
   size_t pin_bytes = 0;
+  void* pin_in[kStreams] = {};   // page-locked staging of PAGEABLE inputs (filled by the copy pool)
+  size_t pin_in_bytes = 0;
+  cudaEvent_t in_done[kStreams] = {};  // the H2D copies out of pin_in[s] have completed: the slab may be refilled
+  CopyPool* pool = nullptr;
   void* shared = nullptr;
   size_t shared_bytes = 0;
   void release() {
@@ -116,8 +195,13 @@ struct HostCache {
       if (done[s]) cudaEventDestroy(done[s]);
       if (dev[s]) cudaFree(dev[s]);
       if (pin[s]) cudaFreeHost(pin[s]);
-      st[s] = nullptr, done[s] = nullptr, dev[s] = nullptr, pin[s] = nullptr;
+      if (pin_in[s]) cudaFreeHost(pin_in[s]);
+      if (in_done[s]) cudaEventDestroy(in_done[s]);
+      st[s] = nullptr, done[s] = nullptr, dev[s] = nullptr, pin[s] = nullptr, pin_in[s] = nullptr, in_done[s] = nullptr;
     }
+    delete pool;
+    pool = nullptr;
+    pin_in_bytes = 0;
     if (shared) cudaFree(shared);
     shared = nullptr;
     dev_bytes = pin_bytes = shared_bytes = 0;
@@ -168,6 +252,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     for (int s = 0; s < kStreams; ++s) {
       if (check_cuda(cudaStreamCreateWithFlags(&hc.st[s], cudaStreamNonBlocking), "stream create")) return B200OPT_ECUDA;
       if (check_cuda(cudaEventCreateWithFlags(&hc.done[s], cudaEventDisableTiming), "event create")) return B200OPT_ECUDA;
+      if (check_cuda(cudaEventCreateWithFlags(&hc.in_done[s], cudaEventDisableTiming), "event create")) return B200OPT_ECUDA;
     }
   }
   if (chunk <= 0) chunk = 1 << 15;
@@ -175,8 +260,15 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   // carve one device slab and one pinned slab per stream
   std::vector<size_t> in_off(ins.size()), out_off(outs.size()), bounce_off(outs.size());
   std::vector<bool> out_pinned(outs.size());
-  size_t dev_need = 0, pin_need = 0;
-  for (size_t i = 0; i < ins.size(); ++i) in_off[i] = dev_need, dev_need += align256(ins[i].bytes_per_problem * chunk);
+  std::vector<bool> in_staged(ins.size());
+  std::vector<size_t> stage_off(ins.size());
+  size_t dev_need = 0, pin_need = 0, pin_in_need = 0;
+  for (size_t i = 0; i < ins.size(); ++i) {
+    in_off[i] = dev_need, dev_need += align256(ins[i].bytes_per_problem * chunk);
+    // a pageable input that is worth it (>= 1 MiB per chunk) is staged through page-locked memory by the copy pool
+    in_staged[i] = ins[i].bytes_per_problem * (size_t)chunk >= ((size_t)1 << 20) && !is_pinned(ins[i].h);
+    if (in_staged[i]) stage_off[i] = pin_in_need, pin_in_need += align256(ins[i].bytes_per_problem * chunk);
+  }
   const size_t queue_off = dev_need;  // 8 bytes per stream for the ticket counter of the dynamic problem queue
   dev_need += 256;
   for (size_t i = 0; i < outs.size(); ++i) {
@@ -200,6 +292,20 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     }
     hc.pin_bytes = pin_need;
   }
+  if (pin_in_need > hc.pin_in_bytes) {
+    for (int s = 0; s < kStreams; ++s) {
+      if (hc.pin_in[s]) cudaFreeHost(hc.pin_in[s]);
+      hc.pin_in[s] = nullptr;
+      if (check_cuda(cudaMallocHost(&hc.pin_in[s], pin_in_need), "input staging cudaMallocHost")) return hc.pin_in_bytes = 0, B200OPT_ECUDA;
+    }
+    hc.pin_in_bytes = pin_in_need;
+  }
+  if (pin_in_need && !hc.pool) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int helpers = hw > 16 ? 7 : (hw > 4 ? (int)hw / 2 - 1 : 1);  // the calling thread copies too
+    hc.pool = new CopyPool(helpers);
+  }
+  bool in_busy[kStreams] = {};
   if (shared_bytes > hc.shared_bytes) {
     if (hc.shared) cudaFree(hc.shared);
     hc.shared = nullptr;
@@ -233,11 +339,25 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     const int64_t nb = (batch - off < chunk) ? batch - off : chunk;
     if (int e = drain(s)) return e;  // the bounce buffers of this stream are about to be reused
     char* base = static_cast<char*>(hc.dev[s]);
+    bool staged_any = false;
     for (size_t i = 0; i < ins.size(); ++i) {
       d_in[i] = base + in_off[i];
-      if (ins[i].bytes_per_problem)
-        cudaMemcpyAsync(base + in_off[i], static_cast<const char*>(ins[i].h) + ins[i].bytes_per_problem * off,
-                        ins[i].bytes_per_problem * nb, cudaMemcpyHostToDevice, hc.st[s]);
+      if (!ins[i].bytes_per_problem) continue;
+      const char* src = static_cast<const char*>(ins[i].h) + ins[i].bytes_per_problem * off;
+      if (in_staged[i]) {
+        if (in_busy[s] && !staged_any) {  // the copy engine may still be reading this slot's previous contents
+          if (check_cuda(cudaEventSynchronize(hc.in_done[s]), who)) return B200OPT_ECUDA;
+        }
+        staged_any = true;
+        char* stage = static_cast<char*>(hc.pin_in[s]) + stage_off[i];
+        hc.pool->copy(stage, src, ins[i].bytes_per_problem * nb);
+        src = stage;
+      }
+      cudaMemcpyAsync(base + in_off[i], src, ins[i].bytes_per_problem * nb, cudaMemcpyHostToDevice, hc.st[s]);
+    }
+    if (staged_any) {
+      cudaEventRecord(hc.in_done[s], hc.st[s]);
+      in_busy[s] = true;
     }
     for (size_t i = 0; i < outs.size(); ++i) d_out[i] = base + out_off[i];
     g_queue_scratch = reinterpret_cast<unsigned long long*>(base + queue_off);

@@ -433,3 +433,27 @@ def test_sixteen_bit_data_fp64_and_ragged_alignment():
                                          torch.cuda.current_stream().cuda_stream), "least_squares int16 pitched")
     torch.cuda.synchronize()
     assert torch.equal(y, ref.value) and torch.equal(steps, ref.stats["num_steps"])
+
+
+def test_pageable_inputs_are_staged_by_the_copy_pool():
+    """Host entry point with ordinary (pageable) NumPy arrays large enough to be staged through the page-locked slab by the
+    helper threads (>= 1 MiB per chunk), odd chunk sizes, repeated calls: bit-identical to the device-pointer path."""
+    w = synthetic.gauss2_batch(40000, seed=41)
+    sv = optx.LevenbergMarquardt(1e-4, 1e-4)
+    ref = optx.least_squares(optx.models.gauss2, sv, _cuda(w["y0"]), (_cuda(w["x"]), _cuda(w["d"])), throw=False)
+    for chunk in (0, 4096, 9999, 40000):
+        y0 = np.array(w["y0"], copy=True)
+        d = np.array(w["d"], copy=True)
+        h = optx.least_squares(optx.models.gauss2, sv, y0, (w["x"], d), throw=False, chunk=chunk)
+        assert np.array_equal(h.value, to_np(ref.value)) and np.array_equal(h.stats["num_steps"], to_np(ref.stats["num_steps"]))
+        assert np.array_equal(h.result, to_np(ref.result))
+    # float16 rows, pageable
+    d16 = w["d"].astype(np.float16)
+    a = optx.least_squares(optx.models.gauss2, sv, _cuda(w["y0"]), (_cuda(w["x"]), torch.as_tensor(d16, device=DEV)), throw=False)
+    h = optx.least_squares(optx.models.gauss2, sv, np.array(w["y0"]), (w["x"], np.array(d16)), throw=False, chunk=8192)
+    assert np.array_equal(h.value, to_np(a.value))
+    from optimistix_b200 import _lib
+
+    _lib.load().b200opt_host_cache_release()  # joins the helper threads; the next call builds a new cache
+    h2 = optx.least_squares(optx.models.gauss2, sv, np.array(w["y0"]), (w["x"], np.array(d16)), throw=False, chunk=8192)
+    assert np.array_equal(h2.value, h.value)
