@@ -1,58 +1,8 @@
 #include <stdlib.h>
 
-#include "lsq_kernel_p2x.cuh"
+#include "lsq_kernel_p2.cuh"
 #include "lsq_launch.cuh"
 namespace b200opt {
-
-// 1: two problems per warp (lsq_kernel_p2x.cuh), 0: one problem per warp (lsq_kernel_p2.cuh); A/B builds: tools/lm_variants.sh
-#ifndef LSQ_P2X
-#define LSQ_P2X 1
-#endif
-
-template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2x(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2x<PModel, TRUST, NPAIRS>;
-  const size_t smem = lsq_p2x_smem_bytes<PModel>(p.m_pad);
-  if (smem > 227 * 1024) return -1;  // caller falls back
-  static LaunchCache cache;
-  const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
-  if (blocks_per_sm < 0) return B200OPT_ECUDA;
-  const int64_t per_cta = 2 * kLsqWarpsPerBlock;  // problems resident per CTA
-  const int64_t need = (p.batch + per_cta - 1) / per_cta;
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
-  const int grid = (int)(need < cap ? need : cap);
-  QueueCounter qc;
-  LsqParams<float> pq = p;
-  pq.queue = nullptr;
-  if (need > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh); not worth its set-up for a wave or two
-    qc.acquire(stream);
-    pq.queue = qc.ptr;
-  }
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
-  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2x launch");
-}
-
-// packed-fp32 fast path (lsq_kernel_p2.cuh); everything it does not cover goes to the scalar kernel
-template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const LsqParams<float>& p, cudaStream_t stream) {
-  auto kern = lsq_solve_kernel_p2<PModel, TRUST, NPAIRS>;
-  const size_t per_warp = WarpReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)(3 + PModel::NAUX) * p.m_pad;
-  const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
-  if (smem > 227 * 1024) return -1;  // caller falls back
-  static LaunchCache cache;
-  const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
-  if (blocks_per_sm < 0) return B200OPT_ECUDA;
-  const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
-  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
-  const int grid = (int)(need < cap ? need : cap);
-  QueueCounter qc;
-  LsqParams<float> pq = p;
-  pq.queue = nullptr;
-  if (need > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh); not worth its set-up for a wave or two
-    qc.acquire(stream);
-    pq.queue = qc.ptr;
-  }
-  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
-  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
-}
 
 int lsq_launch_gauss2(const LsqArgs& a) {
   const bool d16 = a.opts->data_dtype != B200OPT_DATA_AS_COMPUTE;  // 16-bit rows: any alignment (the loader has a scalar path)
@@ -81,13 +31,8 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.data_kind = a.opts->data_dtype;
     p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
-    int rc = -1;
-#if LSQ_P2X
-    if (a.m == 256) rc = lm ? lsq_launch_p2x<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2x<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
-    else rc = lm ? lsq_launch_p2x<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2x<Gauss2P2, false, 0>(p, a.stream);
-    if (rc >= 0) return rc;
-#endif
-    if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);
+    int rc;
+    if (a.m == 256) rc = lm ? lsq_launch_p2<Gauss2P2, true, 4>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 4>(p, a.stream);  // configs[1]
     else rc = lm ? lsq_launch_p2<Gauss2P2, true, 0>(p, a.stream) : lsq_launch_p2<Gauss2P2, false, 0>(p, a.stream);
     if (rc >= 0) return rc;
   }

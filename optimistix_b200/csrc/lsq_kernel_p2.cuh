@@ -455,6 +455,13 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 // without spills, FIVE CTAs = 20 problems per SM - was measured and dropped as well: bit-identical results, 15.15 ms against
 // 14.55 ms.  The extra shared-memory traffic and Jacobian-row recomputation cost more than the fifth CTA hides: this kernel has
 // no single limiter (ncu, lsq_r10: issue slots 62%, FMA pipe 57%, shared-memory wavefronts 45% of peak).)
+// (A two-problems-per-warp variant - the row sweeps of each problem on all 32 lanes, one after the other, the 8 x 8 algebra of the
+// two problems at the same time in the two half-warps, G and g in shared memory between iterations, 24 problems resident per SM
+// - was measured and dropped in round 2: bit-identical results, ~25% fewer instructions per problem-iteration, 13.28 ms against
+// 12.88 ms per 1 Mi fits (2.17 against 1.96 ms at 131 k).  With S the latency of a problem's row sweeps and A that of its algebra
+// the SM retires (warps x problems per warp) / (problems per warp x S + A) problem-iterations per unit time: 16 / (S + A) here,
+// 24 / (2 S + A) there - equal when S = A, which is where this kernel is.  Shared memory (16 KB per warp for two problems) keeps
+// the variant at 12 warps per SM.  See git history, profiles/lm_ab_p2x_r2.log and DESIGN.md section 10.)
 // (A half-warp-per-problem variant - two problems per warp sharing the replicated 8 x 8 algebra - was measured and dropped:
 // 10% fewer instructions but only 22.8 of 32 lanes active on average (accept / reject and iteration counts differ between the
 // two problems) and 12 instead of 16 warps per SM: 16.8 ms against 15.6 ms for 1 Mi fits.  See git history and profiles/README.md.)
