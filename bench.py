@@ -107,7 +107,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -556,8 +556,8 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
         e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / K
         d2h = hs.value.nbytes + hs.stats["num_steps"].nbytes + hs.result.nbytes
         checks["e2e_bitwise_equal_device_path"] = bool(np.array_equal(hs.value, sol.value.cpu().numpy()))
-        e2e = {"value": batch * world / (e2e_ms / 1e3), "unit": "problems/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_ms, "api": "the *_host C entry point via the optimistix_b200 entry point called with NumPy inputs (page-locked)",
+        e2e = {"value": batch * world / (e2e_ms / 1e3), "unit": "problems/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "bytes_note": f"whole job: {world} rank(s) x ({int(h2d)} B in, {int(d2h)} B out) per step", "ms_per_step": e2e_ms, "api": "the *_host C entry point via the optimistix_b200 entry point called with NumPy inputs (page-locked)",
                "chunk": args.chunk}
         launches += K * ((batch + args.chunk - 1) // args.chunk)
         # the same call with ordinary (pageable) NumPy arrays: what a caller who did not pin anything gets
@@ -597,7 +597,7 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
             ev1.record()
             torch.cuda.synchronize()
             dms16 = max_over_ranks(ev0.elapsed_time(ev1)) / K
-            e2e["float16_data"] = {"value": batch * world / (ms16 / 1e3), "ms_per_step": ms16, "h2d_bytes_per_step": int(h16["y0"].nbytes + h16["prob"].nbytes + inp["shared"].nbytes),
+            e2e["float16_data"] = {"value": batch * world / (ms16 / 1e3), "ms_per_step": ms16, "h2d_bytes_per_step": int(h16["y0"].nbytes + h16["prob"].nbytes + inp["shared"].nbytes) * world,
                                   "device_resident_ms_per_step": dms16, "device_resident_value": batch * world / (dms16 / 1e3),
                                   "successful_frac": float((s16.result == 0).float().mean().item()), "mean_num_steps": float(s16.stats["num_steps"].float().mean().item()),
                                   "e2e_bitwise_equal_device_path": bool(np.array_equal(hs16.value, s16.value.cpu().numpy())),
