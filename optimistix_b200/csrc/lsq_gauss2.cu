@@ -4,6 +4,29 @@
 #include "lsq_launch.cuh"
 namespace b200opt {
 
+// packed-fp32 fast path (lsq_kernel_p2.cuh); everything it does not cover goes to the scalar kernel
+template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const LsqParams<float>& p, cudaStream_t stream) {
+  auto kern = lsq_solve_kernel_p2<PModel, TRUST, NPAIRS>;
+  const size_t per_warp = WarpReduceLayout<float, Tri<PModel::N>::size + PModel::N>::elems + (size_t)(3 + PModel::NAUX) * p.m_pad;
+  const size_t smem = sizeof(float) * ((size_t)p.m_pad + kLsqWarpsPerBlock * per_warp);
+  if (smem > 227 * 1024) return -1;  // caller falls back
+  static LaunchCache cache;
+  const int blocks_per_sm = cache.configure(kern, kLsqWarpsPerBlock * 32, smem);
+  if (blocks_per_sm < 0) return B200OPT_ECUDA;
+  const int64_t need = (p.batch + kLsqWarpsPerBlock - 1) / kLsqWarpsPerBlock;
+  const int64_t cap = (int64_t)device_sm_count() * blocks_per_sm;
+  const int grid = (int)(need < cap ? need : cap);
+  QueueCounter qc;
+  LsqParams<float> pq = p;
+  pq.queue = nullptr;
+  if (need > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh); not worth its set-up for a wave or two
+    qc.acquire(stream);
+    pq.queue = qc.ptr;
+  }
+  kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
+  return check_cuda(cudaGetLastError(), "lsq_solve_kernel_p2 launch");
+}
+
 int lsq_launch_gauss2(const LsqArgs& a) {
   const bool d16 = a.opts->data_dtype != B200OPT_DATA_AS_COMPUTE;  // 16-bit rows: any alignment (the loader has a scalar path)
   const bool aligned = d16 || ((a.prob_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0));
