@@ -152,6 +152,7 @@ __device__ __forceinline__ float2 exp_mhalf2(float2 t) {
 struct Gauss2P2 {
   static constexpr int N = 8;
   static constexpr int NAUX = 2;
+  static constexpr int NCONST = 2;  // trailing parameters (b0, b1) whose Jacobian columns (1, x) are the same for every y and problem
   struct Consts {
     float2 i1, c1, i2, c2;    // z = x * i + c,  c = -mu * i
     float2 a1, a2, b0, b1;    // amplitudes and baseline (residual)
@@ -167,6 +168,11 @@ struct Gauss2P2 {
     c.i1 = p2(i1), c.c1 = p2(-y[1] * i1), c.i2 = p2(i2), c.c2 = p2(-y[4] * i2);
     c.a1 = p2(y[0]), c.a2 = p2(y[3]), c.b0 = p2(y[6]), c.b1 = p2(y[7]);
     c.ai1 = p2(y[0] * i1), c.ai2 = p2(y[3] * i2);
+    return c;
+  }
+  __device__ static __forceinline__ Consts prepare_const() {  // any y: only the NCONST trailing Jacobian columns are read
+    Consts c;
+    c.i1 = c.c1 = c.i2 = c.c2 = c.a1 = c.a2 = c.b0 = c.b1 = c.ai1 = c.ai2 = p2(0.f);
     return c;
   }
   __device__ static __forceinline__ float2 residual(const Consts& c, float2 x, float2 d, float2 (&aux)[NAUX]) {
@@ -190,6 +196,15 @@ struct Gauss2P2 {
   }
 };
 
+// Round-2 latency / work trims (bit mask, A/B builds: tools/lm_variants.sh -DLSQ_P2_OPT=...; results are bit-identical to 0):
+//   1  the five butterfly rounds of the ||r||^2 reduction are interleaved with the rows of the predicted-reduction quadratic form
+//      (the reduction sits behind a divergence check = a basic-block boundary, so the assembler does not overlap them itself)
+//   2  Gram entries between parameters whose Jacobian column depends neither on y nor on the problem (PModel::NCONST trailing
+//      parameters: the baseline columns 1 and x) are summed ONCE per warp with the same code path and reused
+//   4  the f-space Cauchy test (one comparison per row) runs only when the y-space test passed (terminate needs both)
+#ifndef LSQ_P2_OPT
+#define LSQ_P2_OPT 7
+#endif
 #ifndef LSQ_P2_MINBLOCKS
 #define LSQ_P2_MINBLOCKS 4
 #endif
@@ -205,6 +220,9 @@ struct Gauss2P2 {
 constexpr int kUnrollR = LSQ_P2_UNROLL_R, kUnrollJ = LSQ_P2_UNROLL_J;  // (macros are not expanded inside #pragma)
 // NPAIRS > 0: the number of row pairs per lane (m / 64) is a compile-time constant: both row sweeps are fully unrolled and
 // the accumulators are initialised by the first pair instead of being zeroed.  NPAIRS == 0: any m % 64 == 0.
+template <class PModel> __host__ __device__ constexpr bool p2_const_entry(int a, int b) {
+  return (LSQ_P2_OPT & 2) && a >= PModel::N - PModel::NCONST && b >= PModel::N - PModel::NCONST;
+}
 template <class PModel, bool TRUST, int NPAIRS>
 __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_solve_kernel_p2(const LsqParams<float> p) {
   using T = float;
@@ -232,6 +250,40 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
   __syncthreads();
   const float2* xs2 = reinterpret_cast<const float2*>(xs);
   const float2* ds2 = reinterpret_cast<const float2*>(ds);
+
+  // problem-independent Gram entries (LSQ_P2_OPT & 2): the same pair sums, pair -> scalar adds and warp all-reduce as below
+  T gconst[(PModel::NCONST * (PModel::NCONST + 1)) / 2 + 1];
+  if (LSQ_P2_OPT & 2) {
+    T cacc[NG + N];
+#pragma unroll
+    for (int a = 0; a < NG + N; ++a) cacc[a] = T(0);
+    const typename PModel::Consts pc0 = PModel::prepare_const();
+    float2 c2[NG];
+#pragma unroll
+    for (int a = 0; a < NG; ++a) c2[a] = make_float2(0.f, 0.f);
+    for (int k = 0; k < npairs; ++k) {
+      const int idx = k * 32 + lane;
+      float2 aux[NAUX], j[N];
+#pragma unroll
+      for (int q = 0; q < NAUX; ++q) aux[q] = make_float2(0.f, 0.f);
+      PModel::jac(pc0, xs2[idx], aux, j);
+#pragma unroll
+      for (int a = N - PModel::NCONST; a < N; ++a)
+#pragma unroll
+        for (int b = N - PModel::NCONST; b <= a; ++b)
+          c2[Tri<N>::at(a, b)] = (NPAIRS > 0 && k == 0) ? mul2(j[a], j[b]) : fma2(j[a], j[b], c2[Tri<N>::at(a, b)]);
+    }
+#pragma unroll
+    for (int a = N - PModel::NCONST; a < N; ++a)
+#pragma unroll
+      for (int b = N - PModel::NCONST; b <= a; ++b) cacc[Tri<N>::at(a, b)] = c2[Tri<N>::at(a, b)].x + c2[Tri<N>::at(a, b)].y;
+    warp_allreduce_array<T, NG + N>(cacc, scratch, lane);
+    int q = 0;
+#pragma unroll
+    for (int a = N - PModel::NCONST; a < N; ++a)
+#pragma unroll
+      for (int b = N - PModel::NCONST; b <= a; ++b) gconst[q++] = cacc[Tri<N>::at(a, b)];
+  }
 
   for (int64_t prob = warp0; prob < p.batch; prob = next_problem_warp(p.queue, prob, nwarps, lane)) {
     T y[N], ye[N];
@@ -287,18 +339,46 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 #pragma unroll kUnrollR
         for (int k = 0; k < npairs; ++k) res_pair(k);
       }
-      const T rre = warp_sum(part.x + part.y);
-
       T d[N];
 #pragma unroll
       for (int j = 0; j < N; ++j) d[j] = ye[j] - y[j];
 
       // ---- search (trust_region.py:86-104 / learning_rate.py:24-35)
       bool accept = true;
+      T rre;
+      T lin = T(0), quad = T(0);
+      if (TRUST && (LSQ_P2_FAST & 2) && !(LSQ_P2_FAST & 8) && (LSQ_P2_OPT & 1)) {
+        // 0.5 d.G d = sum_i d_i (0.5 G_ii d_i + sum_{j<i} G_ij d_j), its rows issued between the rounds of the ||r||^2 butterfly
+        T hq = T(0);
+        auto quad_row = [&](int i) {
+          T gd = T(0.5) * G[Tri<N>::at(i, i)] * d[i];
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            if (j < i) gd += G[Tri<N>::at(i, j)] * d[j];
+          hq += d[i] * gd;
+          lin += d[i] * g[i];
+        };
+        T v = part.x + part.y;
+        constexpr int kRowsAfterRound[5] = {(N * 3) / 8, (N * 5) / 8, (N * 6) / 8, (N * 7) / 8, N};  // N = 8: rows 0-2, 3-4, 5, 6, 7
+        int i0 = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          v += __shfl_xor_sync(kFull, v, 16 >> r);
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (i >= i0 && i < kRowsAfterRound[r]) quad_row(i);
+          i0 = kRowsAfterRound[r];
+        }
+        rre = v;
+        quad = hq + hq;
+      } else {
+        rre = warp_sum(part.x + part.y);
+      }
       if (TRUST) {
-        T lin = T(0), quad = T(0);
         if (LSQ_P2_FAST & 8) {
           lin = predn;
+        } else if ((LSQ_P2_FAST & 2) && (LSQ_P2_OPT & 1)) {
+          // done above
         } else if (LSQ_P2_FAST & 2) {
           T hq = T(0);  // 0.5 d.G d = sum_i d_i (0.5 G_ii d_i + sum_{j<i} G_ij d_j)
 #pragma unroll
@@ -364,11 +444,12 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
               if (a >= a_lo && a < a_hi) {
 #pragma unroll
                 for (int b = 0; b <= a; ++b)
-                  acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
+                  if (!p2_const_entry<PModel>(a, b))
+                    acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
                 acc2[NG + a] = init ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
               }
             }
-            if (half == 0) {
+            if (half == 0 && (!(LSQ_P2_OPT & 4) || yconv)) {
               const float2 ro = racc2[idx];
               fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
             }
@@ -384,7 +465,8 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
           for (int a = 0; a < N; ++a) {
             if (a >= a_lo && a < a_hi) {
 #pragma unroll
-              for (int b = 0; b <= a; ++b) acc[Tri<N>::at(a, b)] = acc2[Tri<N>::at(a, b)].x + acc2[Tri<N>::at(a, b)].y;
+              for (int b = 0; b <= a; ++b)
+                acc[Tri<N>::at(a, b)] = p2_const_entry<PModel>(a, b) ? T(0) : acc2[Tri<N>::at(a, b)].x + acc2[Tri<N>::at(a, b)].y;
               acc[NG + a] = acc2[NG + a].x + acc2[NG + a].y;
             }
           }
@@ -393,6 +475,13 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
         else warp_allreduce_array<T, NG + N>(acc, scratch, lane);
 #pragma unroll
         for (int a = 0; a < NG; ++a) G[a] = acc[a];
+        if (LSQ_P2_OPT & 2) {
+          int q = 0;
+#pragma unroll
+          for (int a = N - PModel::NCONST; a < N; ++a)
+#pragma unroll
+            for (int b = N - PModel::NCONST; b <= a; ++b) G[Tri<N>::at(a, b)] = gconst[q++];
+        }
 #pragma unroll
         for (int a = 0; a < N; ++a) g[a] = acc[NG + a];
         fconv = __all_sync(kFull, fconv);
