@@ -79,6 +79,22 @@ def test_bfgs_prefix_state_parity():
         assert (to_np(sol.result) == ref["result"]).all()
 
 
+@pytest.mark.parametrize("norm", [optx.max_norm, optx.two_norm, optx.rms_norm])
+def test_bfgs_norms(norm):
+    """Termination norms: max_norm runs the division-free test evaluated by the trial warps, two_norm / rms_norm the quotient
+    form after the adoption; the oracle always forms the quotients (_misc.py:291-310).  Short problems (n = 8) so that the
+    counts are not yet decorrelated by ~760 steps of rounding: identical counts and codes on nearly all of them."""
+    w = synthetic.rosenbrock_batch(256, n=8)
+    sol = optx.minimise(optx.models.rosenbrock, optx.BFGS(1e-8, 1e-8, norm=norm), torch.as_tensor(w["y0"], device=DEV), None,
+                        throw=False, max_steps=4096)
+    ref = S.bfgs(M.rosenbrock, w["y0"], None, rtol=1e-8, atol=1e-8, norm=norm.norm_name, max_steps=4096)
+    s = compare(sol, ref, 1e-8, 1e-8, f"bfgs norm={norm.norm_name}")
+    assert s["result_match"] == 1.0
+    assert s["steps_match"] >= 0.98  # measured: 1.0 / 1.0 / 0.996 (max / two / rms), mean 112 steps
+    assert s["within_tol"] == 1.0
+    assert abs(s["mean_steps"][0] / s["mean_steps"][1] - 1.0) <= 0.002
+
+
 def test_bfgs_golden():
     g = np.load(os.path.join(G, "bfgs_rosenbrock_f64.npz"))
     w = synthetic.rosenbrock_batch(64)
