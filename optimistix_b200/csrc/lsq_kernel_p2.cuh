@@ -152,6 +152,9 @@ __device__ __forceinline__ float2 exp_mhalf2(float2 t) {
 struct Gauss2P2 {
   static constexpr int N = 8;
   static constexpr int NAUX = 2;
+  // LSQ_P2_OPT & 8: the first Gram half-sweep takes the entries among the first Gaussian's parameters and the baseline (it never
+  // forms the second Gaussian's Jacobian columns: 4 packed instructions per row pair less), the second one everything else
+  static constexpr unsigned kHalf0Mask = 0xC7;
   static constexpr int NCONST = 2;  // trailing parameters (b0, b1) whose Jacobian columns (1, x) are the same for every y and problem
   struct Consts {
     float2 i1, c1, i2, c2;    // z = x * i + c,  c = -mu * i
@@ -202,8 +205,10 @@ struct Gauss2P2 {
 //   2  Gram entries between parameters whose Jacobian column depends neither on y nor on the problem (PModel::NCONST trailing
 //      parameters: the baseline columns 1 and x) are summed ONCE per warp with the same code path and reused
 //   4  the f-space Cauchy test (one comparison per row) runs only when the y-space test passed (terminate needs both)
+//   8  the two Gram half-sweeps split the entries by parameter GROUP (PModel::kHalf0Mask) instead of by parameter index, so
+//      that the first one needs only part of the Jacobian row
 #ifndef LSQ_P2_OPT
-#define LSQ_P2_OPT 7
+#define LSQ_P2_OPT 15
 #endif
 #ifndef LSQ_P2_MINBLOCKS
 #define LSQ_P2_MINBLOCKS 4
@@ -222,6 +227,15 @@ constexpr int kUnrollR = LSQ_P2_UNROLL_R, kUnrollJ = LSQ_P2_UNROLL_J;  // (macro
 // the accumulators are initialised by the first pair instead of being zeroed.  NPAIRS == 0: any m % 64 == 0.
 template <class PModel> __host__ __device__ constexpr bool p2_const_entry(int a, int b) {
   return (LSQ_P2_OPT & 2) && a >= PModel::N - PModel::NCONST && b >= PModel::N - PModel::NCONST;
+}
+// which of the two Gram half-sweeps carries entry (a, b) of the lower triangle (b == N: the gradient entry of parameter a)
+template <class PModel> __host__ __device__ constexpr int p2_half(int a, int b) {
+  if (LSQ_P2_SPLIT == 0) return 0;
+  if (LSQ_P2_OPT & 8) {
+    const bool a0 = (PModel::kHalf0Mask >> a) & 1, b0 = (b == PModel::N) || ((PModel::kHalf0Mask >> b) & 1);
+    return (a0 && b0) ? 0 : 1;
+  }
+  return a < LSQ_P2_SPLIT ? 0 : 1;
 }
 template <class PModel, bool TRUST, int NPAIRS>
 __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_solve_kernel_p2(const LsqParams<float> p) {
@@ -426,7 +440,6 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
         constexpr int SPLIT = LSQ_P2_SPLIT;
 #pragma unroll
         for (int half = 0; half < (SPLIT > 0 ? 2 : 1); ++half) {
-          const int a_lo = (half == 0) ? 0 : SPLIT, a_hi = (half == 0 && SPLIT > 0) ? SPLIT : N;
           float2 acc2[NG + N];
           if (NPAIRS == 0) {
 #pragma unroll
@@ -441,13 +454,11 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
             PModel::jac(pc, xs2[idx], aux, j);
 #pragma unroll
             for (int a = 0; a < N; ++a) {
-              if (a >= a_lo && a < a_hi) {
 #pragma unroll
-                for (int b = 0; b <= a; ++b)
-                  if (!p2_const_entry<PModel>(a, b))
-                    acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
-                acc2[NG + a] = init ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
-              }
+              for (int b = 0; b <= a; ++b)
+                if (p2_half<PModel>(a, b) == half && !p2_const_entry<PModel>(a, b))
+                  acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
+              if (p2_half<PModel>(a, N) == half) acc2[NG + a] = init ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
             }
             if (half == 0 && (!(LSQ_P2_OPT & 4) || yconv)) {
               const float2 ro = racc2[idx];
@@ -463,12 +474,11 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
           }
 #pragma unroll
           for (int a = 0; a < N; ++a) {
-            if (a >= a_lo && a < a_hi) {
 #pragma unroll
-              for (int b = 0; b <= a; ++b)
+            for (int b = 0; b <= a; ++b)
+              if (p2_half<PModel>(a, b) == half)
                 acc[Tri<N>::at(a, b)] = p2_const_entry<PModel>(a, b) ? T(0) : acc2[Tri<N>::at(a, b)].x + acc2[Tri<N>::at(a, b)].y;
-              acc[NG + a] = acc2[NG + a].x + acc2[NG + a].y;
-            }
+            if (p2_half<PModel>(a, N) == half) acc[NG + a] = acc2[NG + a].x + acc2[NG + a].y;
           }
         }
         if (LSQ_P2_FAST & 4) warp_allreduce_array_f2<NG + N>(acc, scratch, lane);
