@@ -40,6 +40,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #ifndef LSQ_P2_FAST
 #define LSQ_P2_FAST 3
 #endif
+// Round-2 latency / work trims (bit mask, A/B builds: tools/lm_variants.sh -DLSQ_P2_OPT=...; results are bit-identical to 0):
+//   1  the five butterfly rounds of the ||r||^2 reduction are interleaved with the rows of the predicted-reduction quadratic form
+//      (the reduction sits behind a divergence check = a basic-block boundary, so the assembler does not overlap them itself)
+//   2  Gram entries between parameters whose Jacobian column depends neither on y nor on the problem (PModel::NCONST trailing
+//      parameters: the baseline columns 1 and x) are summed ONCE per warp with the same code path and reused
+//   4  the f-space Cauchy test (one comparison per row) runs only when the y-space test passed (terminate needs both)
+//   8  the two Gram half-sweeps split the entries by parameter GROUP (PModel::kHalf0Mask) instead of by parameter index, so
+//      that the first one needs only part of the Jacobian row
+//  16  exp split: lo = fma(t, K, -hi) with the negation as an operand modifier instead of a second product t * (-K)
+#ifndef LSQ_P2_OPT
+#define LSQ_P2_OPT 31
+#endif
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // x < 0 or NaN -> NaN, x == 0 -> +inf (reported as `singular`)
@@ -142,8 +154,12 @@ template <int K> __device__ __forceinline__ void warp_allreduce_array_f2(float (
 __device__ __forceinline__ float2 exp_mhalf2(float2 t) {
   const float K = -0.72134752044448170368f;  // -log2(e) / 2
   const float2 hi = mul2(t, p2(K));
+#if LSQ_P2_OPT & 16
+  const float2 lo = fma2(t, p2(K), make_float2(-hi.x, -hi.y));  // t K - hi, exact (the negation is an operand modifier)
+#else
   const float2 nhi = mul2(t, p2(-K));           // == -hi exactly
   const float2 lo = fma2(t, p2(K), nhi);        // t K - hi, exact
+#endif
   const float2 e0 = make_float2(ex2_approx(hi.x), ex2_approx(hi.y));
   return fma2(mul2(e0, lo), p2(0.69314718055994530942f), e0);
 }
@@ -199,17 +215,6 @@ struct Gauss2P2 {
   }
 };
 
-// Round-2 latency / work trims (bit mask, A/B builds: tools/lm_variants.sh -DLSQ_P2_OPT=...; results are bit-identical to 0):
-//   1  the five butterfly rounds of the ||r||^2 reduction are interleaved with the rows of the predicted-reduction quadratic form
-//      (the reduction sits behind a divergence check = a basic-block boundary, so the assembler does not overlap them itself)
-//   2  Gram entries between parameters whose Jacobian column depends neither on y nor on the problem (PModel::NCONST trailing
-//      parameters: the baseline columns 1 and x) are summed ONCE per warp with the same code path and reused
-//   4  the f-space Cauchy test (one comparison per row) runs only when the y-space test passed (terminate needs both)
-//   8  the two Gram half-sweeps split the entries by parameter GROUP (PModel::kHalf0Mask) instead of by parameter index, so
-//      that the first one needs only part of the Jacobian row
-#ifndef LSQ_P2_OPT
-#define LSQ_P2_OPT 15
-#endif
 #ifndef LSQ_P2_MINBLOCKS
 #define LSQ_P2_MINBLOCKS 4
 #endif
