@@ -49,8 +49,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //   8  the two Gram half-sweeps split the entries by parameter GROUP (PModel::kHalf0Mask) instead of by parameter index, so
 //      that the first one needs only part of the Jacobian row
 //  16  exp split: lo = fma(t, K, -hi) with the negation as an operand modifier instead of a second product t * (-K)
+//  32  the first Gram half-sweep leaves j[1] in the (dead) slot of the old accepted residual for the second one
 #ifndef LSQ_P2_OPT
-#define LSQ_P2_OPT 31
+#define LSQ_P2_OPT 63
 #endif
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
@@ -206,6 +207,20 @@ struct Gauss2P2 {
     const float2 z1 = fma2(x, c.i1, c.c1), z2 = fma2(x, c.i2, c.c2);
     j[0] = aux[0];
     j[1] = mul2(mul2(aux[0], z1), c.ai1);
+    j[2] = mul2(j[1], z1);
+    j[3] = aux[1];
+    j[4] = mul2(mul2(aux[1], z2), c.ai2);
+    j[5] = mul2(j[4], z2);
+    j[6] = p2(1.0f);
+    j[7] = x;
+  }
+  // LSQ_P2_OPT & 32: the first Gram half-sweep hands j[1] to the second one (through the slot of the old accepted residual,
+  // which is dead once the f-space test has read it), so that the second does not form it again
+  __device__ static __forceinline__ float2 carry_out(const float2 (&j)[N]) { return j[1]; }
+  __device__ static __forceinline__ void jac_carry(const Consts& c, float2 x, const float2 (&aux)[NAUX], float2 carry, float2 (&j)[N]) {
+    const float2 z1 = fma2(x, c.i1, c.c1), z2 = fma2(x, c.i2, c.c2);
+    j[0] = aux[0];
+    j[1] = carry;
     j[2] = mul2(j[1], z1);
     j[3] = aux[1];
     j[4] = mul2(mul2(aux[1], z2), c.ai2);
@@ -456,7 +471,8 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
 #pragma unroll
             for (int q = 0; q < NAUX; ++q) aux[q] = auxs2[q * (mp >> 1) + idx];
             const float2 re = rtry2[idx];
-            PModel::jac(pc, xs2[idx], aux, j);
+            if ((LSQ_P2_OPT & 32) && SPLIT > 0 && half == 1) PModel::jac_carry(pc, xs2[idx], aux, racc2[idx], j);
+            else PModel::jac(pc, xs2[idx], aux, j);
 #pragma unroll
             for (int a = 0; a < N; ++a) {
 #pragma unroll
@@ -469,6 +485,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
               const float2 ro = racc2[idx];
               fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
             }
+            if ((LSQ_P2_OPT & 32) && SPLIT > 0 && half == 0) reinterpret_cast<float2*>(racc)[idx] = PModel::carry_out(j);
           };
           if (NPAIRS > 0) {
 #pragma unroll

@@ -40,7 +40,7 @@ for (text, n, s), loc in zip(sass, lines):
 tot = sum(by_outer.values())
 print(f"total {tot/steps:.1f} instr per problem-step")
 srcs = {}
-for (f, l), n in sorted(by_outer.items(), key=lambda kv: -kv[1])[:45]:
+for (f, l), n in sorted(by_outer.items(), key=lambda kv: -kv[1])[:int(__import__("os").environ.get("TOPN","45"))]:
     if f not in srcs:
         for root in ("optimistix_b200/csrc", "."):
             pth = os.path.join(root, f)
