@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
   constexpr int N = kBfgsN;
   using Vec = typename Num<T>::Vec;
   constexpr int V = Num<T>::kVec;
-  __shared__ __align__(16) T vq[4][N], vs[4][N], vg[4][N], va[4][N];  // per-warp private copies: q, s, new gradient, a
+  struct WarpVecs {  // per-warp private copies: q, s, new gradient, a - one base address, constant offsets
+    T q[N], s[N], g[N], a[N];
+  };
+  __shared__ __align__(16) WarpVecs wv[4];
   __shared__ __align__(16) T xhq[2][N], xnt[2][N];                    // cross-warp exchange, double buffered
   __shared__ __align__(16) T xye[2][4][N], xge[2][4][N];              // the four warps' trial points and gradients, double buffered
   __shared__ __align__(16) T xfe[2][4], xin[2][4];                    // ... their f and q.s
@@ -133,10 +136,11 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
   const T rtol = p.rtol, atol = p.atol;
   const bool maxnorm = p.norm == B200OPT_NORM_MAX;
   const T wscale = T(1) / T(1 << w);  // 0.5^w, exact
-  const Vec* vq_v = reinterpret_cast<const Vec*>(&vq[w][c0]);
-  const Vec* vs_v = reinterpret_cast<const Vec*>(&vs[w][c0]);
-  const Vec* vg_v = reinterpret_cast<const Vec*>(&vg[w][c0]);
-  const Vec* va_v = reinterpret_cast<const Vec*>(&va[w][c0]);
+  WarpVecs& mv = wv[w];
+  const Vec* vq_v = reinterpret_cast<const Vec*>(&mv.q[c0]);
+  const Vec* vs_v = vq_v + N / V;      // &mv.s[c0]
+  const Vec* vg_v = vq_v + 2 * N / V;  // &mv.g[c0]
+  const Vec* va_v = vq_v + 3 * N / V;  // &mv.a[c0]
 
   __shared__ long long next_slot;
   for (int64_t prob = blockIdx.x; prob < p.batch; prob = next_problem_cta(p.queue, prob, &next_slot)) {
@@ -204,9 +208,9 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
         const T df = fe - f;
         // ---- update_hessian (quasi_newton.py:342-415)
         const bool update = inner > Num<T>::eps();  // :360
-        vs[w][e0] = d0, vs[w][e1] = d1;
-        vg[w][e0] = ge0, vg[w][e1] = ge1;
-        vq[w][e0] = q0, vq[w][e1] = q1;
+        mv.s[e0] = d0, mv.s[e1] = d1;
+        mv.g[e0] = ge0, mv.g[e1] = ge1;
+        mv.q[e0] = q0, mv.q[e1] = q1;
         const T c2 = update ? T(1) / inner : T(0);  // term2 coefficient (:380)
         __syncwarp();
         T s_i = T(0);
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
           if (hb == 0) xhq[buf][row] = acc;
           __syncthreads();
           const T hq0 = xhq[buf][e0], hq1 = xhq[buf][e1];
-          s_i = vs[w][row];
+          s_i = mv.s[row];
           const T b_i = -c2 * xhq[buf][row];
 #if BFGS_EARLY_B
 #pragma unroll
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(kBfgsThreads, BFGS_MINBLOCKS) bfgs_solve_kerne
 #endif
           const T mvp_inner = warp_dot2(q0, q1, hq0, hq1);   // :376
           const T c1 = (inner + mvp_inner) / (inner * inner);  // term1 coefficient (:379)
-          va[w][e0] = c1 * d0 - c2 * hq0, va[w][e1] = c1 * d1 - c2 * hq1;
+          mv.a[e0] = c1 * d0 - c2 * hq0, mv.a[e1] = c1 * d1 - c2 * hq1;
           __syncwarp();
 #if !BFGS_EARLY_B
 #pragma unroll
