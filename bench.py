@@ -75,8 +75,11 @@ class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
+        self._armed = threading.Event()  # samples are kept only after arm(): the thread itself starts before the warm-up
         self._thr = None
         try:
+            if os.environ.get("BENCH_NO_SAMPLER"):
+                raise RuntimeError("disabled by BENCH_NO_SAMPLER")
             import pynvml
 
             pynvml.nvmlInit()
@@ -97,22 +100,31 @@ class ClockSampler:
         }
         while not self._stop.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:  # noqa: BLE001
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                if self._armed.is_set():
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.02)
 
-    def start(self):
+    def start(self, armed: bool = True):
+        """armed=False: start the thread now (before the warm-up: the first NVML queries of a process take tens to hundreds of
+        milliseconds and serialise with CUDA launches - measured as a 0.5 s hole in a timed region), keep samples from arm() on."""
+        if armed:
+            self._armed.set()
         if self.nv is not None:
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
+
+    def arm(self):
+        self._armed.set()
 
     def stop(self):
         self._stop.set()
@@ -502,6 +514,8 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
     torch.cuda.synchronize()
 
     # ---- value: device-resident, one kernel launch per step, CUDA events on the launching (current) stream
+    sampler = ClockSampler(dev.index)
+    sampler.start(armed=False)
     for _ in range(W):
         sol = run_device(name, inp_dev)
     # a step of the small configs lasts ~0.1 ms: keep warming up until the GPU has been busy for 30 ms, or the clocks
@@ -511,17 +525,30 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
     while time.perf_counter() - t_warm < 0.03:
         sol = run_device(name, inp_dev)
         torch.cuda.synchronize()
-    barrier()
-    sampler = ClockSampler(dev.index)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in evs:  # CUDA events are created lazily by their first record(): do that outside the timed region
+        a.record(), b.record()
+    # the timed region starts from an idle GPU (contract), so the first step's bracket contains that step's host-side launch
+    # path: keep the interpreter's collector out of it (measured: occasional 4 - 20 ms holes in the first bracket)
+    import gc
+
+    gc.collect()
+    gc.disable()
+    torch.cuda.synchronize()
+    barrier()
+    sampler.arm()
     t_wall0 = time.perf_counter()
+    host_us = []
     for a, b in evs:
+        th = time.perf_counter()
         a.record()
         sol = run_device(name, inp_dev)
         b.record()
+        host_us.append(round(1e6 * (time.perf_counter() - th)))
     torch.cuda.synchronize()
-    t_total_local = sum(a.elapsed_time(b) for a, b in evs)  # ms, device time of the K steps
+    gc.enable()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t_total_local = sum(step_ms)  # ms, device time of the K steps
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     clocks = sampler.stop()
@@ -645,7 +672,8 @@ def bench_batched(name, batch, inp, args, rank, world, dev, K, W, do_e2e, do_cpu
             "value": value, "unit": "problems/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "dtype": dtype, "data": "synthetic", "batch_per_gpu": batch, "global_batch": batch * world,
             "workload": desc, "roofline": roofline, "fp": fp, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "checks": checks, "wall_ms_timed_region": wall_ms}
+            "clocks": clocks, "checks": checks, "wall_ms_timed_region": wall_ms, "ms_each_step": [round(v, 4) for v in step_ms],
+            "host_us_each_step": host_us}
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -801,7 +829,8 @@ def main():
                            "numa_binding": numa},
                 "roofline": head["roofline"], "fp": head["fp"], "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"],
                 "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "checks": head["checks"],
-                "wall_ms_timed_region": head["wall_ms_timed_region"]}
+                "wall_ms_timed_region": head["wall_ms_timed_region"], "ms_each_step": head["ms_each_step"],
+                "host_us_each_step": head["host_us_each_step"]}
         if secondary is not None:
             line["secondary"] = secondary
         print(json.dumps(line))

@@ -101,6 +101,12 @@ typedef struct b200opt_options {
   int32_t linear_solver;      /* least squares only: B200OPT_LINSOLVE_* (the `linear_solver=` field of LevenbergMarquardt /
                                * GaussNewton, levenberg_marquardt.py:286, gauss_newton.py:387) */
   int32_t data_dtype;         /* least squares only: B200OPT_DATA_* - storage type of the per-problem data rows */
+  void* scratch;              /* optional: >= 8 bytes of DEVICE memory, 8-byte aligned, that this call may use (the ticket counter of
+                               * the dynamic problem queue; zeroed by the library in stream order, free again when the call's work on
+                               * the stream is done).  NULL: the library takes the bytes from the stream-ordered allocator
+                               * (cudaMallocAsync / cudaFreeAsync) - correct, but the default pool gives its memory back at every
+                               * synchronisation, so the first launch after a sync then pays for a fresh allocation (0.5 - 10 ms).
+                               * An XLA FFI handler passes its ScratchAllocator's buffer, PyTorch callers a caching-allocator tensor. */
 } b200opt_options_t;
 
 /* Storage type of `problem_args` of b200opt_least_squares(_host).  AS_COMPUTE: the compute dtype (the default).  F16 / U16 /

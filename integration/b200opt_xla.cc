@@ -35,6 +35,7 @@ static ffi::Error LeastSquaresImpl(cudaStream_t stream, int32_t solver, int32_t 
   const int32_t n = (int32_t)y0.dimensions()[1], m = (int32_t)prob.dimensions()[1];
   b200opt_options_t o = options(rtol, atol, norm, max_steps);
   o.linear_solver = linear_solver, o.data_dtype = data_dtype;
+  o.scratch = nullptr;  // or 8 bytes from the handler's ffi::ScratchAllocator (include/b200opt.h: b200opt_options_t.scratch)
   return status(b200opt_least_squares(solver, model_id, dtype_of(y0.element_type()), B, n, m, y0.untyped_data(), shared.untyped_data(),
                                       prob.untyped_data(), m, &o, y->untyped_data(), num_steps->typed_data(), result->typed_data(),
                                       nullptr, nullptr, stream));

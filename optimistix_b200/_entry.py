@@ -326,6 +326,8 @@ def least_squares(fn, solver, y0, args=None, options=None, *, has_aux=False, max
     if buf.device:
         step_size = buf.empty((B,), y0)
         nacc = buf.empty_i32((B,), y0)
+        scratch = buf.empty_i32((2,), y0)  # options.scratch: the launch's problem-queue counter (caching allocator, stream-ordered reuse)
+        opts.scratch = scratch.data_ptr()
         with _on_device_of(buf, y0):
             code = lib.b200opt_least_squares(solver_id, fn.model_id, buf.dtype_code, B, n, m, buf.ptr(y0), buf.ptr(shared),
                                              buf.ptr(prob), m, C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res),
@@ -532,6 +534,8 @@ def minimise(fn, solver, y0, args=None, options=None, *, has_aux=False, max_step
         f_out = buf.empty((B,), y0)
         nacc = buf.empty_i32((B,), y0)
         hinv = buf.empty((B, n, n), y0) if return_hessian_inv else None
+        scratch = buf.empty_i32((2,), y0)  # options.scratch (see least_squares)
+        opts.scratch = scratch.data_ptr()
         with _on_device_of(buf, y0):
             code = lib.b200opt_minimise(_lib.SOLVER_BFGS, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), None, None, 0,
                                         C.byref(opts), buf.ptr(y_out), buf.ptr(steps), buf.ptr(res), buf.ptr(f_out),

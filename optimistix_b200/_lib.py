@@ -29,6 +29,7 @@ class Options(C.Structure):
         ("kappa", C.c_double),
         ("linear_solver", C.c_int32),
         ("data_dtype", C.c_int32),
+        ("scratch", C.c_void_p),
     ]
 
 
@@ -151,10 +152,10 @@ def linear_solver_id(linear_solver) -> int:
 
 
 def make_options(rtol, atol, norm="max", max_steps=256, cauchy_termination=True, root_near_zero=False, kappa=1e-2, linear_solver=None,
-                 data_dtype=0):
+                 data_dtype=0, scratch=None):
     if isinstance(norm, str):
         norm_id = NORM_IDS[norm]
     else:
         norm_id = NORM_IDS[getattr(norm, "norm_name")]
     return Options(float(rtol), float(atol), norm_id, int(max_steps), int(bool(cauchy_termination)), int(bool(root_near_zero)), float(kappa),
-                   linear_solver_id(linear_solver), int(data_dtype))
+                   linear_solver_id(linear_solver), int(data_dtype), scratch)

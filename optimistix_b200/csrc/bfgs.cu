@@ -30,7 +30,7 @@ static int min_launch(int64_t batch, int n, const void* y0, const b200opt_option
   QueueCounter qc;
   p.queue = nullptr;
   if (batch > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh)
-    qc.acquire(stream);
+    qc.acquire(stream, o->scratch);
     p.queue = qc.ptr;
   }
   kern<<<grid, kBfgsThreads, 0, stream>>>(p);

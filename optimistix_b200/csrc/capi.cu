@@ -415,6 +415,7 @@ void b200opt_default_options(b200opt_options_t* o) {
   o->kappa = 1e-2;
   o->linear_solver = B200OPT_LINSOLVE_NORMAL_CHOLESKY;
   o->data_dtype = B200OPT_DATA_AS_COMPUTE;
+  o->scratch = nullptr;
 }
 
 int32_t b200opt_least_squares(int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n, int32_t m,

@@ -242,10 +242,11 @@ struct QueueCounter {
   unsigned long long* ptr = nullptr;
   cudaStream_t stream = nullptr;
   bool owned = false;
-  void acquire(cudaStream_t s) {
+  void acquire(cudaStream_t s, void* caller_scratch = nullptr) {
     stream = s;
-    if (g_queue_scratch != nullptr) {  // caller-owned scratch: zero it in stream order, nothing to free
-      if (cudaMemsetAsync(g_queue_scratch, 0, sizeof(unsigned long long), s) == cudaSuccess) ptr = g_queue_scratch;
+    unsigned long long* lent = g_queue_scratch != nullptr ? g_queue_scratch : static_cast<unsigned long long*>(caller_scratch);
+    if (lent != nullptr) {  // caller-owned scratch (b200opt_options_t.scratch, or the host pipeline's slab): zero it in stream order
+      if (cudaMemsetAsync(lent, 0, sizeof(unsigned long long), s) == cudaSuccess) ptr = lent;
       else cudaGetLastError();
       return;
     }

@@ -212,7 +212,7 @@ int lsq_launch_jit(const LsqArgs& a, int model_id) {
     QueueCounter qc;
     p.queue = nullptr;
     if (need > 4 * cap) {
-      qc.acquire(a.stream);
+      qc.acquire(a.stream, a.opts->scratch);
       p.queue = qc.ptr;
     }
     void* params[] = {&p};

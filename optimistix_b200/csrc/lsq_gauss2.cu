@@ -20,7 +20,7 @@ template <class PModel, bool TRUST, int NPAIRS> static int lsq_launch_p2(const L
   LsqParams<float> pq = p;
   pq.queue = nullptr;
   if (need > 4 * cap) {  // dynamic problem queue after the first resident wave (common.cuh); not worth its set-up for a wave or two
-    qc.acquire(stream);
+    qc.acquire(stream, p.queue);  // p.queue carries the caller's scratch (options.scratch), or NULL
     pq.queue = qc.ptr;
   }
   kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
@@ -52,6 +52,7 @@ int lsq_launch_gauss2(const LsqArgs& a) {
     p.root_near_zero = 0;
     p.vec_ok = 1;
     p.data_kind = a.opts->data_dtype;
+    p.queue = static_cast<unsigned long long*>(a.opts->scratch);
     p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
     const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
     int rc;

@@ -38,7 +38,7 @@ template <class Model, typename T, bool TRUST, bool QRMODE = false> int lsq_laun
   pq.queue = nullptr;
   if (need > 4 * cap) {  // several waves of problems: later ones are handed out dynamically (a launch of a wave or two runs
                          // ~0.1 ms: the stream-ordered counter allocation would cost more than the balance gains)
-    qc.acquire(stream);
+    qc.acquire(stream, p.queue);  // p.queue carries the caller's scratch (options.scratch), or NULL
     pq.queue = qc.ptr;
   }
   kern<<<grid, kLsqWarpsPerBlock * 32, smem, stream>>>(pq);
@@ -76,6 +76,7 @@ template <template <typename> class ModelT, typename T> int lsq_launch_typed(con
   constexpr int V = Num<T>::kVec;
   p.vec_ok = (a.m % V == 0) && (a.prob_stride % V == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % (V * sizeof(T))) == 0);
   p.data_kind = a.opts->data_dtype;
+  p.queue = static_cast<unsigned long long*>(a.opts->scratch);
   p.data_vec = (a.m % 8 == 0) && (a.prob_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.prob) % 16) == 0);
   const bool lm = a.solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
   if (a.opts->linear_solver == B200OPT_LINSOLVE_QR)  // the reference's own linear algebra (see lsq_kernel.cuh, QR mode)

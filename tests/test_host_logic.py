@@ -24,6 +24,7 @@ def test_options_struct_matches_the_library():
     lib.b200opt_default_options(C.byref(o))
     assert (o.rtol, o.atol, o.norm, o.max_steps, o.cauchy_termination, o.root_near_zero, o.kappa) == (1e-8, 1e-8, 0, 256, 1, 0, 1e-2)
     assert (o.linear_solver, o.data_dtype) == (_lib.LINSOLVE_NORMAL_CHOLESKY, _lib.DATA_AS_COMPUTE)
+    assert o.scratch is None  # NULL: the library takes the queue counter from the stream-ordered allocator
     assert all(b == 0xAB for b in bytes(raw)[C.sizeof(_lib.Options):]), "the library wrote past the struct the binding declares"
     with open(_lib.HEADER_PATH) as fh:
         header = fh.read()

@@ -435,6 +435,34 @@ def test_sixteen_bit_data_fp64_and_ragged_alignment():
     assert torch.equal(y, ref.value) and torch.equal(steps, ref.stats["num_steps"])
 
 
+def test_caller_scratch_for_the_problem_queue():
+    """b200opt_options_t.scratch: with a launch large enough for the dynamic problem queue (> 4 resident waves) the ticket counter
+    lives in caller memory instead of a stream-ordered allocation; results do not depend on it (nor on the hand-out order)."""
+    import ctypes as C
+
+    from optimistix_b200 import _lib
+
+    lib = _lib.load()
+    w = synthetic.gauss2_batch(20000, seed=5)
+    ty0, tx, td = _cuda(w["y0"]), _cuda(w["x"]), _cuda(w["d"])
+    outs = []
+    for use_scratch in (False, True, True):
+        scratch = torch.full((2,), -1, dtype=torch.int32, device=DEV)  # not zero: the library must zero it itself
+        opts = _lib.make_options(1e-4, 1e-4, "max", 256, scratch=scratch.data_ptr() if use_scratch else None)
+        y = torch.empty_like(ty0)
+        steps = torch.empty(20000, dtype=torch.int32, device=DEV)
+        res = torch.empty(20000, dtype=torch.int32, device=DEV)
+        _lib.check(lib.b200opt_least_squares(_lib.SOLVER_LM, optx.models.gauss2.model_id, _lib.F32, 20000, 8, 256, ty0.data_ptr(), tx.data_ptr(),
+                                             td.data_ptr(), 256, C.byref(opts), y.data_ptr(), steps.data_ptr(), res.data_ptr(), None, None,
+                                             torch.cuda.current_stream().cuda_stream), "least_squares with caller scratch")
+        torch.cuda.synchronize()
+        if use_scratch:  # 20000 problems, 2368 resident warps: every later problem was a ticket
+            assert int(scratch.view(torch.int64).item()) >= 20000 - 2368
+        outs.append((y, steps, res))
+    for y, steps, res in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(steps, outs[0][1]) and torch.equal(res, outs[0][2])
+
+
 def test_pageable_inputs_are_staged_by_the_copy_pool():
     """Host entry point with ordinary (pageable) NumPy arrays large enough to be staged through the page-locked slab by the
     helper threads (>= 1 MiB per chunk), odd chunk sizes, repeated calls: bit-identical to the device-pointer path."""

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 verification on one B200: full GPU test suite, smoke, the bench line, the reference arm, launch lists and
 # `ncu --set full` captures of the kernels that changed this round (each only after the same command exited 0 without ncu).
-R=${1:-r2i}
+R=${1:-r2z}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/pytest_$R.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_$R.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke_$R.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/smoke_$R.log
@@ -20,6 +20,8 @@ ncu --set full --clock-control none --import-source on -k regex:gn_step_kernel -
 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 14 -c 1 -f -o gpurun_out/gramstate_$R python tools/gram_api_probe.py --rows 8388608 --iters 4 --reps 1 > gpurun_out/ncu_gram_$R.log 2>&1; echo "gram $?"
 python bench.py --workload bfgs --batch 4096 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_bfgs_$R.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:bfgs_solve_kernel -s 3 -c 1 -f -o gpurun_out/bfgs_$R python bench.py --workload bfgs --batch 4096 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_bfgs_$R.log 2>&1; echo "bfgs $?"
+python bench.py --workload newton --batch 32768 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_newton_$R.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:root_solve_kernel -s 3 -c 1 -f -o gpurun_out/newton_$R python bench.py --workload newton --batch 32768 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_newton_$R.log 2>&1; echo "newton $?"
 python bench.py --workload exp_decay --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_exp_$R.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:lsq_solve_kernel -s 3 -c 1 -f -o gpurun_out/lsqexp_$R python bench.py --workload exp_decay --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_exp_$R.log 2>&1; echo "exp $?"
 tail -3 gpurun_out/pytest_$R.log; tail -2 gpurun_out/smoke_$R.log
