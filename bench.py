@@ -130,8 +130,20 @@ class ClockSampler:
         self._stop.set()
         if self._thr:
             self._thr.join()
+        note = None
+        if self.nv is not None and not self.samples:
+            # the timed region was shorter than the sampling period: one query right at its end (the SM clock of a GPU that was
+            # busy microseconds ago; the reasons mask is the current one)
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                note = "timed region shorter than the 20 ms sampling period: sampled once at its end"
+            except Exception:  # noqa: BLE001
+                pass
         if self.nv is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        if note:
+            return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(self.samples), "note": note}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
 
