@@ -554,9 +554,13 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
     }
     if (result == RES_OK && !terminate) result = RES_NL_MAX_STEPS;
 
+    {  // lane j stores y[j]: a select chain and ONE coalesced store (`if (lane == j) y_out[j] = y[j]` compiles to a jump table
+       // whose N divergent paths cost 3.6 % of the kernel's stall samples, profiles/lsq_r2z)
+      T yv = y[0];
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (lane == j) p.y_out[prob * N + j] = y[j];
+      for (int j = 1; j < N; ++j) yv = (lane == j) ? y[j] : yv;
+      if (lane < N) p.y_out[prob * N + lane] = yv;
+    }
     if (lane == 0) {
       p.num_steps[prob] = steps;
       p.result[prob] = result;
