@@ -458,6 +458,22 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
         bool fconv = true;
         const float2* racc2 = reinterpret_cast<const float2*>(racc);
         constexpr int SPLIT = LSQ_P2_SPLIT;
+        if ((LSQ_P2_OPT & 4) && yconv) {
+          // f-space half of the Cauchy test, only when the y-space half passed (terminate needs both): its own loop, ahead of
+          // the sweeps - one warp-uniform branch per accepted step (inside the sweep it was a reconvergence point per row pair),
+          // and before the first half-sweep reuses the old residuals' slot
+          auto f_pair = [&](int k) {
+            const int idx = k * 32 + lane;
+            const float2 re = rtry2[idx], ro = racc2[idx];
+            fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
+          };
+          if (NPAIRS > 0) {
+#pragma unroll
+            for (int k = 0; k < (NPAIRS > 0 ? NPAIRS : 1); ++k) f_pair(k);
+          } else {
+            for (int k = 0; k < npairs; ++k) f_pair(k);
+          }
+        }
 #pragma unroll
         for (int half = 0; half < (SPLIT > 0 ? 2 : 1); ++half) {
           float2 acc2[NG + N];
@@ -481,7 +497,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
                   acc2[Tri<N>::at(a, b)] = init ? mul2(j[a], j[b]) : fma2(j[a], j[b], acc2[Tri<N>::at(a, b)]);
               if (p2_half<PModel>(a, N) == half) acc2[NG + a] = init ? mul2(j[a], re) : fma2(j[a], re, acc2[NG + a]);
             }
-            if (half == 0 && (!(LSQ_P2_OPT & 4) || yconv)) {
+            if (half == 0 && !(LSQ_P2_OPT & 4)) {
               const float2 ro = racc2[idx];
               fconv = fconv && (t_abs(re.x - ro.x) < atol + rtol * t_abs(re.x)) && (t_abs(re.y - ro.y) < atol + rtol * t_abs(re.y));
             }
