@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kLsqWarpsPerBlock * 32, LSQ_P2_MINBLOCKS) lsq_
       bool accept = true;
       T rre;
       T lin = T(0), quad = T(0);
-      if (TRUST && (LSQ_P2_FAST & 2) && !(LSQ_P2_FAST & 8) && (LSQ_P2_OPT & 1)) {
+      if (TRUST && (LSQ_P2_FAST & 2) && !(LSQ_P2_FAST & 8) && (LSQ_P2_OPT & 1) && !first) {  // first step: d = 0, G = 0, g = 0: lin = quad = 0
         // 0.5 d.G d = sum_i d_i (0.5 G_ii d_i + sum_{j<i} G_ij d_j), its rows issued between the rounds of the ||r||^2 butterfly
         T hq = T(0);
         auto quad_row = [&](int i) {
