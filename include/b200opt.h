@@ -217,7 +217,7 @@ int32_t b200opt_minimise_host(int32_t device, int32_t solver, int32_t model_id, 
 
 /* ---- generic per-iteration step for an arbitrary user `fn` (J and r computed by the caller) ------------
  * One call = one AbstractGaussNewton.step + the driver bookkeeping of _iterate.py:234-241 for every
- * still-running problem; n <= 64 (n <= 16: one warp per problem, Gram in registers; 16 < n <= 64: one CTA per problem, Gram
+ * still-running problem; n <= 64 (n <= 16, fp64: n <= 8: one warp per problem, Gram in registers; up to n = 64: one CTA per problem, Gram
  * in shared memory).  `state` is an opaque per-problem carry of b200opt_lsq_step_state_size(dtype,n,m)
  * bytes per problem, zero-initialised by b200opt_lsq_step_init.
  *   r_eval [batch][m], J_eval [batch][m][n]: residual and Jacobian at y_eval (as written by the last call)

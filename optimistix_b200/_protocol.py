@@ -180,7 +180,8 @@ class LsqSession(_Session):
                                              self.y_eval_buf.data_ptr(), self.state.data_ptr(), self.steps.data_ptr(), self.res.data_ptr(),
                                              self._stream()), "b200opt_lsq_step_init")
         # layout of the carry (csrc/lsq_step.cu): [G packed lower | g | rr | delta | first | terminate | num_accepted | r_accepted]
-        self.np_ = 4 if self.n <= 4 else 8 if self.n <= 8 else 16 if self.n <= 16 else 0
+        # csrc/lsq_step.cu pad_n: register kernel for n padded to 4 / 8 / 16 (16: fp32 only), 0 = the CTA kernel
+        self.np_ = 4 if self.n <= 4 else 8 if self.n <= 8 else 16 if (self.n <= 16 and self.dtype_code == _lib.F32) else 0
 
     def body(self):
         rr, JJ = self._first if self._first is not None else self.rj(self.y_eval_buf)

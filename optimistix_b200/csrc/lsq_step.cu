@@ -403,10 +403,12 @@ template <typename T> __global__ void lsq_step_finish_kernel(int64_t batch, int6
   if (result[prob] == RES_OK && !terminate) result[prob] = RES_NL_MAX_STEPS;  // _iterate.py:253-257
 }
 
-static int pad_n(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 0)); }
+// register kernel: n padded to 4 / 8 / 16; 0 = CTA kernel.  fp64 with 8 < n <= 16 takes the CTA kernel too: 136 + 16 packed Gram
+// doubles per thread do not fit the register file (the <double, 16> instantiation spilled 20 KB per thread).
+static int pad_n(int n, bool f64) { return n <= 4 ? 4 : (n <= 8 ? 8 : ((n <= 16 && !f64) ? 16 : 0)); }
 static int head_for(int np) { return np == 4 ? step_state_head<4>() : (np == 8 ? step_state_head<8>() : step_state_head<16>()); }
 // state head (elements before the accepted residuals) for any supported n: register kernel up to 16, CTA kernel up to 64
-static int head_any(int n) { return pad_n(n) ? head_for(pad_n(n)) : big_state_head(n); }
+static int head_any(int n, bool f64) { return pad_n(n, f64) ? head_for(pad_n(n, f64)) : big_state_head(n); }
 
 template <typename T, int NP> static int step_launch(const StepParams<T>& p, cudaStream_t stream) {
   auto kern = lsq_step_kernel<T, NP>;
@@ -421,9 +423,9 @@ template <typename T, int NP> static int step_launch(const StepParams<T>& p, cud
 template <typename T>
 static int step_typed(int solver, int64_t batch, int n, int m, const void* r_eval, const void* J_eval, void* y, void* y_eval,
                       void* state, const b200opt_options_t* o, int32_t* num_steps, int32_t* result, int32_t* active, cudaStream_t st) {
-  const int np = pad_n(n);
+  const int np = pad_n(n, sizeof(T) == 8);
   StepParams<T> p;
-  const int head_sel = head_any(n);
+  const int head_sel = head_any(n, sizeof(T) == 8);
   p.r_eval = static_cast<const T*>(r_eval);
   p.J_eval = static_cast<const T*>(J_eval);
   p.y = static_cast<T*>(y);
@@ -443,14 +445,16 @@ static int step_typed(int solver, int64_t batch, int n, int m, const void* r_eva
   p.root_near_zero = o->root_near_zero;
   p.trust = solver == B200OPT_SOLVER_LEVENBERG_MARQUARDT;
   if (active && check_cuda(cudaMemsetAsync(active, 0, sizeof(int32_t), st), "memset active_count")) return B200OPT_ECUDA;
-  if (np == 0) {  // 16 < n <= 64
+  if (np == 0) {  // 16 < n <= 64 (fp64: 8 < n <= 64)
     const size_t smem = sizeof(T) * ((size_t)n * (n + 1) + 3 * (size_t)n);
     lsq_step_big_kernel<T><<<(unsigned)batch, kBigThreads, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "lsq_step_big_kernel launch");
   }
   if (np == 4) return step_launch<T, 4>(p, st);
   if (np == 8) return step_launch<T, 8>(p, st);
-  return step_launch<T, 16>(p, st);
+  if constexpr (sizeof(T) == 4) return step_launch<T, 16>(p, st);
+  set_error("lsq_step: internal dispatch error (n=%d)", n);
+  return B200OPT_EINVAL;
 }
 }  // namespace b200opt
 
@@ -472,14 +476,14 @@ extern "C" {
 
 int64_t b200opt_lsq_step_state_size(int32_t dtype, int32_t n, int32_t m) {
   if (step_check("lsq_step_state_size", dtype, 0, n, m)) return -1;
-  return step_state_stride(head_any(n), m) * (dtype == B200OPT_F32 ? 4 : 8);
+  return step_state_stride(head_any(n, dtype == B200OPT_F64), m) * (dtype == B200OPT_F32 ? 4 : 8);
 }
 
 int32_t b200opt_lsq_step_init(int32_t dtype, int64_t batch, int32_t n, int32_t m, const void* y0, void* y, void* y_eval,
                               void* state, int32_t* num_steps, int32_t* result, void* stream) {
   if (int e = step_check("lsq_step_init", dtype, batch, n, m)) return e;
   if (batch == 0) return 0;
-  const int head = head_any(n);
+  const int head = head_any(n, dtype == B200OPT_F64);
   const int64_t stride = step_state_stride(head, m);
   const int ng_np = head - 5;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -522,7 +526,7 @@ int32_t b200opt_lsq_step_finish(int32_t dtype, int64_t batch, int32_t n, int32_t
                                 void* stream) {
   if (int e = step_check("lsq_step_finish", dtype, batch, n, m)) return e;
   if (batch == 0) return 0;
-  const int head = head_any(n);
+  const int head = head_any(n, dtype == B200OPT_F64);
   const int64_t stride = step_state_stride(head, m);
   const int term_off = head - 5 + 3;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -379,20 +379,22 @@ def test_root_find_via_lm_n28(idx):
     assert np.allclose(to_np(sol.value), ref["value"][0], rtol=1e-6, atol=1e-10)
 
 
-def test_generic_lm_step_kernels_agree_across_the_size_boundary():
-    """The same 16-parameter problem through the register kernel (n = 16) and, padded with a decoupled 17th unknown, through
-    the CTA kernel (n = 17): identical iteration counts, the same solution."""
+@pytest.mark.parametrize("dtype,n,tol", [(torch.float32, 16, 1e-5), (torch.float64, 8, 1e-9), (torch.float64, 16, 1e-9)])
+def test_generic_lm_step_kernels_agree_across_the_size_boundary(dtype, n, tol):
+    """The same n-parameter problem through one step kernel and, padded with a decoupled (n + 1)-th unknown, through the next:
+    fp32 n = 16 (register kernel) vs 17 (CTA kernel); fp64 n = 8 (register kernel) vs 9 (CTA kernel: the packed fp64 Gram of 16
+    unknowns does not fit a thread's registers); fp64 16 vs 17 (both in the CTA kernel).  Same result code, same solution."""
     g = torch.Generator(device=DEV).manual_seed(2)
-    A = torch.randn(40, 16, generator=g, dtype=torch.float64, device=DEV)
-    b = torch.randn(40, generator=g, dtype=torch.float64, device=DEV)
-    f16 = lambda y, _: torch.tanh(A @ y) - 0.3 * b
-    f17 = lambda y, _: torch.cat([torch.tanh(A @ y[:16]) - 0.3 * b, y[16:] - 2.0])
-    s16 = optx.least_squares(f16, optx.LevenbergMarquardt(1e-9, 1e-9), torch.zeros(16, dtype=torch.float64, device=DEV), None, throw=False,
-                             max_steps=1000)
-    s17 = optx.least_squares(f17, optx.LevenbergMarquardt(1e-9, 1e-9), torch.zeros(17, dtype=torch.float64, device=DEV), None, throw=False,
-                             max_steps=1000)
-    assert _res_name(s16) == _res_name(s17) == "successful"
-    assert torch.allclose(s17.value[:16], s16.value, rtol=1e-6, atol=1e-8) and abs(float(s17.value[16]) - 2.0) < 1e-8
+    A = torch.randn(40, n, generator=g, dtype=torch.float64, device=DEV).to(dtype)
+    b = torch.randn(40, generator=g, dtype=torch.float64, device=DEV).to(dtype)
+    fa = lambda y, _: torch.tanh(A @ y) - 0.3 * b
+    fb = lambda y, _: torch.cat([torch.tanh(A @ y[:n]) - 0.3 * b, y[n:] - 2.0])
+    sa = optx.least_squares(fa, optx.LevenbergMarquardt(tol, tol), torch.zeros(n, dtype=dtype, device=DEV), None, throw=False, max_steps=1000)
+    sb = optx.least_squares(fb, optx.LevenbergMarquardt(tol, tol), torch.zeros(n + 1, dtype=dtype, device=DEV), None, throw=False,
+                            max_steps=1000)
+    assert _res_name(sa) == _res_name(sb) == "successful"
+    loose = 1e-6 if dtype == torch.float64 else 2e-3
+    assert torch.allclose(sb.value[:n], sa.value, rtol=loose, atol=loose) and abs(float(sb.value[n]) - 2.0) < loose
 
 
 # ---- Newton / Chord beyond n = 32: one CTA per problem, the Jacobian in shared memory (the reference has no size limit,
