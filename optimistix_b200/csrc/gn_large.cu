@@ -311,13 +311,23 @@ __device__ void fast_tri_solves(FastSmem& fs) {
     }
     __syncthreads();
     if (tid < 32) fs.rhs[32 * k + tid] = fs.zk[tid];
-    // rhs_i -= L_ik z_k for the block rows below: warp w takes rows w, w + 32, ...
+    // rhs_i -= L_ik z_k for the block rows below: one thread per row (128-bit loads of the row: conflict free at pitch 36, z_k as
+    // broadcasts) - a warp per row with a shuffle reduction took up to seven rounds of ~200 cycles per block column
     const int R = 32 * (FNB - 1 - k);
-    for (int r = warp; r < R; r += 32) {
-      const int ib = k + 1 + (r >> 5), rr = r & 31;
-      float v = fs.S[fblk(ib, k) + rr * FP + lane] * fs.zk[lane];
-      v = warp_sum(v);
-      if (lane == 0) fs.rhs[32 * ib + rr] -= v;
+    if (tid < R) {
+      const int ib = k + 1 + (tid >> 5), rr = tid & 31;
+      const float* Lr = fs.S + fblk(ib, k) + rr * FP;
+      float acc = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 l = *reinterpret_cast<const float4*>(Lr + 4 * c4);
+        const float4 z = *reinterpret_cast<const float4*>(fs.zk + 4 * c4);
+        acc = fmaf(l.x, z.x, acc);
+        acc = fmaf(l.y, z.y, acc);
+        acc = fmaf(l.z, z.z, acc);
+        acc = fmaf(l.w, z.w, acc);
+      }
+      fs.rhs[32 * ib + rr] -= acc;
     }
     __syncthreads();
   }
