@@ -209,6 +209,16 @@ int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id,
                                int32_t n, const void* y0, const void* shared_args, int64_t shared_args_count,
                                const void* problem_args, int64_t problem_args_stride, const b200opt_options_t* opts,
                                void* y_out, int32_t* num_steps, int32_t* result, int64_t chunk);
+/* As b200opt_root_find_host, with the per-problem arguments given as `n_parts` (<= 4) separate host arrays - part p is
+ * [batch][part_elems[p]], contiguous - which the family's layout concatenates per problem (implicit_euler: y_prev [n], dt [1];
+ * the arguments of the reference's fn(y, args) stay the arrays the caller already has).  The pipeline copies the parts as they
+ * are and a copy kernel lays them out as [chunk][problem_args_stride] on the device (unused trailing elements of a row are
+ * zero): no packing pass over the host arrays (71 MB per call for configs[2]). */
+int32_t b200opt_root_find_host_parts(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch,
+                                     int32_t n, const void* y0, const void* shared_args, int64_t shared_args_count,
+                                     const void* const* parts, const int32_t* part_elems, int32_t n_parts,
+                                     int64_t problem_args_stride, const b200opt_options_t* opts, void* y_out,
+                                     int32_t* num_steps, int32_t* result, int64_t chunk);
 void b200opt_host_cache_release(void);
 int32_t b200opt_minimise_host(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
                               const void* y0, const void* shared_args, int64_t shared_args_count,

@@ -408,9 +408,17 @@ def root_find(fn, solver, y0, args=None, options=None, *, has_aux=False, max_ste
             raise NotImplementedError("lower/upper bounds are only wired on the device-pointer entry point")
         t = _torch()
         device = t.cuda.current_device() if t.cuda.is_available() else 0
-        code = lib.b200opt_root_find_host(device, solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared),
-                                          int(shared.shape[0]), buf.ptr(prob), stride, C.byref(opts), buf.ptr(y_out),
-                                          buf.ptr(steps), buf.ptr(res), int(chunk))
+        if isinstance(prob, _HostParts):
+            k = len(prob.arrays)
+            ptrs = (C.c_void_p * k)(*[buf.ptr(x) for x in prob.arrays])
+            elems = (C.c_int32 * k)(*prob.elems)
+            code = lib.b200opt_root_find_host_parts(device, solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared),
+                                                    int(shared.shape[0]), ptrs, elems, k, stride, C.byref(opts), buf.ptr(y_out),
+                                                    buf.ptr(steps), buf.ptr(res), int(chunk))
+        else:
+            code = lib.b200opt_root_find_host(device, solver_id, fn.model_id, buf.dtype_code, B, n, buf.ptr(y0), buf.ptr(shared),
+                                              int(shared.shape[0]), buf.ptr(prob), stride, C.byref(opts), buf.ptr(y_out),
+                                              buf.ptr(steps), buf.ptr(res), int(chunk))
     _lib.check(code, "b200opt_root_find")
     y_out = _attach_registered(adjoint, "root", fn, a, y_out, buf)
     return _finish(buf, single, throw, y_out, steps, res, max_steps)
@@ -421,6 +429,13 @@ def _bound(buf, b, n, dev):
         t = _torch()
         return t.broadcast_to(t.as_tensor(b, dtype=buf.tdtype, device=dev), (n,)).contiguous()
     return np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=buf.ndtype), (n,)))
+
+
+class _HostParts:
+    """Per-problem arguments as separate host arrays (part p: [B, elems[p]]) for b200opt_root_find_host_parts."""
+
+    def __init__(self, arrays, elems):
+        self.arrays, self.elems = arrays, elems
 
 
 def _pack_root_args(fn, a, buf, dev, B, n, single):
@@ -456,13 +471,10 @@ def _pack_root_args(fn, a, buf, dev, B, n, single):
         prob[:, n] = dt
         prob[:, n + 1] = 0
     else:
-        t = _torch()
+        # host buffers: the two per-problem arrays go to the C pipeline as they are (b200opt_root_find_host_parts lays them out
+        # as [y_prev | dt | pad] rows on the device); packing them here was 71 MB of host copies per call for configs[2]
         shared = np.concatenate([A.reshape(-1), Bm.reshape(-1)])
-        prob = _host_empty((B, stride), buf.ndtype)
-        pt = t.from_numpy(prob)  # torch's copy kernels are multi-threaded; numpy slice assignment is not
-        pt[:, :n].copy_(t.from_numpy(y_prev))
-        pt[:, n].copy_(t.from_numpy(dt))
-        pt[:, n + 1].zero_()
+        prob = _HostParts([np.ascontiguousarray(y_prev), np.ascontiguousarray(dt)], [n, 1])
     return shared, prob, stride
 
 

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "b200opt_minimise": (_i32, [_i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200opt_least_squares_host": (_i32, [_i32, _i32, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _i64]),
     "b200opt_root_find_host": (_i32, [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _i64]),
+    "b200opt_root_find_host_parts": (_i32, [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(C.c_int32), _i32, _i64,
+                                            C.POINTER(Options), _vp, _vp, _vp, _i64]),
     "b200opt_minimise_host": (_i32, [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, C.POINTER(Options), _vp, _vp, _vp, _i64]),
     "b200opt_host_cache_release": (None, []),
     "b200opt_lsq_step_state_size": (_i64, [_i32, _i32, _i32]),

@@ -266,7 +266,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   for (size_t i = 0; i < ins.size(); ++i) {
     in_off[i] = dev_need, dev_need += align256(ins[i].bytes_per_problem * chunk);
     // a pageable input that is worth it (>= 1 MiB per chunk) is staged through page-locked memory by the copy pool
-    in_staged[i] = ins[i].bytes_per_problem * (size_t)chunk >= ((size_t)1 << 20) && !is_pinned(ins[i].h);
+    in_staged[i] = ins[i].h != nullptr && ins[i].bytes_per_problem * (size_t)chunk >= ((size_t)1 << 20) && !is_pinned(ins[i].h);
     if (in_staged[i]) stage_off[i] = pin_in_need, pin_in_need += align256(ins[i].bytes_per_problem * chunk);
   }
   const size_t queue_off = dev_need;  // 8 bytes per stream for the ticket counter of the dynamic problem queue
@@ -342,7 +342,7 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
     bool staged_any = false;
     for (size_t i = 0; i < ins.size(); ++i) {
       d_in[i] = base + in_off[i];
-      if (!ins[i].bytes_per_problem) continue;
+      if (!ins[i].bytes_per_problem || !ins[i].h) continue;  // h == NULL: device-only scratch of that size per problem
       const char* src = static_cast<const char*>(ins[i].h) + ins[i].bytes_per_problem * off;
       if (in_staged[i]) {
         if (in_busy[s] && !staged_any) {  // the copy engine may still be reading this slot's previous contents
@@ -379,6 +379,27 @@ static int host_pipeline(const char* who, int device, int64_t batch, int64_t chu
   return check_cuda(cudaGetLastError(), who);
 }
 
+// rows [nb][stride] from up to four per-problem part arrays (b200opt_root_find_host_parts); unused trailing elements are zero
+struct PackParts {
+  const void* src[4];
+  int elems[4];
+  int n;
+};
+template <typename T> __global__ void pack_parts_kernel(T* dst, int64_t stride, int64_t nb, PackParts pp) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nb * stride) return;
+  const int64_t prob = e / stride;
+  int j = (int)(e - prob * stride);
+  T v = T(0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q < pp.n) {
+      if (j >= 0 && j < pp.elems[q]) v = static_cast<const T*>(pp.src[q])[prob * pp.elems[q] + j];
+      j -= pp.elems[q];
+    }
+  }
+  dst[e] = v;
+}
 }  // namespace b200opt
 
 using namespace b200opt;
@@ -512,6 +533,49 @@ int32_t b200opt_root_find_host(int32_t device, int32_t solver, int32_t model_id,
       [&](int64_t nb, const void* d_shared, const void** d_in, void** d_out, cudaStream_t st) {
         return b200opt_root_find(solver, model_id, dtype, nb, n, d_in[0], d_shared, d_in[1], problem_args_stride, nullptr,
                                  nullptr, opts, d_out[0], static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), st);
+      });
+}
+
+int32_t b200opt_root_find_host_parts(int32_t device, int32_t solver, int32_t model_id, int32_t dtype, int64_t batch, int32_t n,
+                                     const void* y0, const void* shared_args, int64_t shared_args_count, const void* const* parts,
+                                     const int32_t* part_elems, int32_t n_parts, int64_t problem_args_stride,
+                                     const b200opt_options_t* opts, void* y_out, int32_t* num_steps, int32_t* result, int64_t chunk) {
+  if (int e = validate_common("root_find_host_parts", dtype, batch, opts)) return e;
+  if (batch == 0) return 0;
+  if (!y0 || !shared_args || !parts || !part_elems || !y_out || !num_steps || !result || n_parts < 1 || n_parts > 4) {
+    set_error("root_find_host_parts: NULL buffer or n_parts outside 1..4");
+    return B200OPT_EINVAL;
+  }
+  int64_t total = 0;
+  for (int q = 0; q < n_parts; ++q) {
+    if (!parts[q] || part_elems[q] < 1) {
+      set_error("root_find_host_parts: part %d is NULL or empty", q);
+      return B200OPT_EINVAL;
+    }
+    total += part_elems[q];
+  }
+  if (total > problem_args_stride) {
+    set_error("root_find_host_parts: the parts hold %lld elements per problem, the stride is %lld", (long long)total,
+              (long long)problem_args_stride);
+    return B200OPT_EINVAL;
+  }
+  const size_t es = dtype == B200OPT_F32 ? 4 : 8;
+  std::vector<HostIn> ins = {{y0, es * n}, {nullptr, es * (size_t)problem_args_stride}};  // [1]: the packed rows, device only
+  for (int q = 0; q < n_parts; ++q) ins.push_back({parts[q], es * (size_t)part_elems[q]});
+  return host_pipeline(
+      "root_find_host_parts", device, batch, chunk, shared_args, es * shared_args_count, ins, {{y_out, es * n}, {num_steps, 4}, {result, 4}},
+      [&](int64_t nb, const void* d_shared, const void** d_in, void** d_out, cudaStream_t st) {
+        PackParts pp;
+        pp.n = n_parts;
+        for (int q = 0; q < 4; ++q) pp.src[q] = q < n_parts ? d_in[2 + q] : nullptr, pp.elems[q] = q < n_parts ? part_elems[q] : 0;
+        void* rows = const_cast<void*>(d_in[1]);
+        const int64_t cells = nb * problem_args_stride;
+        const unsigned grid = (unsigned)((cells + 255) / 256);
+        if (dtype == B200OPT_F64) pack_parts_kernel<double><<<grid, 256, 0, st>>>(static_cast<double*>(rows), problem_args_stride, nb, pp);
+        else pack_parts_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(rows), problem_args_stride, nb, pp);
+        if (check_cuda(cudaGetLastError(), "pack_parts_kernel launch")) return (int)B200OPT_ECUDA;
+        return (int)b200opt_root_find(solver, model_id, dtype, nb, n, d_in[0], d_shared, rows, problem_args_stride, nullptr, nullptr, opts,
+                                      d_out[0], static_cast<int32_t*>(d_out[1]), static_cast<int32_t*>(d_out[2]), st);
       });
 }
 

@@ -117,3 +117,23 @@ def test_newton_host_entry_point():
     host = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-8, 1e-8), w["y0"], (w["A"], w["B"], w["y_prev"], w["dt"]),
                           throw=False, chunk=200)
     assert np.array_equal(host.value, to_np(dev.value)) and np.array_equal(host.stats["num_steps"], to_np(dev.stats["num_steps"]))
+    # the Python entry point hands (y_prev, dt) to b200opt_root_find_host_parts; the packed-row entry point gives the same bits
+    import ctypes as C
+
+    from optimistix_b200 import _lib
+
+    lib = _lib.load()
+    n, B = 32, 777
+    rows = np.zeros((B, n + 2))
+    rows[:, :n], rows[:, n] = w["y_prev"], w["dt"]
+    shared = np.concatenate([w["A"].reshape(-1), w["B"].reshape(-1)])
+    y = np.empty((B, n))
+    steps, res = np.empty(B, np.int32), np.empty(B, np.int32)
+    opts = _lib.make_options(1e-8, 1e-8, "max", 256)
+    _lib.check(lib.b200opt_root_find_host(0, _lib.SOLVER_NEWTON, optx.models.implicit_euler.model_id, _lib.F64, B, n, w["y0"].ctypes.data,
+                                          shared.ctypes.data, shared.size, rows.ctypes.data, n + 2, C.byref(opts), y.ctypes.data,
+                                          steps.ctypes.data, res.ctypes.data, 300), "root_find_host")
+    assert np.array_equal(y, host.value) and np.array_equal(steps, host.stats["num_steps"]) and np.array_equal(res, host.result)
+    # single problem and a pageable chunk layout that does not divide the batch
+    one = optx.root_find(optx.models.implicit_euler, optx.Newton(1e-8, 1e-8), w["y0"][5], (w["A"], w["B"], w["y_prev"][5], w["dt"][5]), throw=False)
+    assert np.array_equal(one.value, host.value[5])
