@@ -93,33 +93,33 @@ template <typename T, int K> __device__ __forceinline__ void warp_allreduce_arra
   T* tot = sm + 32 * L::KP;
   // lanes 0-15 sum rows 0-15 of quad-column q, lanes 16-31 rows 16-31 of the same quad (a quarter-warp reads 8
   // consecutive quads of one row: conflict free); the halves meet through one xor-16 shuffle per element.
+  // (no divergence: lanes beyond the last quad column recompute that column - broadcast loads, nothing extra in shared memory -
+  //  and only the store is predicated; a branch around the block cost a reconvergence point per reduction)
   for (int qb = 0; qb < L::KQ; qb += 16) {
-    const int q = qb + (lane & 15), h = lane >> 4;
-    const bool on = q < L::KQ;
-    const unsigned mask = __ballot_sync(kFull, on);
-    if (on) {
-      T a[V];
+    const int q0 = qb + (lane & 15), h = lane >> 4;
+    const bool on = q0 < L::KQ;
+    const int q = on ? q0 : L::KQ - 1;
+    T a[V];
 #pragma unroll
-      for (int e = 0; e < V; ++e) a[e] = T(0);
+    for (int e = 0; e < V; ++e) a[e] = T(0);
 #pragma unroll
-      for (int l = 0; l < 16; ++l) {
-        const Vec w = *reinterpret_cast<const Vec*>(sm + (h * 16 + l) * L::KP + q * V);
-        const T* ww = reinterpret_cast<const T*>(&w);
+    for (int l = 0; l < 16; ++l) {
+      const Vec w = *reinterpret_cast<const Vec*>(sm + (h * 16 + l) * L::KP + q * V);
+      const T* ww = reinterpret_cast<const T*>(&w);
 #pragma unroll
-        for (int e = 0; e < V; ++e) a[e] += ww[e];
-      }
+      for (int e = 0; e < V; ++e) a[e] += ww[e];
+    }
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const T o = __shfl_xor_sync(mask, a[e], 16);
-        a[e] = (h == 0) ? a[e] + o : o + a[e];  // rows 0-15 first, then 16-31: same order in both halves
-      }
-      if (h == 0) {
-        Vec w;
-        T* ww = reinterpret_cast<T*>(&w);
+    for (int e = 0; e < V; ++e) {
+      const T o = __shfl_xor_sync(kFull, a[e], 16);
+      a[e] = (h == 0) ? a[e] + o : o + a[e];  // rows 0-15 first, then 16-31: same order in both halves
+    }
+    if (h == 0 && on) {
+      Vec w;
+      T* ww = reinterpret_cast<T*>(&w);
 #pragma unroll
-        for (int e = 0; e < V; ++e) ww[e] = a[e];
-        *reinterpret_cast<Vec*>(tot + q * V) = w;
-      }
+      for (int e = 0; e < V; ++e) ww[e] = a[e];
+      *reinterpret_cast<Vec*>(tot + q * V) = w;
     }
   }
   __syncwarp();
