@@ -40,7 +40,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #ifndef LSQ_P2_FAST
 #define LSQ_P2_FAST 3
 #endif
-// Round-2 latency / work trims (bit mask, A/B builds: tools/lm_variants.sh -DLSQ_P2_OPT=...; results are bit-identical to 0):
+// Round-2 latency / work trims (bit mask; A/B builds: tools/kernel_variants.sh lsq_gauss2 tag:"-DLSQ_P2_OPT=...", timed and
+// checked bit for bit against the baseline by tools/call_lm_ab.sh; results are bit-identical to 0; measurements: DESIGN.md 4.1b):
 //   1  the five butterfly rounds of the ||r||^2 reduction are interleaved with the rows of the predicted-reduction quadratic form
 //      (the reduction sits behind a divergence check = a basic-block boundary, so the assembler does not overlap them itself)
 //   2  Gram entries between parameters whose Jacobian column depends neither on y nor on the problem (PModel::NCONST trailing
